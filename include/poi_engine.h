@@ -1,0 +1,188 @@
+/*
+ * poi_engine.h -- C-ABI of the B200-native next-POI training engine.
+ *
+ * The reference (tangrizzly/Point-of-Interest-Recommendation) has no FFI: its
+ * seam is the Python model-class surface that prog_*.py calls, i.e. the objects
+ * that wrap `theano.function`.  Each entry point below
+ * names the compiled Theano function / shared-variable operation it replaces.
+ * The Python classes in point-of-interest-recommendation_b200/public/ bind these
+ * through ctypes (see INTEGRATION.md for the stub a reference maintainer adds).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (message: poi_last_error);
+ *     nothing throws across the ABI;
+ *   - "dev" pointers are device memory BORROWED from the caller (torch tensors on
+ *     the engine's device); the engine never frees them.  "host" pointers are
+ *     ordinary host memory.  No torch types appear in any signature;
+ *   - one engine per (process, GPU); not thread-safe; work is enqueued on the
+ *     engine's stream (poi_set_stream) and every train/predict call synchronises
+ *     before returning host scalars, like a theano.function call does;
+ *   - tables are fp32 row-major [(rows) x dim]; index matrices are int32
+ *     row-major [n_user x lmax] exactly as the reference's theano.shared int32
+ *     masks (GRU.py:50-55, GRU_Spatial.py:46-49); pad POI index = n_item, pad
+ *     interval index = n_dist;
+ *   - dim, n_hidden must be multiples of 4 (128-bit vector access).
+ */
+#ifndef POI_ENGINE_H_
+#define POI_ENGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct poi_engine poi_engine;
+
+/* ---- lifetime / plumbing --------------------------------------------------------------- */
+int         poi_engine_create(int device, poi_engine** out);
+void        poi_engine_destroy(poi_engine* e);
+const char* poi_last_error(poi_engine* e);          /* also valid with e == NULL (create errors) */
+int         poi_set_stream(poi_engine* e, void* cuda_stream);   /* cudaStream_t; NULL = default  */
+int         poi_sync(poi_engine* e);
+/* kernels launched by this engine since creation (bench.py's gpu_launches claim) */
+int         poi_launch_count(poi_engine* e, int64_t* out);
+/* time of the most recent train call's phases in ms (CUDA events on the engine stream):
+ * out[0]=whole call, [1]=index prep+sort, [2]=gather, [3]=forward GEMMs+recurrence,
+ * [4]=loss head, [5]=backward, [6]=weight grads + dense update, [7]=sparse row update */
+int         poi_last_phase_ms(poi_engine* e, float* out8);
+int         poi_enable_phase_timing(poi_engine* e, int on);
+/* 0 = SIMT fp32 FMA GEMMs, 1 = tcgen05 3xTF32 (fp32-faithful), 2 = tcgen05 1xTF32 */
+int         poi_set_gemm_mode(poi_engine* e, int mode);
+int         poi_get_gemm_mode(poi_engine* e, int* mode);
+
+/* ---- first-slice kernels, individually testable ------------ */
+
+/* out[i,:] = table[idx[i],:]   -- Theano AdvancedSubtensor1, e.g. `self.lt[pidxs]`
+ * (GRU.py:327, GRU_Spatial.py:144-146, BPR.py:207-208, PRME.py:178-180, GeoIE.py:143-145). */
+int poi_gather_rows(poi_engine* e, const float* table_dev, int64_t n_rows, int dim,
+                    const int32_t* idx_dev, int64_t n_idx, float* out_dev);
+
+/* Sorted unique of an int32 vector -- Theano `Unique(False,False,False)` (GRU.py:329-331,
+ * GRU_Spatial.py:149-153, GeoIE.py:147-153).  uniq_dev/count_dev need room for n entries;
+ * *n_unique_host receives the number of distinct values. */
+int poi_unique(poi_engine* e, const int32_t* idx_dev, int64_t n, int32_t key_bound,
+               int32_t* uniq_dev, int32_t* count_dev, int64_t* n_unique_host);
+
+/* table[U] -= alpha * (sum over duplicate occurrences of grad rows + lambda*count*table[U]),
+ * U = unique(idx) -- `T.set_subtensor(uiq_x, uiq_x - lr * T.grad(cost, self.lt)[uiq_pqs])`
+ * (GRU.py:372-373, GRU_Spatial.py:212-215, GeoIE.py:174-181); grad_dev is one row per
+ * occurrence [n x dim] (may be NULL = zero).  Summation order is fixed -> bit-reproducible. */
+int poi_scatter_sgd(poi_engine* e, float* table_dev, int64_t n_rows, int dim,
+                    const int32_t* idx_dev, int64_t n, const float* grad_dev,
+                    float alpha, float lambda);
+
+/* sum of squares of n floats, fp64 accumulation -- building block of `model.l2.eval()`
+ * (GRU.py:305-309, GRU_Spatial.py:83-88, BPR.py:195-198, PRME.py:166-169, GeoIE.py:92-98). */
+int poi_sumsq(poi_engine* e, const float* x_dev, int64_t n, double* out_host);
+
+/* ---- GRU family: OboGru / Gru / OboSpatialGru (Distance2Pre) --------------------------- */
+typedef struct {
+    float*   lt;        /* [(n_item+1) x d]   item table, last row = pad   (GRU.py:60,66)         */
+    int64_t  n_rows_lt; /* n_item + 1                                                             */
+    int32_t  d;         /* n_in                                                                   */
+    int32_t  H;         /* n_hidden                                                               */
+    float*   ui;        /* [3 x H x din], din = d (GRU.py:61) or 2d (GRU_Spatial.py:51)           */
+    float*   wh;        /* [3 x H x H]                                      (GRU.py:62)           */
+    float*   bi;        /* [3 x H]                                          (GRU.py:64)           */
+    /* Distance2Pre only (all NULL / 0 for the plain GRU): */
+    float*   di;        /* [(n_dist+1) x d]   interval table               (GRU_Spatial.py:57)   */
+    int32_t  n_rows_di; /* n_dist + 1                                                             */
+    float*   vs;        /* [(n_dist+1) x H]                                 (GRU_Spatial.py:60)   */
+    float*   bs;        /* [n_dist+1]                                       (GRU_Spatial.py:61)   */
+    float*   scal;      /* dev float[3] = {wd, loss_weight[0], loss_weight[1]} (GRU_Spatial.py:66-71) */
+} poi_gru_params;
+
+typedef struct {
+    const int32_t* p;    /* tra_buys_masks      [n_user x lmax]  (GRU.py:50)                      */
+    const int32_t* q;    /* tra_buys_neg_masks  [n_user x lmax]  (GRU.py:54)                      */
+    const int32_t* dp;   /* tra_dist_masks      (GRU_Spatial.py:47)   NULL for the plain GRU      */
+    const int32_t* dq;   /* tra_dist_neg_masks  (GRU_Spatial.py:49)   NULL for the plain GRU      */
+    const int32_t* lens; /* [n_user] = tra_masks.sum(1); masks are prefix masks (Load_Data_by_length.py:123) */
+    int32_t lmax;
+    int32_t n_user;
+} poi_seq_index;
+
+/* One `seq_train` call: OboGru.seq_train(uidx) (GRU.py:378-389) / Gru.seq_train(start_end)
+ * (GRU.py:481-498) when params->di == NULL; OboSpatialGru.seq_train(uidx)
+ * (GRU_Spatial.py:220-229,290-292) otherwise.  B users are one mini-batch step
+ * (B=1 = the reference's one-by-one semantics; B>1 for Distance2Pre = the mini-batch
+ * extension of SURVEY.md 3.6).  Index matrices are DEVICE resident (like theano.shared);
+ * uidx_host are the B row numbers (`givens`, GRU.py:382-385).  max_len_host = max lens
+ * over the batch.  Updates params in place.  out_host (double[5]):
+ *   plain GRU   : out[0] = -sum(loss)            (GRU.py:380,483)
+ *   Distance2Pre: out[0..4] = los, sur, upq, softmax(loss_weight)[0..1] (GRU_Spatial.py:222) */
+int poi_gru_train(poi_engine* e, const poi_gru_params* params, const poi_seq_index* index,
+                  const int32_t* uidx_host, int32_t B, int32_t max_len_host,
+                  float alpha, float lambda, double* out_host);
+
+/* Same step with the batch's index ROWS supplied from HOST memory ([B x lmax] each, pinned
+ * or pageable; dp/dq NULL for the plain GRU): the host->device copies are part of the call.
+ * This is the end-to-end entry bench.py times (`e2e`). */
+int poi_gru_train_host_rows(poi_engine* e, const poi_gru_params* params,
+                            const int32_t* p_host, const int32_t* q_host,
+                            const int32_t* dp_host, const int32_t* dq_host,
+                            const int32_t* lens_host, int32_t B, int32_t lmax,
+                            float alpha, float lambda, double* out_host);
+
+/* `seq_predict(start_end)` (GRU.py:197-205, GRU_Spatial.py:282-288): forward over the padded
+ * training sequences using the trained_* copies passed in `params` (lt=trained_items,
+ * di=trained_dists).  hts_dev [B x H]; sts_dev [B x (n_dist+1)] or NULL for the plain GRU. */
+int poi_gru_predict(poi_engine* e, const poi_gru_params* params, const poi_seq_index* index,
+                    const int32_t* uidx_host, int32_t B, int32_t max_len_host,
+                    float* hts_dev, float* sts_dev);
+
+/* ---- BPR-MF: OboBpr.bpr_train (BPR.py:234-241) / Bpr.bpr_train (BPR.py:389-397) --------- */
+/* n sequential (u, p, q) SGD steps in the order given -- exactly n back-to-back
+ * `model.train(uidx, [p, q])` calls (prog_bpr_gru_spatial.py:240-244); per-occurrence
+ * gradient, last writer wins (BPR.py:228-230).  loss_host[n] = -log sigmoid(u_i). */
+int poi_bpr_train_seq(poi_engine* e, float* ux_dev, float* lt_dev, int32_t d,
+                      const int32_t* u_host, const int32_t* p_host, const int32_t* q_host,
+                      int64_t n, float alpha, float lambda, double* loss_host);
+/* one mini-batch step with duplicate-summed unique-row updates (Bpr, BPR.py:351-397) */
+int poi_bpr_train_batch(poi_engine* e, float* ux_dev, int64_t n_user, float* lt_dev,
+                        int64_t n_rows_lt, int32_t d,
+                        const int32_t* p_host, const int32_t* q_host, const int32_t* mask_host,
+                        const int32_t* u_host, int64_t n, float alpha, float lambda,
+                        double* loss_host);
+
+/* ---- PRME: OboPrme.prme_train (PRME.py:212-219) ----------------------------------------- */
+/* n sequential (u, [p, q, prev], dist_km, gap) ASCENT steps, = n back-to-back
+ * `model.train(uidx, [p, q, prev], dist, gap)` calls (prog_prme.py:191-197).
+ * loss_host[n] = log sigmoid(Dq - Dp). */
+int poi_prme_train_seq(poi_engine* e, float* du_dev, float* dp_dev, float* ds_dev, int32_t d,
+                       const int32_t* u_host, const int32_t* p_host, const int32_t* q_host,
+                       const int32_t* prev_host, const double* dist_host, const int32_t* gap_host,
+                       int64_t n, int32_t threshold, double component_weight,
+                       float alpha, float lambda, double* loss_host);
+
+/* ---- GeoIE: GeoIE.seq_train (GeoIE.py:185-194) ------------------------------------------ */
+typedef struct {
+    float*  g;  float* h;  float* z;   /* [(n_item+1) x H]  (GeoIE.py:65-72) */
+    float*  t;                         /* [n_user x H]                        */
+    double* ab;                        /* dev double[2] = {a, b}  (GeoIE.py:74-78) */
+    int64_t n_rows;                    /* n_item + 1 */
+    int32_t H;
+} poi_geoie_params;
+/* p_row_host/q_row_host: the user's rows of tra_buys_masks / tra_buys_neg_masks [lmax];
+ * dist_pos/dist_neg (float) and msk (int32) are the (n x n) host matrices the driver
+ * passes (prog_geoie.py:179-183).  out_host[0] = sum log sigmoid(sp - sq). */
+int poi_geoie_train(poi_engine* e, const poi_geoie_params* params, int32_t uidx,
+                    const int32_t* p_row_host, const int32_t* q_row_host, int32_t lmax,
+                    const float* dist_pos_host, const float* dist_neg_host,
+                    const int32_t* msk_host, int32_t n, float alpha, float lambda,
+                    double* out_host);
+
+/* ---- evaluation helpers (scoring + top-K) ---------------------------- */
+/* scores[b, i] = users[b,:] . items[i,:] (+ wd * prob[b, i] if prob_dev != NULL), then the
+ * indices of the top_k largest scores per row in descending order -- the product of
+ * compute_sub_all_scores (GRU.py:93-96, GRU_Spatial.py:117-125) fused with
+ * Valuate.py:91-100,133-146.  items excludes the pad row.  topk_dev [B x top_k] int32. */
+int poi_score_topk(poi_engine* e, const float* users_dev, int32_t B, const float* items_dev,
+                   int64_t n_item, int32_t H, const float* prob_dev, float wd,
+                   int32_t top_k, int32_t* topk_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POI_ENGINE_H_ */

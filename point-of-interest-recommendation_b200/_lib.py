@@ -1,0 +1,78 @@
+"""ctypes binding of libpoi_b200.so -- one prototype per symbol declared in include/poi_engine.h.
+
+There is no CPU fallback: if the shared library has not been built the import fails, and if no
+B200 is present ``poi_engine_create`` fails; both loudly.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpoi_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libpoi_b200.so is not built (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "from the repository root. There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+
+class PoiGruParams(Structure):
+    _fields_ = [("lt", c_void_p), ("n_rows_lt", c_int64), ("d", c_int32), ("H", c_int32),
+                ("ui", c_void_p), ("wh", c_void_p), ("bi", c_void_p),
+                ("di", c_void_p), ("n_rows_di", c_int32), ("vs", c_void_p), ("bs", c_void_p),
+                ("scal", c_void_p)]
+
+
+class PoiSeqIndex(Structure):
+    _fields_ = [("p", c_void_p), ("q", c_void_p), ("dp", c_void_p), ("dq", c_void_p),
+                ("lens", c_void_p), ("lmax", c_int32), ("n_user", c_int32)]
+
+
+class PoiGeoieParams(Structure):
+    _fields_ = [("g", c_void_p), ("h", c_void_p), ("z", c_void_p), ("t", c_void_p), ("ab", c_void_p),
+                ("n_rows", c_int64), ("H", c_int32)]
+
+
+_E = c_void_p
+_PROTOS = {
+    "poi_engine_create": (c_int, [c_int, POINTER(_E)]),
+    "poi_engine_destroy": (None, [_E]),
+    "poi_last_error": (c_char_p, [_E]),
+    "poi_set_stream": (c_int, [_E, c_void_p]),
+    "poi_sync": (c_int, [_E]),
+    "poi_launch_count": (c_int, [_E, POINTER(c_int64)]),
+    "poi_last_phase_ms": (c_int, [_E, POINTER(c_float)]),
+    "poi_enable_phase_timing": (c_int, [_E, c_int]),
+    "poi_set_gemm_mode": (c_int, [_E, c_int]),
+    "poi_get_gemm_mode": (c_int, [_E, POINTER(c_int)]),
+    "poi_gather_rows": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "poi_unique": (c_int, [_E, c_void_p, c_int64, c_int32, c_void_p, c_void_p, POINTER(c_int64)]),
+    "poi_scatter_sgd": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_float]),
+    "poi_sumsq": (c_int, [_E, c_void_p, c_int64, POINTER(c_double)]),
+    "poi_gru_train": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32,
+                              c_float, c_float, POINTER(c_double)]),
+    "poi_gru_train_host_rows": (c_int, [_E, POINTER(PoiGruParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int32, c_int32, c_float, c_float, POINTER(c_double)]),
+    "poi_gru_predict": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32,
+                                c_void_p, c_void_p]),
+    "poi_bpr_train_seq": (c_int, [_E, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_float, c_float, c_void_p]),
+    "poi_bpr_train_batch": (c_int, [_E, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int64, c_float, c_float, POINTER(c_double)]),
+    "poi_prme_train_seq": (c_int, [_E, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_float, c_float,
+                                   c_void_p]),
+    "poi_geoie_train": (c_int, [_E, POINTER(PoiGeoieParams), c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                c_void_p, c_void_p, c_int32, c_float, c_float, POINTER(c_double)]),
+    "poi_score_topk": (c_int, [_E, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_float, c_int32,
+                               c_void_p]),
+}
+
+EXPORTED = sorted(_PROTOS)
+
+for _name, (_res, _args) in _PROTOS.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header and library out of sync
+    _fn.restype = _res
+    _fn.argtypes = _args

@@ -1,0 +1,163 @@
+// common.cuh -- engine object, workspace arena, launch accounting, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/poi_engine.h"
+
+#define POI_WARP 32
+
+struct PoiChunk { char* ptr; size_t cap; };
+
+struct poi_engine {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int gemm_mode = 0;
+    // bump arena (device scratch owned by the engine); reset at the start of every call
+    std::vector<PoiChunk> chunks;
+    size_t cur_chunk = 0, cur_off = 0, high_water = 0, call_bytes = 0;
+    // pinned host staging
+    double*  h_out = nullptr;        // 64 doubles
+    char*    h_stage = nullptr;      // pinned staging for small host->device index uploads
+    size_t   h_stage_cap = 0;
+    // phase timing
+    bool timing = false;
+    cudaEvent_t ev[9] = {};
+    float phase_ms[8] = {};
+};
+
+static thread_local std::string g_create_err;
+
+#define POI_FAIL(e, ...)                                                         \
+    do {                                                                         \
+        char _b[512];                                                            \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                                   \
+        (e)->err = std::string(_b) + " [" + __FILE__ + ":" + std::to_string(__LINE__) + "]"; \
+        return -1;                                                               \
+    } while (0)
+
+#define POI_CK(e, call)                                                          \
+    do {                                                                         \
+        cudaError_t _s = (call);                                                 \
+        if (_s != cudaSuccess) POI_FAIL(e, "CUDA error %s: %s", #call, cudaGetErrorString(_s)); \
+    } while (0)
+
+#define POI_TRY(call)                                                            \
+    do {                                                                         \
+        int _r = (call);                                                         \
+        if (_r != 0) return _r;                                                  \
+    } while (0)
+
+// every kernel launch goes through here so that poi_launch_count is exact
+#define POI_LAUNCH(e, kern, grid, block, smem, ...)                              \
+    do {                                                                         \
+        kern<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);             \
+        (e)->launches++;                                                         \
+        cudaError_t _s = cudaPeekAtLastError();                                  \
+        if (_s != cudaSuccess) POI_FAIL(e, "launch %s failed: %s", #kern, cudaGetErrorString(_s)); \
+    } while (0)
+
+static inline size_t poi_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t poi_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// arena: bump allocation out of a list of cudaMalloc'ed chunks.  When a call needed more than
+// one chunk, the next reset consolidates into a single chunk of the high-water size, so the
+// steady state is allocation-free.
+// ---------------------------------------------------------------------------------------------
+static int arena_reset(poi_engine* e) {
+    if (e->chunks.size() > 1) {
+        POI_CK(e, cudaStreamSynchronize(e->stream));
+        size_t total = 0;
+        for (auto& c : e->chunks) { total += c.cap; cudaFree(c.ptr); }
+        e->chunks.clear();
+        total = poi_align_up(std::max(total, e->high_water) + (total >> 3), (size_t)1 << 20);
+        char* p = nullptr;
+        POI_CK(e, cudaMalloc(&p, total));
+        e->chunks.push_back({p, total});
+    }
+    e->cur_chunk = 0; e->cur_off = 0; e->call_bytes = 0;
+    return 0;
+}
+
+static int arena_alloc(poi_engine* e, size_t bytes, void** out) {
+    bytes = poi_align_up(std::max<size_t>(bytes, 16), 256);
+    while (true) {
+        if (e->cur_chunk < e->chunks.size()) {
+            PoiChunk& c = e->chunks[e->cur_chunk];
+            if (e->cur_off + bytes <= c.cap) {
+                *out = c.ptr + e->cur_off;
+                e->cur_off += bytes;
+                e->call_bytes += bytes;
+                e->high_water = std::max(e->high_water, e->call_bytes);
+                return 0;
+            }
+            e->cur_chunk++; e->cur_off = 0;
+            continue;
+        }
+        size_t cap = poi_align_up(std::max(bytes, (size_t)64 << 20), (size_t)1 << 20);
+        char* p = nullptr;
+        POI_CK(e, cudaMalloc(&p, cap));
+        e->chunks.push_back({p, cap});
+    }
+}
+
+template <typename T>
+static int arena_get(poi_engine* e, size_t n, T** out) {
+    void* p = nullptr;
+    POI_TRY(arena_alloc(e, n * sizeof(T), &p));
+    *out = reinterpret_cast<T*>(p);
+    return 0;
+}
+
+static int stage_reserve(poi_engine* e, size_t bytes) {
+    if (bytes <= e->h_stage_cap) return 0;
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    e->h_stage = nullptr; e->h_stage_cap = 0;
+    size_t cap = poi_align_up(bytes + (bytes >> 2), 4096);
+    POI_CK(e, cudaMallocHost((void**)&e->h_stage, cap));
+    e->h_stage_cap = cap;
+    return 0;
+}
+
+static inline void phase_mark(poi_engine* e, int i) {
+    if (e->timing) cudaEventRecord(e->ev[i], e->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// log(sigmoid(x)) = -softplus(-x), the form Theano rewrites to
+__device__ __forceinline__ float logsigmoidf_(float x) {
+    return -(fmaxf(-x, 0.0f) + log1pf(expf(-fabsf(x))));
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4fma(float s, float4 a, float4 c) { return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w)); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }

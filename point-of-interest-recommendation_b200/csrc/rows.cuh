@@ -1,0 +1,253 @@
+// rows.cuh -- the HBM-bound row kernels: embedding gather, sparse row SGD (segment gather-reduce),
+// streaming sum of squares.  All accesses are 128-bit and coalesced along the row.
+#pragma once
+#include "common.cuh"
+#include "sort.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// gather: out[i,:] = table[idx[i],:]           (AdvancedSubtensor1; GRU.py:327 etc.)
+// LPR lanes cooperate on one row (LPR*16 B per access); each lane group keeps UNR rows in flight.
+// ---------------------------------------------------------------------------------------------
+template <int LPR, int UNR>
+__global__ void __launch_bounds__(256)
+k_gather_rows(const float* __restrict__ table, int dim4, const int32_t* __restrict__ idx,
+              int64_t n_idx, float* __restrict__ out) {
+    const int lane = threadIdx.x % LPR;
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LPR;
+    const float4* tab4 = reinterpret_cast<const float4*>(table);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    for (int64_t r0 = group * UNR; r0 < n_idx; r0 += n_groups * UNR) {
+        int64_t src[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) src[u] = (r0 + u < n_idx) ? (int64_t)idx[r0 + u] : -1;
+        for (int c = lane; c < dim4; c += LPR) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (src[u] >= 0) v[u] = __ldg(tab4 + src[u] * dim4 + c);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (src[u] >= 0) __stcs(out4 + (r0 + u) * dim4 + c, v[u]);
+        }
+    }
+}
+
+static int launch_gather_rows(poi_engine* e, const float* table, int dim, const int32_t* idx,
+                              int64_t n_idx, float* out) {
+    if (n_idx <= 0) return 0;
+    const int dim4 = dim / 4;
+    const int UNR = 4;
+    int lpr = dim4 <= 8 ? 8 : (dim4 <= 16 ? 16 : 32);
+    int64_t groups_needed = poi_cdiv(n_idx, UNR);
+    int64_t threads_needed = groups_needed * lpr;
+    unsigned grid = (unsigned)std::min<int64_t>(poi_cdiv(threads_needed, 256), (int64_t)e->num_sms * 16);
+    grid = std::max(grid, 1u);
+    if (lpr == 8)       POI_LAUNCH(e, (k_gather_rows<8, 4>), grid, 256, 0, table, dim4, idx, n_idx, out);
+    else if (lpr == 16) POI_LAUNCH(e, (k_gather_rows<16, 4>), grid, 256, 0, table, dim4, idx, n_idx, out);
+    else                POI_LAUNCH(e, (k_gather_rows<32, 4>), grid, 256, 0, table, dim4, idx, n_idx, out);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sum of squares, fp64 accumulation, fixed-order two-stage reduction   (model.l2.eval())
+// ---------------------------------------------------------------------------------------------
+constexpr int SUMSQ_BLOCKS_PER_SM = 8;
+
+__global__ void __launch_bounds__(256)
+k_sumsq_partial(const float* __restrict__ x, int64_t n, double* __restrict__ part) {
+    __shared__ double sh[8];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    double acc = 0.0;
+    for (int64_t i = tid; i < n4; i += nth) {
+        float4 v = __ldcs(x4 + i);
+        float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        acc += (double)s;
+    }
+    if (tid == 0) for (int64_t i = n4 * 4; i < n; ++i) acc += (double)x[i] * (double)x[i];
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void k_sum_partials_d(const double* __restrict__ part, int n, double* out, int out_stride, int ncols) {
+    // one thread per column, sequential over partial rows: fixed order, deterministic
+    int c = threadIdx.x;
+    if (c < ncols) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += part[(size_t)i * ncols + c];
+        out[c * out_stride] = t;
+    }
+}
+
+static int launch_sumsq(poi_engine* e, const float* x, int64_t n, double* out_dev) {
+    int blocks = (int)std::min<int64_t>(std::max<int64_t>(poi_cdiv(n / 4 + 1, 256), 1), (int64_t)e->num_sms * SUMSQ_BLOCKS_PER_SM);
+    double* part = nullptr;
+    POI_TRY(arena_get(e, (size_t)blocks, &part));
+    POI_LAUNCH(e, k_sumsq_partial, blocks, 256, 0, x, n, part);
+    POI_LAUNCH(e, k_sum_partials_d, 1, 32, 0, part, blocks, out_dev, 1, 1);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sparse row SGD by segment gather-reduce
+//
+//   table[r] <- table[r] - alpha * ( sum_{occ in seg(r)} grad(occ) + lambda * count(r) * table[r] )
+//
+// = `T.set_subtensor(uiq_x, uiq_x - lr * T.grad(cost, self.lt)[uiq_pqs])` (GRU.py:372-373,
+// GRU_Spatial.py:212-215): the dense Theano gradient sums every duplicate occurrence, and the L2
+// term of the cost counts every gathered row (padding included, GRU.py:365).  Here the dense
+// (n_item+1) x d gradient is never materialised: each unique row walks its own occurrence list
+// (ascending occurrence id = fixed summation order, no atomics, bit-reproducible).
+//
+// The per-occurrence gradient is described by up to two (row pointer, scale) pairs.
+// ---------------------------------------------------------------------------------------------
+enum RowSrcMode { SRC_DENSE_GRADS = 0, SRC_GRU_LT = 1, SRC_GRU_DI = 2, SRC_NONE = 3 };
+
+struct RowSrc {
+    int mode;
+    // SRC_DENSE_GRADS: grad rows [n x dim]
+    const float* grads;
+    // SRC_GRU_*: DX [T*B x ldx] (cols [0,d) -> lt, [d,2d) -> di), Hc [T*B x d], e [T*B]
+    const float* DX; int ldx; const float* Hc; const float* ev;
+    int B; int T; int64_t LB;   // LB = lmax * B  (p occurrences [0,LB), q occurrences [LB,2LB))
+    int dim;
+};
+
+struct OccPair { const float* p1; const float* p2; float s2; };
+
+__device__ __forceinline__ OccPair occ_begin(const RowSrc& s, uint32_t occ) {
+    OccPair o; o.p1 = nullptr; o.p2 = nullptr; o.s2 = 0.f;
+    if (s.mode == SRC_DENSE_GRADS) {
+        if (s.grads) o.p1 = s.grads + (size_t)occ * s.dim;
+    } else if (s.mode == SRC_GRU_LT) {
+        bool isq = occ >= (uint64_t)s.LB;
+        int64_t m = isq ? (int64_t)occ - s.LB : (int64_t)occ;     // m = t*B + b
+        int64_t TB = (int64_t)s.T * s.B;
+        if (!isq && m < TB) o.p1 = s.DX + (size_t)m * s.ldx;      // d cost / d x_t, t < T
+        if (m >= s.B && m < TB + s.B) {                           // 1 <= t <= T: pair j = t-1
+            int64_t mm = m - s.B;
+            float ev = s.ev[mm];
+            if (ev != 0.f) { o.p2 = s.Hc + (size_t)mm * s.dim; o.s2 = isq ? -ev : ev; }
+        }
+    } else if (s.mode == SRC_GRU_DI) {
+        int64_t TB = (int64_t)s.T * s.B;
+        if ((int64_t)occ < TB) o.p1 = s.DX + (size_t)occ * s.ldx + s.dim;
+    }
+    return o;
+}
+
+constexpr int ROW_LONG_THRESH = 96;
+
+// NCH float4 chunks per lane: dim <= 128*NCH
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_rows_update_warp(SegList seg, float* __restrict__ table, int dim4, float alpha, float lambda,
+                   RowSrc src, int long_thresh, uint32_t* long_list, uint32_t* long_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t nu = *seg.n_unique;
+    for (int64_t sg = warp; sg < nu; sg += nwarps) {
+        const uint32_t s0 = seg.seg_start[sg], s1 = seg.seg_start[sg + 1];
+        const uint32_t cnt = s1 - s0;
+        if ((int)cnt > long_thresh) {
+            if (lane == 0) { uint32_t pos = atomicAdd(long_count, 1u); long_list[pos] = (uint32_t)sg; }
+            continue;
+        }
+        float4 acc[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) acc[k] = f4zero();
+        for (uint32_t i = s0; i < s1; ++i) {
+            OccPair o = occ_begin(src, seg.vals[i]);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                int c = lane + 32 * k;
+                if (c < dim4) {
+                    if (o.p1) acc[k] = f4add(acc[k], ld4(o.p1 + 4 * c));
+                    if (o.p2) acc[k] = f4fma(o.s2, ld4(o.p2 + 4 * c), acc[k]);
+                }
+            }
+        }
+        float* row = table + (size_t)seg.uniq[sg] * dim4 * 4;
+        const float lc = lambda * (float)cnt;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            int c = lane + 32 * k;
+            if (c < dim4) {
+                float4 r = ld4(row + 4 * c);
+                r.x -= alpha * (acc[k].x + lc * r.x); r.y -= alpha * (acc[k].y + lc * r.y);
+                r.z -= alpha * (acc[k].z + lc * r.z); r.w -= alpha * (acc[k].w + lc * r.w);
+                st4(row + 4 * c, r);
+            }
+        }
+    }
+}
+
+// long segments: one CTA per listed segment; warp w sums occurrences s0+w, s0+w+8, ...;
+// the 8 partial rows are then added in warp order.  Fixed order -> deterministic.
+__global__ void __launch_bounds__(256)
+k_rows_update_long(SegList seg, float* __restrict__ table, int dim4, float alpha, float lambda,
+                   RowSrc src, const uint32_t* long_list, const uint32_t* long_count) {
+    extern __shared__ float4 s_part[];          // [8][dim4]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t nl = *long_count;
+    for (uint32_t li = blockIdx.x; li < nl; li += gridDim.x) {
+        const uint32_t sg = long_list[li];
+        const uint32_t s0 = seg.seg_start[sg], s1 = seg.seg_start[sg + 1];
+        for (int c0 = 0; c0 < dim4; c0 += 32) {
+            int c = c0 + lane;
+            float4 acc = f4zero();
+            for (uint32_t i = s0 + w; i < s1; i += 8) {
+                OccPair o = occ_begin(src, seg.vals[i]);
+                if (c < dim4) {
+                    if (o.p1) acc = f4add(acc, ld4(o.p1 + 4 * c));
+                    if (o.p2) acc = f4fma(o.s2, ld4(o.p2 + 4 * c), acc);
+                }
+            }
+            if (c < dim4) s_part[w * dim4 + c] = acc;
+        }
+        __syncthreads();
+        float* row = table + (size_t)seg.uniq[sg] * dim4 * 4;
+        const float lc = lambda * (float)(s1 - s0);
+        for (int c = threadIdx.x; c < dim4; c += blockDim.x) {
+            float4 a = s_part[c];
+#pragma unroll
+            for (int ww = 1; ww < 8; ++ww) a = f4add(a, s_part[ww * dim4 + c]);
+            float4 r = ld4(row + 4 * c);
+            r.x -= alpha * (a.x + lc * r.x); r.y -= alpha * (a.y + lc * r.y);
+            r.z -= alpha * (a.z + lc * r.z); r.w -= alpha * (a.w + lc * r.w);
+            st4(row + 4 * c, r);
+        }
+        __syncthreads();
+    }
+}
+
+static int launch_rows_update(poi_engine* e, const SegList& seg, float* table, int dim,
+                              float alpha, float lambda, const RowSrc& src, int long_thresh) {
+    if (seg.n <= 0) return 0;
+    const int dim4 = dim / 4;
+    uint32_t *long_list = nullptr, *long_count = nullptr;
+    POI_TRY(arena_get(e, (size_t)seg.n, &long_list));
+    POI_TRY(arena_get(e, 4, &long_count));
+    POI_CK(e, cudaMemsetAsync(long_count, 0, 4, e->stream));
+    int64_t warps = std::min<int64_t>(seg.n, (int64_t)e->num_sms * 64);
+    unsigned grid = (unsigned)std::max<int64_t>(poi_cdiv(warps * 32, 256), 1);
+    if (dim4 <= 32)       POI_LAUNCH(e, (k_rows_update_warp<1>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
+    else if (dim4 <= 64)  POI_LAUNCH(e, (k_rows_update_warp<2>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
+    else if (dim4 <= 128) POI_LAUNCH(e, (k_rows_update_warp<4>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
+    else if (dim4 <= 256) POI_LAUNCH(e, (k_rows_update_warp<8>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
+    else POI_FAIL(e, "row dim %d too large (max 1024)", dim);
+    size_t smem = (size_t)8 * dim4 * sizeof(float4);
+    unsigned lgrid = (unsigned)std::min<int64_t>(seg.n, (int64_t)e->num_sms * 4);
+    POI_LAUNCH(e, k_rows_update_long, lgrid, 256, smem, seg, table, dim4, alpha, lambda, src, long_list, long_count);
+    return 0;
+}

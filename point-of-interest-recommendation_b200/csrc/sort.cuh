@@ -1,0 +1,275 @@
+// sort.cuh -- the integer side of the hot path: stable radix sort of (row index, occurrence id)
+// pairs, exclusive scan, and segment (= sorted-unique) construction.  This replaces Theano's
+// `Unique(False,False,False)` (GRU.py:329-331, GRU_Spatial.py:149-153, GeoIE.py:147-153) and,
+// because the sort keeps every occurrence, also gives the duplicate lists the sparse update
+// needs in order to sum gradients in a fixed order.  All results are bit-exact integers.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan (uint32), multi-level
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_block(const uint32_t* in, uint32_t* out, uint32_t* block_sums, int64_t n) {
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + i;
+        v[i] = idx < n ? in[idx] : 0u;
+        sum += v[i];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t s = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += s;
+        }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t;
+        if (lane == SCAN_THREADS / 32 - 1) block_sums[blockIdx.x] = ti;
+    }
+    __syncthreads();
+    uint32_t excl = warp_tot[wid] + inc - sum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + i;
+        if (idx < n) out[idx] = excl;
+        excl += v[i];
+    }
+}
+
+__global__ void k_scan_add(uint32_t* out, const uint32_t* block_off, int64_t n) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) out[idx] += block_off[idx / SCAN_TILE];
+}
+
+// out may alias in.  total_dev (optional) receives the sum of all elements.
+static int exclusive_scan_u32(poi_engine* e, const uint32_t* in, uint32_t* out, int64_t n,
+                              uint32_t* total_dev) {
+    if (n <= 0) {
+        if (total_dev) POI_CK(e, cudaMemsetAsync(total_dev, 0, 4, e->stream));
+        return 0;
+    }
+    int64_t nb = poi_cdiv(n, SCAN_TILE);
+    uint32_t* bs = nullptr;
+    POI_TRY(arena_get(e, (size_t)nb + 1, &bs));
+    POI_LAUNCH(e, k_scan_block, (unsigned)nb, SCAN_THREADS, 0, in, out, bs, n);
+    if (nb > 1) {
+        POI_TRY(exclusive_scan_u32(e, bs, bs, nb, total_dev));
+        POI_LAUNCH(e, k_scan_add, (unsigned)poi_cdiv(n, 256), 256, 0, out, bs, n);
+    } else if (total_dev) {
+        POI_CK(e, cudaMemcpyAsync(total_dev, bs, 4, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small path: one CTA, bitonic sort of 64-bit (key<<32 | occurrence) composites in shared memory.
+// The occurrence id in the low word makes the order total, hence identical to a stable sort.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_SORT_MAX = 4096;
+
+__global__ void __launch_bounds__(1024)
+k_small_sort(const uint32_t* keys_in, int n, int np2, uint32_t* keys_out, uint32_t* vals_out) {
+    extern __shared__ unsigned long long s_comp[];
+    for (int i = threadIdx.x; i < np2; i += blockDim.x)
+        s_comp[i] = i < n ? (((unsigned long long)keys_in[i] << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    bool asc = (i & k) == 0;
+                    unsigned long long a = s_comp[i], b = s_comp[ixj];
+                    if ((a > b) == asc) { s_comp[i] = b; s_comp[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned long long c = s_comp[i];
+        keys_out[i] = (uint32_t)(c >> 32);
+        vals_out[i] = (uint32_t)(c & 0xffffffffu);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// large path: LSD radix sort, 8 bits per pass, stable
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_hist(const uint32_t* keys, int64_t n, int shift, uint32_t* hist, int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        int64_t idx = base + j * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// Warp w owns the RS_ITEMS consecutive 32-key chunks (w*RS_ITEMS + j); ranks are assigned in
+// index order inside a chunk (match_any + popc of lower lanes), chunk after chunk inside a warp,
+// warp after warp inside the CTA, CTA after CTA via the scanned histogram -> stable.
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_scatter(const uint32_t* keys_in, const uint32_t* vals_in, int64_t n, int shift,
+                const uint32_t* offs, int nblocks, uint32_t* keys_out, uint32_t* vals_out) {
+    __shared__ uint32_t wcount[RS_THREADS / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_ITEMS * 32;
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        int64_t idx = base + j * 32 + lane;
+        bool ok = idx < n;
+        key[j] = ok ? keys_in[idx] : 0u;
+        val[j] = ok ? (vals_in ? vals_in[idx] : (uint32_t)idx) : 0u;
+        uint32_t dig = ok ? ((key[j] >> shift) & 255u) : 0xffffffffu;
+        uint32_t peers = __match_any_sync(0xffffffffu, dig);
+        uint32_t before = 0;
+        if (ok) before = wcount[w][dig];
+        __syncwarp();
+        if (ok && (peers & lt_mask) == 0) wcount[w][dig] = before + __popc(peers);
+        __syncwarp();
+        rank[j] = before + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    {   // thread == digit: turn per-warp counts into per-warp bases (global offset included)
+        uint32_t run = offs[(size_t)tid * nblocks + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_THREADS / 32; ++ww) {
+            uint32_t c = wcount[ww][tid];
+            wcount[ww][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        int64_t idx = base + j * 32 + lane;
+        if (idx < n) {
+            uint32_t dig = (key[j] >> shift) & 255u;
+            uint32_t pos = wcount[w][dig] + rank[j];
+            keys_out[pos] = key[j];
+            vals_out[pos] = val[j];
+        }
+    }
+}
+
+// Sort (key, occurrence-id) pairs by key, stable.  keys < bound.  Outputs live in the arena.
+static int sort_pairs(poi_engine* e, const uint32_t* keys_in, int64_t n, uint32_t bound,
+                      uint32_t** keys_sorted, uint32_t** vals_sorted) {
+    uint32_t *k0 = nullptr, *v0 = nullptr;
+    POI_TRY(arena_get(e, (size_t)std::max<int64_t>(n, 1), &k0));
+    POI_TRY(arena_get(e, (size_t)std::max<int64_t>(n, 1), &v0));
+    *keys_sorted = k0; *vals_sorted = v0;
+    if (n <= 0) return 0;
+    if (n <= SMALL_SORT_MAX) {
+        int np2 = 32;
+        while (np2 < n) np2 <<= 1;
+        int threads = std::min(1024, std::max(32, np2 / 2));
+        POI_LAUNCH(e, k_small_sort, 1, threads, (size_t)np2 * 8, keys_in, (int)n, np2, k0, v0);
+        return 0;
+    }
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)bound) ++bits;
+    int passes = (bits + 7) / 8;
+    uint32_t *k1 = nullptr, *v1 = nullptr, *hist = nullptr;
+    int nblocks = (int)poi_cdiv(n, RS_TILE);
+    if (passes > 1) {
+        POI_TRY(arena_get(e, (size_t)n, &k1));
+        POI_TRY(arena_get(e, (size_t)n, &v1));
+    }
+    POI_TRY(arena_get(e, (size_t)256 * nblocks, &hist));
+    // ping-pong so that the final pass lands in (k0, v0)
+    const uint32_t* ck = keys_in; const uint32_t* cv = nullptr;
+    for (int p = 0; p < passes; ++p) {
+        bool to0 = ((passes - 1 - p) % 2) == 0;
+        uint32_t* ok = to0 ? k0 : k1; uint32_t* ov = to0 ? v0 : v1;
+        POI_LAUNCH(e, k_radix_hist, nblocks, RS_THREADS, 0, ck, n, p * 8, hist, nblocks);
+        POI_TRY(exclusive_scan_u32(e, hist, hist, (int64_t)256 * nblocks, nullptr));
+        POI_LAUNCH(e, k_radix_scatter, nblocks, RS_THREADS, 0, ck, cv, n, p * 8, hist, nblocks, ok, ov);
+        ck = ok; cv = ov;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// segments = runs of equal keys in the sorted order
+// ---------------------------------------------------------------------------------------------
+struct SegList {
+    uint32_t* keys = nullptr;       // sorted keys              [n]
+    uint32_t* vals = nullptr;       // occurrence ids, ascending inside a segment [n]
+    uint32_t* seg_start = nullptr;  // [n_unique + 1]
+    uint32_t* uniq = nullptr;       // sorted unique keys       [n_unique]
+    uint32_t* n_unique = nullptr;   // device scalar
+    uint32_t* seg_of_occ = nullptr; // optional inverse map occurrence -> segment [n]
+    int64_t n = 0;
+};
+
+__global__ void k_seg_flags(const uint32_t* keys, int64_t n, uint32_t* flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void k_seg_write(const uint32_t* keys, const uint32_t* vals, const uint32_t* excl, int64_t n,
+                            uint32_t* seg_start, uint32_t* uniq, uint32_t* n_unique,
+                            uint32_t* seg_of_occ) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool head = (i == 0 || keys[i] != keys[i - 1]);
+    uint32_t sid = head ? excl[i] : excl[i] - 1u;
+    if (head) { seg_start[sid] = (uint32_t)i; uniq[sid] = keys[i]; }
+    if (seg_of_occ) seg_of_occ[vals[i]] = sid;
+    if (i == n - 1) { uint32_t nu = sid + 1u; *n_unique = nu; seg_start[nu] = (uint32_t)n; }
+}
+
+static int build_segments(poi_engine* e, const uint32_t* keys_dev, int64_t n, uint32_t bound,
+                          bool want_inverse, SegList* out) {
+    out->n = n;
+    POI_TRY(sort_pairs(e, keys_dev, n, bound, &out->keys, &out->vals));
+    uint32_t* excl = nullptr;
+    size_t nn = (size_t)std::max<int64_t>(n, 1);
+    POI_TRY(arena_get(e, nn, &excl));
+    POI_TRY(arena_get(e, nn + 1, &out->seg_start));
+    POI_TRY(arena_get(e, nn, &out->uniq));
+    POI_TRY(arena_get(e, 4, &out->n_unique));
+    out->seg_of_occ = nullptr;
+    if (want_inverse) POI_TRY(arena_get(e, nn, &out->seg_of_occ));
+    if (n <= 0) { POI_CK(e, cudaMemsetAsync(out->n_unique, 0, 4, e->stream)); return 0; }
+    unsigned g = (unsigned)poi_cdiv(n, 256);
+    POI_LAUNCH(e, k_seg_flags, g, 256, 0, out->keys, n, excl);
+    POI_TRY(exclusive_scan_u32(e, excl, excl, n, nullptr));
+    POI_LAUNCH(e, k_seg_write, g, 256, 0, out->keys, out->vals, excl, n, out->seg_start, out->uniq,
+               out->n_unique, out->seg_of_occ);
+    return 0;
+}

@@ -1,0 +1,237 @@
+"""Thin Python face of the C-ABI: turns torch CUDA tensors into raw device pointers and numpy
+arrays into host pointers.  PyTorch is only the device-memory container here; every kernel that
+runs is in libpoi_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_float, c_int, c_int64
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PoiGeoieParams, PoiGruParams, PoiSeqIndex, lib
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> int:
+    if t is None:
+        return 0
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous float32 CUDA tensor" % name)
+    return t.data_ptr()
+
+
+def _dev_i32(t: torch.Tensor, name: str) -> int:
+    if t is None:
+        return 0
+    if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous int32 CUDA tensor" % name)
+    return t.data_ptr()
+
+
+def _host_i32(a, name: str) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a
+
+
+class Engine:
+    """One engine per (process, GPU)."""
+
+    _instances = {}
+
+    def __init__(self, device: int | None = None):
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        rc = lib.poi_engine_create(self.device, byref(h))
+        if rc != 0:
+            raise EngineError("poi_engine_create failed (%d): %s -- the B200 CUDA path is the only path; "
+                              "there is no CPU fallback" % (rc, lib.poi_last_error(None).decode()))
+        self._h = h
+        self.torch_device = torch.device("cuda", self.device)
+
+    @classmethod
+    def get(cls, device: int | None = None) -> "Engine":
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if device not in cls._instances:
+            cls._instances[device] = Engine(device)
+        return cls._instances[device]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.poi_engine_destroy(self._h)
+            self._h = None
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise EngineError(lib.poi_last_error(self._h).decode())
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def set_stream(self, stream: torch.cuda.Stream | None):
+        self._ck(lib.poi_set_stream(self._h, stream.cuda_stream if stream is not None else 0))
+
+    def sync(self):
+        self._ck(lib.poi_sync(self._h))
+
+    def launch_count(self) -> int:
+        n = c_int64()
+        self._ck(lib.poi_launch_count(self._h, byref(n)))
+        return n.value
+
+    def enable_phase_timing(self, on: bool):
+        self._ck(lib.poi_enable_phase_timing(self._h, 1 if on else 0))
+
+    def last_phase_ms(self):
+        buf = (c_float * 8)()
+        self._ck(lib.poi_last_phase_ms(self._h, buf))
+        return list(buf)
+
+    def set_gemm_mode(self, mode: int):
+        self._ck(lib.poi_set_gemm_mode(self._h, int(mode)))
+
+    def get_gemm_mode(self) -> int:
+        m = c_int()
+        self._ck(lib.poi_get_gemm_mode(self._h, byref(m)))
+        return m.value
+
+    # ---- first-slice kernels ----------------------------------------------------------------
+    def gather_rows(self, table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None):
+        n = idx.numel()
+        if out is None:
+            out = torch.empty((n, table.shape[1]), dtype=torch.float32, device=table.device)
+        self._ck(lib.poi_gather_rows(self._h, _dev_f32(table, "table"), table.shape[0], table.shape[1],
+                                     _dev_i32(idx, "idx"), n, _dev_f32(out, "out")))
+        return out
+
+    def unique(self, idx: torch.Tensor, key_bound: int):
+        n = idx.numel()
+        uq = torch.empty(max(n, 1), dtype=torch.int32, device=idx.device)
+        cnt = torch.empty(max(n, 1), dtype=torch.int32, device=idx.device)
+        nu = c_int64()
+        self._ck(lib.poi_unique(self._h, _dev_i32(idx, "idx"), n, int(key_bound), uq.data_ptr(), cnt.data_ptr(), byref(nu)))
+        return uq[: nu.value], cnt[: nu.value]
+
+    def scatter_sgd(self, table: torch.Tensor, idx: torch.Tensor, grad: torch.Tensor | None, alpha: float, lam: float):
+        self._ck(lib.poi_scatter_sgd(self._h, _dev_f32(table, "table"), table.shape[0], table.shape[1],
+                                     _dev_i32(idx, "idx"), idx.numel(), _dev_f32(grad, "grad"), alpha, lam))
+
+    def sumsq(self, x: torch.Tensor) -> float:
+        out = c_double()
+        self._ck(lib.poi_sumsq(self._h, _dev_f32(x, "x"), x.numel(), byref(out)))
+        return out.value
+
+    # ---- GRU family -------------------------------------------------------------------------
+    @staticmethod
+    def gru_params(lt, ui, wh, bi, di=None, vs=None, bs=None, scal=None) -> PoiGruParams:
+        p = PoiGruParams()
+        p.lt = _dev_f32(lt, "lt"); p.n_rows_lt = lt.shape[0]; p.d = lt.shape[1]; p.H = wh.shape[1]
+        p.ui = _dev_f32(ui, "ui"); p.wh = _dev_f32(wh, "wh"); p.bi = _dev_f32(bi, "bi")
+        if di is not None:
+            p.di = _dev_f32(di, "di"); p.n_rows_di = di.shape[0]
+            p.vs = _dev_f32(vs, "vs"); p.bs = _dev_f32(bs, "bs"); p.scal = _dev_f32(scal, "scal")
+        else:
+            p.di = 0; p.n_rows_di = 0; p.vs = 0; p.bs = 0; p.scal = 0
+        return p
+
+    @staticmethod
+    def seq_index(p, q, lens, dp=None, dq=None) -> PoiSeqIndex:
+        ix = PoiSeqIndex()
+        ix.p = _dev_i32(p, "p"); ix.q = _dev_i32(q, "q"); ix.lens = _dev_i32(lens, "lens")
+        ix.dp = _dev_i32(dp, "dp"); ix.dq = _dev_i32(dq, "dq")
+        ix.n_user, ix.lmax = p.shape
+        return ix
+
+    def gru_train(self, params: PoiGruParams, index: PoiSeqIndex, uidx, max_len: int, alpha: float, lam: float):
+        uidx = _host_i32(uidx, "uidx").reshape(-1)
+        out = (c_double * 5)()
+        self._ck(lib.poi_gru_train(self._h, byref(params), byref(index), uidx.ctypes.data, uidx.size, int(max_len),
+                                   alpha, lam, out))
+        return list(out)
+
+    def gru_train_host_rows(self, params: PoiGruParams, p, q, lens, alpha: float, lam: float, dp=None, dq=None):
+        """p, q, dp, dq: host int32 [B, lmax] (numpy, or pinned CPU torch tensors); lens int32 [B]."""
+        def hp(a):
+            if a is None:
+                return 0, None
+            if isinstance(a, torch.Tensor):
+                assert a.dtype == torch.int32 and a.is_contiguous() and not a.is_cuda
+                return a.data_ptr(), a
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            return a.ctypes.data, a
+        pp, k0 = hp(p); qq, k1 = hp(q); dpp, k2 = hp(dp); dqq, k3 = hp(dq); ll, k4 = hp(lens)
+        B, lmax = p.shape
+        out = (c_double * 5)()
+        self._ck(lib.poi_gru_train_host_rows(self._h, byref(params), pp, qq, dpp, dqq, ll, int(B), int(lmax),
+                                             alpha, lam, out))
+        return list(out)
+
+    def gru_predict(self, params: PoiGruParams, index: PoiSeqIndex, uidx, max_len: int):
+        uidx = _host_i32(uidx, "uidx").reshape(-1)
+        B = uidx.size
+        dev = self.torch_device
+        hts = torch.empty((B, params.H), dtype=torch.float32, device=dev)
+        sts = torch.empty((B, params.n_rows_di), dtype=torch.float32, device=dev) if params.di else None
+        self._ck(lib.poi_gru_predict(self._h, byref(params), byref(index), uidx.ctypes.data, B, int(max_len),
+                                     hts.data_ptr(), sts.data_ptr() if sts is not None else 0))
+        return hts, sts
+
+    # ---- BPR / PRME -------------------------------------------------------------------------
+    def bpr_train_seq(self, ux, lt, u, p, q, alpha, lam) -> np.ndarray:
+        u = _host_i32(u, "u").reshape(-1); p = _host_i32(p, "p").reshape(-1); q = _host_i32(q, "q").reshape(-1)
+        loss = np.empty(u.size, dtype=np.float64)
+        self._ck(lib.poi_bpr_train_seq(self._h, _dev_f32(ux, "ux"), _dev_f32(lt, "lt"), lt.shape[1],
+                                       u.ctypes.data, p.ctypes.data, q.ctypes.data, u.size, alpha, lam,
+                                       loss.ctypes.data))
+        return loss
+
+    def bpr_train_batch(self, ux, lt, p, q, mask, u, alpha, lam) -> float:
+        p = _host_i32(p, "p").reshape(-1); q = _host_i32(q, "q").reshape(-1)
+        mask = _host_i32(mask, "mask").reshape(-1); u = _host_i32(u, "u").reshape(-1)
+        out = c_double()
+        self._ck(lib.poi_bpr_train_batch(self._h, _dev_f32(ux, "ux"), ux.shape[0], _dev_f32(lt, "lt"), lt.shape[0],
+                                         lt.shape[1], p.ctypes.data, q.ctypes.data, mask.ctypes.data, u.ctypes.data,
+                                         p.size, alpha, lam, byref(out)))
+        return out.value
+
+    def prme_train_seq(self, du, dp, ds, u, p, q, prev, dist, gap, thd, cw, alpha, lam) -> np.ndarray:
+        u = _host_i32(u, "u").reshape(-1); p = _host_i32(p, "p").reshape(-1); q = _host_i32(q, "q").reshape(-1)
+        prev = _host_i32(prev, "prev").reshape(-1); gap = _host_i32(gap, "gap").reshape(-1)
+        dist = np.ascontiguousarray(dist, dtype=np.float64).reshape(-1)
+        loss = np.empty(u.size, dtype=np.float64)
+        self._ck(lib.poi_prme_train_seq(self._h, _dev_f32(du, "du"), _dev_f32(dp, "dp"), _dev_f32(ds, "ds"),
+                                        dp.shape[1], u.ctypes.data, p.ctypes.data, q.ctypes.data, prev.ctypes.data,
+                                        dist.ctypes.data, gap.ctypes.data, u.size, int(thd), float(cw), alpha, lam,
+                                        loss.ctypes.data))
+        return loss
+
+    # ---- GeoIE ------------------------------------------------------------------------------
+    def geoie_train(self, g, h, z, t, ab, uidx, p_row, q_row, dist_pos, dist_neg, msk, alpha, lam) -> float:
+        prm = PoiGeoieParams()
+        prm.g = _dev_f32(g, "g"); prm.h = _dev_f32(h, "h"); prm.z = _dev_f32(z, "z"); prm.t = _dev_f32(t, "t")
+        if not (ab.is_cuda and ab.dtype == torch.float64 and ab.numel() == 2):
+            raise TypeError("ab must be a float64 CUDA tensor of 2 elements")
+        prm.ab = ab.data_ptr(); prm.n_rows = g.shape[0]; prm.H = g.shape[1]
+        p_row = _host_i32(p_row, "p_row").reshape(-1); q_row = _host_i32(q_row, "q_row").reshape(-1)
+        msk = _host_i32(msk, "msk")
+        n = msk.shape[0]
+        dpos = np.ascontiguousarray(dist_pos, dtype=np.float32); dneg = np.ascontiguousarray(dist_neg, dtype=np.float32)
+        out = c_double()
+        self._ck(lib.poi_geoie_train(self._h, byref(prm), int(uidx), p_row.ctypes.data, q_row.ctypes.data,
+                                     p_row.size, dpos.ctypes.data, dneg.ctypes.data, msk.ctypes.data, int(n),
+                                     alpha, lam, byref(out)))
+        return out.value
+
+    # ---- evaluation -------------------------------------------------------------------------
+    def score_topk(self, users, items, top_k, prob=None, wd=0.0):
+        B = users.shape[0]
+        out = torch.empty((B, top_k), dtype=torch.int32, device=users.device)
+        self._ck(lib.poi_score_topk(self._h, _dev_f32(users, "users"), B, _dev_f32(items, "items"), items.shape[0],
+                                    items.shape[1], _dev_f32(prob, "prob"), float(wd), int(top_k), out.data_ptr()))
+        return out

@@ -1,0 +1,157 @@
+"""GRU-family parity: the CUDA path (through the model classes -> ctypes -> C-ABI) against the CPU
+oracle on identical injected arrays.  Tolerance: the north-star bar, 1e-4 relative on losses and
+on every updated parameter tensor (fp32 device arithmetic vs float64 oracle)."""
+import numpy as np
+import pytest
+
+from oracle import explicit as E
+from oracle import fixtures as Fx
+from oracle import models as OM
+from tests.util import assert_close, state_from_model
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+ALPHA, LAM = 0.01, 0.001
+
+
+def _mk(rs, n_user, n_item, d, lmax, n_dist=None):
+    P, Q, M = Fx.ragged_sequences(rs, n_user, n_item, lmax)
+    st = Fx.nonzero_bias(rs, Fx.gru_state(rs, n_item, d, d, n_dist))
+    tes = [[n_item]] * n_user
+    test = [tes, [[0]] * n_user, tes]
+    if n_dist is None:
+        return P, Q, M, st, test
+    DP, DQ = Fx.interval_matrices(rs, P, Q, M, n_dist)
+    return P, Q, M, DP, DQ, st, test
+
+
+@pytest.mark.parametrize("d,lmax,n_item", [(8, 9, 50), (20, 17, 300), (32, 40, 500), (128, 12, 1000)])
+def test_obo_gru_trajectory(engine, d, lmax, n_item):
+    from poi_b200.public.GRU import OboGru
+    rs = np.random.RandomState(d + lmax)
+    n_user = 6
+    P, Q, M, st, test = _mk(rs, n_user, n_item, d, lmax)
+    model = OboGru([P, M, Q], test, [ALPHA, LAM], n_user, n_item, d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for u in [0, 3, 1, 0, 5, 2, 4]:
+        loss = model.train(u)
+        ref_loss, ref = OM.obo_gru_train(ref, P[u], Q[u], M[u], ALPHA, LAM)
+        assert_close(loss, ref_loss, RTOL, "loss user %d" % u)
+    got = state_from_model(model, ["lt", "ui", "wh", "bi"])
+    for k in got:
+        assert_close(got[k], ref[k], RTOL, k)
+    l2 = model.l2.eval()
+    assert_close(l2, OM.l2_value(ref, ["lt", "ui", "wh", "bi"], LAM), 1e-5, "l2")
+
+
+def test_obo_gru_first_step_is_log2(engine):
+    """Known answer: with h_{-1}=0 the t=0 term is log sigmoid(0); a length-1 user costs exactly log 2."""
+    from poi_b200.public.GRU import OboGru
+    rs = np.random.RandomState(3)
+    n_item, d = 30, 8
+    P = np.full((2, 5), n_item, dtype=np.int32); Q = P.copy(); M = np.zeros((2, 5), dtype=np.int32)
+    P[:, 0] = [3, 4]; Q[:, 0] = [7, 9]; M[:, 0] = 1
+    st = Fx.gru_state(rs, n_item, d, d)
+    tes = [[n_item]] * 2
+    model = OboGru([P, M, Q], [tes, [[0]] * 2, tes], [ALPHA, LAM], 2, n_item, d, d, init=st)
+    assert abs(model.train(0) - np.log(2.0)) < 1e-6
+
+
+@pytest.mark.parametrize("B", [2, 5])
+def test_gru_minibatch(engine, B):
+    from poi_b200.public.GRU import Gru
+    rs = np.random.RandomState(40 + B)
+    n_user, n_item, d, lmax = 7, 200, 32, 21
+    P, Q, M, st, test = _mk(rs, n_user, n_item, d, lmax)
+    model = Gru([P, M, Q], test, [ALPHA, LAM], n_user, n_item, d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for start in range(0, n_user, B):
+        se = np.arange(start, min(start + B, n_user), dtype=np.int32)
+        loss = model.train(se)
+        ref_loss, ref = OM.gru_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM)
+        assert_close(loss, ref_loss, RTOL, "loss batch %d" % start)
+    got = state_from_model(model, ["lt", "ui", "wh", "bi"])
+    for k in got:
+        assert_close(got[k], ref[k], RTOL, k)
+
+
+@pytest.mark.parametrize("d,lmax,n_item,n_dist", [(8, 9, 50, 12), (20, 23, 400, 200), (128, 10, 900, 200), (32, 33, 300, 37)])
+def test_obo_spatial_gru_trajectory(engine, d, lmax, n_item, n_dist):
+    from poi_b200.public.GRU_Spatial import OboSpatialGru
+    rs = np.random.RandomState(d * 3 + lmax)
+    n_user = 5
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    tes_d = [[n_dist]] * n_user
+    model = OboSpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for u in [0, 2, 4, 1, 0, 3]:
+        los, sur, upq, ls = model.train(u)
+        (rl, rs_, ru, rw), ref = OM.obo_spatial_gru_train(ref, P[u], Q[u], DP[u], DQ[u], M[u], ALPHA, LAM)
+        assert_close(los, rl, RTOL, "los"); assert_close(sur, rs_, RTOL, "sur"); assert_close(upq, ru, RTOL, "upq")
+        assert_close(ls, rw, RTOL, "ls")
+    got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
+    for k in got:
+        assert_close(got[k], ref[k], RTOL, k)
+    names = ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"]
+    assert_close(model.l2.eval(), OM.l2_value(ref, names, LAM), 1e-5, "l2")
+
+
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_spatial_gru_minibatch_extension(engine, B):
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(70 + B)
+    n_user, n_item, d, lmax, n_dist = 8, 300, 32, 19, 50
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    tes_d = [[n_dist]] * n_user
+    model = SpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for start in range(0, n_user, B):
+        se = np.arange(start, min(start + B, n_user), dtype=np.int32)
+        los, sur, upq, ls = model.train(se)
+        (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
+        assert_close([los, sur, upq], [rl, rs_, ru], RTOL, "losses batch %d" % start)
+    got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
+    for k in got:
+        assert_close(got[k], ref[k], RTOL, k)
+
+
+def test_spatial_host_rows_equals_resident(engine):
+    """The end-to-end entry (host index rows, H2D inside the call) must give the same bits as the
+    device-resident entry."""
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(11)
+    n_user, n_item, d, lmax, n_dist = 16, 500, 32, 15, 40
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    tes_d = [[n_dist]] * n_user
+    mk = lambda: SpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+    a, b = mk(), mk()
+    se = np.arange(4, 12, dtype=np.int32)
+    ra = a.train(se)
+    rb = b.train_host_rows(P[se], Q[se], DP[se], DQ[se], M[se].sum(1).astype(np.int32))
+    assert ra[:3] == rb[:3]
+    for k in ["lt", "di", "ui", "wh", "vs"]:
+        assert np.array_equal(getattr(a, k).get_value(), getattr(b, k).get_value()), k
+
+
+def test_predict_matches_oracle(engine):
+    from poi_b200.public.GRU_Spatial import OboSpatialGru
+    from poi_b200.public.GRU import OboGru
+    rs = np.random.RandomState(21)
+    n_user, n_item, d, lmax, n_dist = 9, 120, 20, 14, 30
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    tes_d = [[n_dist]] * n_user
+    model = OboSpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+    model.update_trained_items(); model.update_trained_dists()
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    ref["trained_items"], ref["trained_dists"] = ref["lt"], ref["di"]
+    se = np.array([1, 2, 3, 7, 8], dtype=np.int32)
+    hts, sts = model.predict(se)
+    rh, rs_ = OM.gru_predict(ref, P[se], M[se], DP[se])
+    assert_close(hts, rh, RTOL, "hts"); assert_close(sts, rs_, RTOL, "sts")
+    stg = Fx.gru_state(rs, n_item, d, d)
+    g = OboGru([P, M, Q], test, [ALPHA, LAM], n_user, n_item, d, d, init=stg)
+    g.update_trained_items()
+    refg = {k: np.asarray(v, dtype=np.float64) for k, v in stg.items()}
+    refg["trained_items"] = refg["lt"]
+    assert_close(g.predict(se), OM.gru_predict(refg, P[se], M[se]), RTOL, "gru hts")
