@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- train check-ins/sec of the Distance2Pre hot path on synthetic check-in sequences.
+
+Workload (BASELINE.json configs[1], "c2"): |POI| = 40k, |U| = 10k, seq = 32, d = H = 128, 201 distance
+intervals, alpha = 0.01, lambda = 0.001; one step = one mini-batch `SpatialGru.train` call over
+`--batch` users (gather -> GRU recurrence -> interval-softmax head -> BPR + survival loss -> BPTT ->
+dense SGD -> sparse row SGD).  A check-in = one valid training position (L-1 per user).
+
+  value      device-timed (CUDA events on the engine stream), index matrices resident in HBM
+  e2e        the same step through the host-rows entry: the batch's index rows come from pinned host
+             memory every step (H2D inside the timed region) and the loss scalars are read back
+  roofline   the dominant kernel category of the step, from the engine's per-launch CUDA-event
+             profiler, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+             the CPU oracle (numpy restatement of the reference semantics, all host threads via BLAS)
+             on a bounded sample of the same workload
+
+python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B] [--config c2]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "train check-ins/sec"
+UNIT = "check-ins/s"
+ALPHA, LAM = 0.01, 0.001
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def build_workload(cfg_name, users_cap=None):
+    import poi_b200  # noqa: F401
+    from poi_b200 import synth
+    cfg = dict(synth.CONFIGS[cfg_name])
+    n_user = cfg["n_user"] if users_cap is None else min(cfg["n_user"], users_cap)
+    ds = synth.make_dataset(n_user, cfg["n_item"], cfg["seq"], UD=cfg["UD"], dd=cfg["dd"])
+    st = synth.init_state(cfg["n_item"], cfg["d"], cfg["d"], ds["dist_num"])
+    return cfg, ds, st
+
+
+def checkins_of(lens):
+    return int(np.maximum(np.asarray(lens, dtype=np.int64) - 1, 0).sum())
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy explicit restatement), mini-batch semantics identical to the GPU arm
+# --------------------------------------------------------------------------------------------------
+def cpu_steps(ds, st, batch, n_steps, warmup):
+    from oracle import explicit as E
+    ref = {k: np.asarray(v, dtype=np.float32) for k, v in st.items()}
+    U = ds["n_user"]
+    times, done = [], 0
+    for i in range(warmup + n_steps):
+        s = (i * batch) % U
+        se = np.arange(s, min(s + batch, U))
+        t0 = time.perf_counter()
+        _, ref = E.gru_family_train_batch(ref, ds["P"][se], ds["Q"][se], ds["M"][se], ALPHA, LAM,
+                                          ds["DP"][se], ds["DQ"][se], dtype=np.float32)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt); done += checkins_of(ds["lens"][se])
+    return done / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (oracle port; Theano is not installable,
+    SURVEY.md 8c) on the box's host cores, same config / metric / unit, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, ds, st = build_workload(args.config)
+    cores = os.cpu_count() or 1
+    try:
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
+    batch = min(args.cpu_batch, ds["n_user"])
+    steps = max(1, args.steps)
+    value, sec = cpu_steps(ds, st, batch, steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2: Distance2Pre |POI|=40k |U|=10k seq=32 d=128 D=200", "users_per_step": batch,
+                   "semantics": "mini-batch extension (SURVEY 3.6), same as the GPU arm"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d users (numpy oracle, BLAS threads = all cores)" % (steps, batch)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path is CUDA only (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import poi_b200  # noqa: F401
+    from poi_b200.public.GRU_Spatial import SpatialGru
+
+    cfg, ds, st = build_workload(args.config)
+    U, I, d, seq, D = ds["n_user"], ds["n_item"], cfg["d"], ds["seq"], ds["dist_num"]
+    tes = ds["tes"]
+    model = SpatialGru([ds["P"], ds["M"], ds["Q"]], [tes, np.ones_like(tes), tes],
+                       [ds["DP"], np.full_like(tes, D), ds["DQ"]], [ALPHA, LAM], U, I, [D, cfg["dd"] / 1000.0],
+                       d, d, init=st, device=local_rank)
+    eng = model.engine
+    eng.set_gemm_mode(args.gemm_mode)
+    B = min(args.batch, U)
+    dev = torch.device("cuda", local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def batch_users(i):
+        # weak scaling: every rank trains its own batch of B users per step (rank-strided user ranges)
+        s = ((i * world + rank) * B) % U
+        se = (np.arange(s, s + B) % U).astype(np.int32)
+        return se
+
+    pinned = {}
+    for k in ("P", "Q", "DP", "DQ"):
+        pinned[k] = torch.from_numpy(ds[k]).pin_memory()
+    lens_pin = torch.from_numpy(ds["lens"]).pin_memory()
+
+    def step_resident(i):
+        return model.train(batch_users(i))
+
+    def step_host_rows(i):
+        se = torch.from_numpy(batch_users(i).astype(np.int64))
+        rows = [pinned[k][se].pin_memory() for k in ("P", "Q", "DP", "DQ")]
+        ln = lens_pin[se].pin_memory()
+        return model.train_host_rows(rows[0], rows[1], rows[2], rows[3], ln)
+
+    def timed(step_fn, n_warm, n_steps, first_step):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        for i in range(n_warm):
+            step_fn(first_step + i)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        done = 0
+        losses = []
+        wall0 = time.perf_counter()
+        for i in range(n_steps):
+            flush.fill_(i & 0xff)                       # evict L2 between timed iterations (outside the events)
+            ev[i][0].record()
+            out = step_fn(first_step + n_warm + i)
+            ev[i][1].record()
+            done += checkins_of(ds["lens"][batch_users(first_step + n_warm + i)])
+            losses.append(out[0])
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        if dist is not None:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return ms, done, losses, wall
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launch_count()
+    ms, done, losses, _ = timed(step_resident, W, K, 0)
+    launches = eng.launch_count() - l0
+    ms_e2e, done_e2e, _, _ = timed(step_host_rows, 1, K, W + K)
+    clocks = sampler.stop()
+
+    # per-launch profile of the same steps (CUDA events around every kernel on the engine stream)
+    eng.kprof_reset(); eng.kprof_enable(True)
+    nprof = min(K, 3)
+    for i in range(nprof):
+        step_resident(2 * (W + K) + i)
+    prof = eng.kprof_get()
+    eng.kprof_enable(False)
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms_max, ms_e2e_max = allmax(ms), allmax(ms_e2e)
+    done_all, done_e2e_all = allsum(done), allsum(done_e2e)
+    launches_all = int(allsum(launches))
+    if rank != 0:
+        return
+
+    peaks = load_peaks()
+    value = done_all / (ms_max * 1e-3)
+    e2e_val = done_e2e_all / (ms_e2e_max * 1e-3)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    name, rec = dom
+    if rec["flops"] > 0:
+        ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained)",
+                "share_of_step": rec["ms"] / tot_ms, "launches_per_step": rec["launches"] / nprof,
+                "avg_launch_us": rec["ms"] * 1e3 / max(rec["launches"], 1)}
+    else:
+        ach = rec["bytes"] / (rec["ms"] * 1e-3) / 1e9
+        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"],
+                "share_of_step": rec["ms"] / tot_ms, "launches_per_step": rec["launches"] / nprof,
+                "avg_launch_us": rec["ms"] * 1e3 / max(rec["launches"], 1)}
+    hbm_kernels = {}
+    for k in ("gather", "rows"):
+        r = prof[k]
+        if r["ms"] > 0:
+            g = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+            hbm_kernels[k] = {"achieved_GBps": g, "frac_of_hbm_peak": g / peaks["hbm"], "ms_per_step": r["ms"] / nprof}
+    breakdown = {k: round(v["ms"] / nprof, 4) for k, v in prof.items() if v["ms"] > 0}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = min(args.cpu_batch, U)
+        v, sec = cpu_steps(ds, st, cb, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "3 steps x %d users of the same workload (numpy oracle, BLAS threads = all cores)" % cb}
+
+    h2d = 4 * B * seq * 4 + B * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.gemm_mode == 0 else ("3xtf32" if args.gemm_mode == 1 else "tf32"),
+        "data": "synthetic",
+        "config": {"workload": "c2: Distance2Pre |POI|=%d |U|=%d seq=%d d=%d D=%d" % (I, U, seq, d, D),
+                   "users_per_step_per_gpu": B, "check_ins_per_step": done_all / K,
+                   "semantics": "mini-batch extension (SURVEY 3.6); B=1 is the reference's one-by-one mode",
+                   "gemm_mode": args.gemm_mode, "l2": "flushed between timed steps (256 MB write)",
+                   "parallelism": "1 GPU" if world == 1 else "dp%d replicas" % world},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 40,
+                "ms_per_step": ms_e2e_max / K},
+        "gpu_launches": launches_all,
+        "roofline": roof, "hbm_kernels": hbm_kernels, "kernel_ms_per_step": breakdown,
+        "cpu_baseline": cpu, "clocks": clocks, "final_loss": float(losses[-1]),
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--batch", type=int, default=4096, help="users per step per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=512, help="users per CPU-oracle step")
+    ap.add_argument("--gemm-mode", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,9 @@ _PROTOS = {
     "poi_launch_count": (c_int, [_E, POINTER(c_int64)]),
     "poi_last_phase_ms": (c_int, [_E, POINTER(c_float)]),
     "poi_enable_phase_timing": (c_int, [_E, c_int]),
+    "poi_kprof_enable": (c_int, [_E, c_int]),
+    "poi_kprof_reset": (c_int, [_E]),
+    "poi_kprof_get": (c_int, [_E, POINTER(c_double)]),
     "poi_set_gemm_mode": (c_int, [_E, c_int]),
     "poi_get_gemm_mode": (c_int, [_E, POINTER(c_int)]),
     "poi_gather_rows": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),

@@ -13,6 +13,11 @@
 
 struct PoiChunk { char* ptr; size_t cap; };
 
+// kernel categories for the built-in per-launch profiler (bench.py's roofline numbers)
+enum PoiCat { CAT_OTHER = 0, CAT_INDEX = 1, CAT_GATHER = 2, CAT_GEMM = 3, CAT_WGRAD = 4, CAT_LOSS = 5,
+              CAT_ELTWISE = 6, CAT_ROWS = 7, CAT_MF = 8, CAT_GEOIE = 9, CAT_EVAL = 10, CAT_REDUCE = 11, POI_NCAT = 12 };
+struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
+
 struct poi_engine {
     int device = 0;
     int num_sms = 148;
@@ -27,6 +32,14 @@ struct poi_engine {
     double*  h_out = nullptr;        // 64 doubles
     char*    h_stage = nullptr;      // pinned staging for small host->device index uploads
     size_t   h_stage_cap = 0;
+    // per-launch profiler: CUDA events around every kernel on the engine stream
+    bool kprof = false;
+    int cur_cat = CAT_OTHER;
+    double cur_flops = 0.0, cur_bytes = 0.0;
+    std::vector<ProfRec> recs;
+    size_t nrec = 0;
+    double cat_ms[POI_NCAT] = {}, cat_flops[POI_NCAT] = {}, cat_bytes[POI_NCAT] = {};
+    int64_t cat_launches[POI_NCAT] = {};
     // phase timing
     bool timing = false;
     cudaEvent_t ev[9] = {};
@@ -55,14 +68,44 @@ static thread_local std::string g_create_err;
         if (_r != 0) return _r;                                                  \
     } while (0)
 
-// every kernel launch goes through here so that poi_launch_count is exact
+static inline ProfRec* prof_begin(poi_engine* e);
+
+// every kernel launch goes through here so that poi_launch_count is exact; `cat`/work set by
+// POI_CAT apply to the launches that follow
+#define POI_CAT(e, c, fl, by) do { (e)->cur_cat = (c); (e)->cur_flops = (double)(fl); (e)->cur_bytes = (double)(by); } while (0)
 #define POI_LAUNCH(e, kern, grid, block, smem, ...)                              \
     do {                                                                         \
+        ProfRec* _pr = (e)->kprof ? prof_begin(e) : nullptr;                     \
         kern<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);             \
+        if (_pr) cudaEventRecord(_pr->b, (e)->stream);                           \
+        (e)->cur_flops = 0.0; (e)->cur_bytes = 0.0;                              \
         (e)->launches++;                                                         \
         cudaError_t _s = cudaPeekAtLastError();                                  \
         if (_s != cudaSuccess) POI_FAIL(e, "launch %s failed: %s", #kern, cudaGetErrorString(_s)); \
     } while (0)
+
+static inline ProfRec* prof_begin(poi_engine* e) {
+    if (e->nrec == e->recs.size()) {
+        ProfRec r; cudaEventCreate(&r.a); cudaEventCreate(&r.b); r.cat = 0; r.flops = r.bytes = 0;
+        e->recs.push_back(r);
+    }
+    ProfRec* r = &e->recs[e->nrec++];
+    r->cat = e->cur_cat; r->flops = e->cur_flops; r->bytes = e->cur_bytes;
+    cudaEventRecord(r->a, e->stream);
+    return r;
+}
+// call after the stream has been synchronised
+static inline void prof_harvest(poi_engine* e) {
+    for (size_t i = 0; i < e->nrec; ++i) {
+        ProfRec& r = e->recs[i];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            e->cat_ms[r.cat] += ms; e->cat_flops[r.cat] += r.flops; e->cat_bytes[r.cat] += r.bytes;
+            e->cat_launches[r.cat]++;
+        }
+    }
+    e->nrec = 0;
+}
 
 static inline size_t poi_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int64_t poi_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

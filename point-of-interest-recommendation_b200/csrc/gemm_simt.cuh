@@ -126,6 +126,7 @@ static int launch_gemm_tn(poi_engine* e, const float* A, int lda, const float* W
                           int64_t M, int N, int K, const Epi& epi) {
     if (M <= 0 || N <= 0) return 0;
     if (M > 0x7fffffffLL) POI_FAIL(e, "gemm M too large");
+    POI_CAT(e, CAT_GEMM, 2.0 * (double)M * N * K, 0);
     int64_t big_ctas = poi_cdiv(M, 128) * poi_cdiv(N, 128);
     if (big_ctas >= 2 * e->num_sms) {
         dim3 grid((unsigned)poi_cdiv(N, 128), (unsigned)poi_cdiv(M, 128));
@@ -252,6 +253,7 @@ static int launch_gemm_atb(poi_engine* e, const float* A, int lda, const float* 
     splits = (int)std::max<int64_t>(1, poi_cdiv(std::max<int64_t>(M, 1), mps));
     plan->splits = splits; plan->m_per_split = mps; plan->N1 = N1; plan->N2 = N2;
     POI_TRY(arena_get(e, (size_t)splits * N1 * N2, &plan->part));
+    POI_CAT(e, CAT_WGRAD, 2.0 * (double)M * N1 * N2, 0);
     dim3 grid((unsigned)poi_cdiv(N2, 64), (unsigned)poi_cdiv(N1, 64), (unsigned)splits);
     POI_LAUNCH(e, (k_gemm_atb<64, 64, 16, 4, 4>), grid, 256, 0, A, lda, Bm, ldb, M, N1, N2, mps, plan->part);
     return 0;
@@ -275,6 +277,7 @@ __global__ void k_reduce_update(const float* __restrict__ part, int splits, int 
 static int launch_reduce_update(poi_engine* e, const AtbPlan& p, float* theta, int ldt,
                                 int n1_true, int n2_true, float alpha, float lambda) {
     int64_t n = (int64_t)n1_true * n2_true;
+    POI_CAT(e, CAT_WGRAD, 0, 0);
     POI_LAUNCH(e, k_reduce_update, (unsigned)poi_cdiv(n, 256), 256, 0, p.part, p.splits, p.N1, p.N2,
                theta, ldt, n1_true, n2_true, alpha, lambda);
     return 0;
@@ -309,6 +312,7 @@ static int launch_colsum(poi_engine* e, const float* A, int lda, int64_t M, int 
     plan->splits = splits; plan->m_per_split = mps; plan->N1 = 1; plan->N2 = N;
     POI_TRY(arena_get(e, (size_t)splits * N, &plan->part));
     dim3 grid((unsigned)colblocks, (unsigned)splits);
+    POI_CAT(e, CAT_WGRAD, 0, (double)M * N * 4);
     POI_LAUNCH(e, k_colsum_partial, grid, 256, 0, A, lda, M, N, mps, plan->part);
     return 0;
 }

@@ -91,6 +91,7 @@ __global__ void k_transpose_pad(const float* __restrict__ in, int R, int Cc, flo
 
 static int launch_transpose_pad(poi_engine* e, const float* in, int R, int Cc, float* out, int ldo) {
     dim3 grid((unsigned)poi_cdiv(Cc, 32), (unsigned)poi_cdiv(ldo, 32));
+    POI_CAT(e, CAT_ELTWISE, 0, 0);
     POI_LAUNCH(e, k_transpose_pad, grid, dim3(32, 8), 0, in, R, Cc, out, ldo);
     return 0;
 }
@@ -376,6 +377,10 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
     {
         int64_t rows = (int64_t)(T + (training ? 1 : 0)) * B;
         unsigned grid = (unsigned)std::min<int64_t>(poi_cdiv(rows * 32, 256), (int64_t)e->num_sms * 16);
+        // algorithmic bytes: rows read from the tables + the dense tiles written + the indices
+        double gb = (double)rows * d * 4 + (training ? (double)TB * d * 4 * 2 : 0.0) + (head ? (double)TB * d * 4 : 0.0)
+                  + (double)TB * din * 4 + 4.0 * (double)rows * (head ? 3 : 2);
+        POI_CAT(e, CAT_GATHER, 0, gb);
         POI_LAUNCH(e, k_gather_inputs, grid, 256, 0, p->lt, p->di, ix.PQt, ix.DPt, B, T, LB, d / 4, din / 4,
                    training ? 1 : 0, X, XDiff);
     }
@@ -426,6 +431,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
     double *part, *out_dev;
     POI_TRY(arena_get(e, (size_t)loss_blocks * 4, &part));
     POI_TRY(arena_get(e, 8, &out_dev));
+    POI_CAT(e, CAT_LOSS, 0, (double)TB * ((head ? 2.0 * nDp : 0.0) + 2.0 * H) * 4);
     POI_LAUNCH(e, k_loss_head, loss_blocks, 256, 0, S, nD, nDp, Hc, XDiff, H / 4, ix.DPt, ix.DQt, ix.lensB,
                p->scal, B, T, scale, head ? 1 : 0, ev, part);
     phase_mark(e, 4);
@@ -447,10 +453,12 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
             POI_TRY(launch_transpose_pad(e, p->vs, nD, H, vsT, nDp));
             POI_TRY(gemm_tn(e, S, nDp, vsT, nDp, TB, H, nDp, EpiDHl{DHl, ev, XDiff, H}));
         } else {
+            POI_CAT(e, CAT_ELTWISE, 0, 0);
             POI_LAUNCH(e, k_dhl_nohead, (unsigned)poi_cdiv(TB * (H / 4), 256), 256, 0, ev, XDiff, DHl, TB, H / 4);
         }
         {
             size_t o = (size_t)(T - 1) * B * H;
+            POI_CAT(e, CAT_ELTWISE, 0, 0);
             POI_LAUNCH(e, k_bwd_prep, (unsigned)poi_cdiv((int64_t)B * H / 4, 256), 256, 0, DHl + o, Z + o, C + o,
                        Hs + o, DA + (size_t)(T - 1) * B * 3 * H, DHK, B, H);
         }
@@ -486,6 +494,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
         POI_TRY(launch_reduce_update(e, g_vs, p->vs, H, nD, H, alpha, lambda));
         POI_TRY(launch_reduce_update(e, g_bs, p->bs, nD, 1, nD, alpha, lambda));
     }
+    POI_CAT(e, CAT_REDUCE, 0, 0);
     POI_LAUNCH(e, k_finalize_gru, 1, 32, 0, part, loss_blocks, p->scal, head ? 1 : 0,
                (double)n_nonempty * 0.6931471805599453, (double)scale, alpha, lambda, out_dev);
     phase_mark(e, 6);
@@ -494,16 +503,21 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
     RowSrc src;
     src.mode = SRC_GRU_LT; src.grads = nullptr; src.DX = DX; src.ldx = din; src.Hc = Hc; src.ev = ev;
     src.B = B; src.T = T; src.LB = LB; src.dim = d;
-    POI_TRY(launch_rows_update(e, seg_lt, p->lt, d, alpha, lambda, src, ROW_LONG_THRESH));
+    // algorithmic bytes of the sparse step: 2 table rows per check-in, read + written,
+    // plus the gradient rows that feed them (dx, and e*h for p and q)
+    POI_TRY(launch_rows_update(e, seg_lt, p->lt, d, alpha, lambda, src, ROW_LONG_THRESH,
+                               (double)TB * d * 4 * (4.0 + 3.0) + 8.0 * (double)LB));
     if (head) {
         src.mode = SRC_GRU_DI;
-        POI_TRY(launch_rows_update(e, seg_di, p->di, d, alpha, lambda, src, ROW_LONG_THRESH));
+        POI_TRY(launch_rows_update(e, seg_di, p->di, d, alpha, lambda, src, ROW_LONG_THRESH,
+                                   (double)TB * d * 4 + 4.0 * (double)LB));
     }
     phase_mark(e, 7);
 
     POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     phase_mark(e, 8);
     POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
     for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];
     if (e->timing) {
         cudaEventElapsedTime(&e->phase_ms[0], e->ev[0], e->ev[8]);

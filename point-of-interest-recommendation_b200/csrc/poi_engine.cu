@@ -51,6 +51,7 @@ void poi_engine_destroy(poi_engine* e) {
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& r : e->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     delete e;
 }
 
@@ -66,9 +67,25 @@ int poi_set_gemm_mode(poi_engine* e, int mode) {
     e->gemm_mode = mode; return 0;
 }
 int poi_get_gemm_mode(poi_engine* e, int* mode) { *mode = e->gemm_mode; return 0; }
+int poi_kprof_enable(poi_engine* e, int on) { e->kprof = on != 0; return 0; }
+int poi_kprof_reset(poi_engine* e) {
+    for (int c = 0; c < POI_NCAT; ++c) { e->cat_ms[c] = e->cat_flops[c] = e->cat_bytes[c] = 0.0; e->cat_launches[c] = 0; }
+    return 0;
+}
+int poi_kprof_get(poi_engine* e, double* out) {
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    prof_harvest(e);
+    for (int c = 0; c < POI_NCAT; ++c) {
+        out[c * 4 + 0] = e->cat_ms[c]; out[c * 4 + 1] = (double)e->cat_launches[c];
+        out[c * 4 + 2] = e->cat_flops[c]; out[c * 4 + 3] = e->cat_bytes[c];
+    }
+    return 0;
+}
 
 static int begin_call(poi_engine* e) {
     POI_CK(e, cudaSetDevice(e->device));
+    if (e->nrec > 4096) { POI_CK(e, cudaStreamSynchronize(e->stream)); prof_harvest(e); }
+    POI_CAT(e, CAT_OTHER, 0, 0);
     POI_TRY(arena_reset(e));
     return 0;
 }
@@ -142,6 +159,7 @@ int poi_gru_train(poi_engine* e, const poi_gru_params* p, const poi_seq_index* i
     POI_TRY(gru_upload_i32(e, uidx_host, (size_t)B, &uidx_dev, &so));
     GruIdx ix;
     POI_TRY(gru_alloc_idx(e, B, index->lmax, head, &ix));
+    POI_CAT(e, CAT_INDEX, 0, 0);
     POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv((int64_t)B * index->lmax, 256), 256, 0, index->p, index->q,
                head ? index->dp : nullptr, head ? index->dq : nullptr, index->lens, index->lmax, uidx_dev, B,
                ix.PQt, ix.DPt, ix.DQt, ix.lensB);
@@ -173,6 +191,7 @@ int poi_gru_train_host_rows(poi_engine* e, const poi_gru_params* p, const int32_
     for (int b = 0; b < B; ++b) { max_len = std::max(max_len, lens_host[b]); n_nonempty += lens_host[b] >= 1; }
     GruIdx ix;
     POI_TRY(gru_alloc_idx(e, B, lmax, head, &ix));
+    POI_CAT(e, CAT_INDEX, 0, 0);
     POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv((int64_t)LB, 256), 256, 0, P, Q, DP, DQ, lens, lmax,
                (const int32_t*)nullptr, B, ix.PQt, ix.DPt, ix.DQt, ix.lensB);
     return gru_train_core(e, p, ix, B, lmax, max_len, head ? 0 : n_nonempty, alpha, lambda, out_host);
@@ -216,6 +235,7 @@ int poi_gru_predict(poi_engine* e, const poi_gru_params* p, const poi_seq_index*
     GruIdx ix;
     POI_TRY(gru_alloc_idx(e, B, index->lmax, head, &ix));
     // predict has no negatives: reuse p for the q slot of the slicer
+    POI_CAT(e, CAT_INDEX, 0, 0);
     POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv((int64_t)B * index->lmax, 256), 256, 0, index->p, index->p,
                head ? index->dp : nullptr, head ? index->dp : nullptr, index->lens, index->lmax, uidx_dev, B,
                ix.PQt, ix.DPt, ix.DQt, ix.lensB);
@@ -223,12 +243,14 @@ int poi_gru_predict(poi_engine* e, const poi_gru_params* p, const poi_seq_index*
     float *X, *XDiff, *AX, *Hs, *Z, *R, *C, *RH;
     POI_TRY(gru_forward(e, p, ix, B, index->lmax, T, false, &X, &XDiff, &AX, &Hs, &Z, &R, &C, &RH));
     const int H = p->H;
+    POI_CAT(e, CAT_ELTWISE, 0, 0);
     POI_LAUNCH(e, k_pick_last, (unsigned)poi_cdiv((int64_t)B * H / 4, 256), 256, 0, Hs, ix.lensB, B, H / 4, hts_dev);
     if (head) {
         const int nD = p->n_rows_di, nDp = (nD + 3) / 4 * 4;
         float* lg = nullptr;
         POI_TRY(arena_get(e, (size_t)B * nDp, &lg));
         POI_TRY(gemm_tn(e, hts_dev, H, p->vs, H, B, nD, H, EpiBiasStore{lg, nDp, p->bs, nD}));
+        POI_CAT(e, CAT_LOSS, 0, 0);
         POI_LAUNCH(e, k_softmax_rows, (unsigned)poi_cdiv((int64_t)B * 32, 256), 256, 0, lg, nDp, nD, (int64_t)B, sts_dev);
     }
     POI_CK(e, cudaStreamSynchronize(e->stream));
@@ -260,6 +282,7 @@ int poi_bpr_train_seq(poi_engine* e, float* ux, float* lt, int32_t d, const int3
     double* loss_dev = nullptr;
     POI_TRY(arena_get(e, (size_t)n, &loss_dev));
     const int d4 = d / 4;
+    POI_CAT(e, CAT_MF, 0, (double)n * 3 * d * 4 * 2);
 #define BPR_GO(N) POI_LAUNCH(e, (k_bpr_seq<N>), 1, 32, 0, ux, lt, d4, (const int32_t*)ds[0], (const int32_t*)ds[1], (const int32_t*)ds[2], n, alpha, lambda, loss_dev)
     if (d4 <= 32) BPR_GO(1); else if (d4 <= 64) BPR_GO(2); else if (d4 <= 128) BPR_GO(4); else BPR_GO(8);
 #undef BPR_GO
@@ -282,6 +305,7 @@ int poi_prme_train_seq(poi_engine* e, float* du, float* dp, float* ds_, int32_t 
     double* loss_dev = nullptr;
     POI_TRY(arena_get(e, (size_t)n, &loss_dev));
     const int d4 = d / 4;
+    POI_CAT(e, CAT_MF, 0, (double)n * 7 * d * 4 * 2);
 #define PRME_GO(N) POI_LAUNCH(e, (k_prme_seq<N>), 1, 32, 0, du, dp, ds_, d4, (const int32_t*)ds[0], (const int32_t*)ds[1], (const int32_t*)ds[2], (const int32_t*)ds[3], (const double*)ds[4], (const int32_t*)ds[5], n, (int)threshold, (float)cw, alpha, lambda, loss_dev)
     if (d4 <= 32) PRME_GO(1); else if (d4 <= 64) PRME_GO(2); else PRME_GO(4);
 #undef PRME_GO

@@ -38,6 +38,7 @@ static int launch_gather_rows(poi_engine* e, const float* table, int dim, const 
     if (n_idx <= 0) return 0;
     const int dim4 = dim / 4;
     const int UNR = 4;
+    POI_CAT(e, CAT_GATHER, 0, 2.0 * (double)n_idx * dim * 4 + 4.0 * (double)n_idx);
     int lpr = dim4 <= 8 ? 8 : (dim4 <= 16 ? 16 : 32);
     int64_t groups_needed = poi_cdiv(n_idx, UNR);
     int64_t threads_needed = groups_needed * lpr;
@@ -92,6 +93,7 @@ static int launch_sumsq(poi_engine* e, const float* x, int64_t n, double* out_de
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(poi_cdiv(n / 4 + 1, 256), 1), (int64_t)e->num_sms * SUMSQ_BLOCKS_PER_SM);
     double* part = nullptr;
     POI_TRY(arena_get(e, (size_t)blocks, &part));
+    POI_CAT(e, CAT_REDUCE, 0, (double)n * 4);
     POI_LAUNCH(e, k_sumsq_partial, blocks, 256, 0, x, n, part);
     POI_LAUNCH(e, k_sum_partials_d, 1, 32, 0, part, blocks, out_dev, 1, 1);
     return 0;
@@ -232,8 +234,10 @@ k_rows_update_long(SegList seg, float* __restrict__ table, int dim4, float alpha
 }
 
 static int launch_rows_update(poi_engine* e, const SegList& seg, float* table, int dim,
-                              float alpha, float lambda, const RowSrc& src, int long_thresh) {
+                              float alpha, float lambda, const RowSrc& src, int long_thresh,
+                              double algo_bytes = 0.0) {
     if (seg.n <= 0) return 0;
+    POI_CAT(e, CAT_ROWS, 0, algo_bytes);
     const int dim4 = dim / 4;
     uint32_t *long_list = nullptr, *long_count = nullptr;
     POI_TRY(arena_get(e, (size_t)seg.n, &long_list));

@@ -256,6 +256,7 @@ __global__ void k_seg_write(const uint32_t* keys, const uint32_t* vals, const ui
 static int build_segments(poi_engine* e, const uint32_t* keys_dev, int64_t n, uint32_t bound,
                           bool want_inverse, SegList* out) {
     out->n = n;
+    POI_CAT(e, CAT_INDEX, 0, 0);
     POI_TRY(sort_pairs(e, keys_dev, n, bound, &out->keys, &out->vals));
     uint32_t* excl = nullptr;
     size_t nn = (size_t)std::max<int64_t>(n, 1);

@@ -93,6 +93,21 @@ class Engine:
         self._ck(lib.poi_last_phase_ms(self._h, buf))
         return list(buf)
 
+    KPROF_CATS = ["other", "index", "gather", "gemm", "wgrad", "loss", "eltwise", "rows", "mf", "geoie", "eval", "reduce"]
+
+    def kprof_enable(self, on: bool):
+        self._ck(lib.poi_kprof_enable(self._h, 1 if on else 0))
+
+    def kprof_reset(self):
+        self._ck(lib.poi_kprof_reset(self._h))
+
+    def kprof_get(self):
+        """{category: dict(ms, launches, flops, bytes)} accumulated since the last reset."""
+        buf = (c_double * 48)()
+        self._ck(lib.poi_kprof_get(self._h, buf))
+        return {c: dict(ms=buf[i * 4], launches=int(buf[i * 4 + 1]), flops=buf[i * 4 + 2], bytes=buf[i * 4 + 3])
+                for i, c in enumerate(self.KPROF_CATS)}
+
     def set_gemm_mode(self, mode: int):
         self._ck(lib.poi_set_gemm_mode(self._h, int(mode)))
 
