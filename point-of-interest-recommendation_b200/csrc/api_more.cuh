@@ -1,16 +1,163 @@
 // api_more.cuh -- remaining extern "C" entry points (Bpr mini-batch, GeoIE, score+top-K)
 #pragma once
+
+// per-occurrence loss gradients of the Bpr mini-batch (BPR.py:372-383), L2 handled by the row update
+__global__ void __launch_bounds__(256)
+k_bpr_batch_grads(const float* __restrict__ ux, const float* __restrict__ lt, int d4,
+                  const int32_t* __restrict__ us, const int32_t* __restrict__ ps, const int32_t* __restrict__ qs,
+                  const int32_t* __restrict__ mask, int64_t n, float* __restrict__ GU, float* __restrict__ GPQ,
+                  double* __restrict__ part) {
+    __shared__ double sh[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + w, nwarps = (int64_t)gridDim.x * 8;
+    double acc = 0.0;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const float4* u4 = reinterpret_cast<const float4*>(ux) + (size_t)us[i] * d4;
+        const float4* p4 = reinterpret_cast<const float4*>(lt) + (size_t)ps[i] * d4;
+        const float4* q4 = reinterpret_cast<const float4*>(lt) + (size_t)qs[i] * d4;
+        float dot = 0.f;
+        for (int c = lane; c < d4; c += 32) {
+            float4 u = u4[c], p = p4[c], q = q4[c];
+            dot += u.x * (p.x - q.x) + u.y * (p.y - q.y) + u.z * (p.z - q.z) + u.w * (p.w - q.w);
+        }
+        dot = warp_sum(dot);
+        const float m = (float)mask[i];
+        const float g = sigmoidf_(-dot) * m;
+        if (lane == 0) acc += (double)(logsigmoidf_(dot) * m);
+        for (int c = lane; c < d4; c += 32) {
+            float4 u = u4[c], p = p4[c], q = q4[c];
+            reinterpret_cast<float4*>(GU)[(size_t)i * d4 + c] = make_float4(-g * (p.x - q.x), -g * (p.y - q.y), -g * (p.z - q.z), -g * (p.w - q.w));
+            reinterpret_cast<float4*>(GPQ)[(size_t)i * d4 + c] = make_float4(-g * u.x, -g * u.y, -g * u.z, -g * u.w);
+            reinterpret_cast<float4*>(GPQ)[(size_t)(n + i) * d4 + c] = make_float4(g * u.x, g * u.y, g * u.z, g * u.w);
+        }
+    }
+    if (lane == 0) sh[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 8; ++i) t += sh[i]; part[blockIdx.x] = t; }
+}
+
 extern "C" {
-int poi_bpr_train_batch(poi_engine* e, float*, int64_t, float*, int64_t, int32_t, const int32_t*, const int32_t*,
-                        const int32_t*, const int32_t*, int64_t, float, float, double*) {
-    POI_FAIL(e, "poi_bpr_train_batch: not implemented yet");
+
+int poi_bpr_train_batch(poi_engine* e, float* ux, int64_t n_user, float* lt, int64_t n_rows_lt, int32_t d,
+                        const int32_t* p, const int32_t* q, const int32_t* mask, const int32_t* u, int64_t n,
+                        float alpha, float lambda, double* loss_host) {
+    POI_TRY(begin_call(e));
+    if (d <= 0 || d % 4) POI_FAIL(e, "d must be a positive multiple of 4");
+    if (n <= 0) { *loss_host = 0.0; return 0; }
+    // device copies: [p ; q] contiguous (the key vector of the lt segments), u, mask
+    int32_t *pq_dev = nullptr, *u_dev = nullptr, *m_dev = nullptr;
+    POI_TRY(arena_get(e, (size_t)2 * n, &pq_dev));
+    POI_TRY(arena_get(e, (size_t)n, &u_dev));
+    POI_TRY(arena_get(e, (size_t)n, &m_dev));
+    POI_TRY(stage_reserve(e, (size_t)n * 16 + 1024));
+    int32_t* st = reinterpret_cast<int32_t*>(e->h_stage);
+    memcpy(st, p, n * 4); memcpy(st + n, q, n * 4); memcpy(st + 2 * n, u, n * 4); memcpy(st + 3 * n, mask, n * 4);
+    POI_CK(e, cudaMemcpyAsync(pq_dev, st, (size_t)2 * n * 4, cudaMemcpyHostToDevice, e->stream));
+    POI_CK(e, cudaMemcpyAsync(u_dev, st + 2 * n, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    POI_CK(e, cudaMemcpyAsync(m_dev, st + 3 * n, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    float *GU = nullptr, *GPQ = nullptr; double *part = nullptr, *out_dev = nullptr;
+    POI_TRY(arena_get(e, (size_t)n * d, &GU));
+    POI_TRY(arena_get(e, (size_t)2 * n * d, &GPQ));
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(n, 8), (int64_t)e->num_sms * 8));
+    POI_TRY(arena_get(e, (size_t)blocks, &part));
+    POI_TRY(arena_get(e, 1, &out_dev));
+    SegList seg_u, seg_pq;
+    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(u_dev), n, (uint32_t)n_user, false, &seg_u));
+    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(pq_dev), 2 * n, (uint32_t)n_rows_lt, false, &seg_pq));
+    POI_CAT(e, CAT_MF, 0, (double)n * 3 * d * 4 * 2);
+    POI_LAUNCH(e, k_bpr_batch_grads, blocks, 256, 0, ux, lt, d / 4, u_dev, pq_dev, pq_dev + n, m_dev, n, GU, GPQ, part);
+    POI_LAUNCH(e, k_sum_partials_d, 1, 32, 0, part, blocks, out_dev, 1, 1);
+    RowSrc src; memset(&src, 0, sizeof(src));
+    src.mode = SRC_DENSE_GRADS; src.dim = d;
+    src.grads = GU;
+    POI_TRY(launch_rows_update(e, seg_u, ux, d, alpha, lambda, src, ROW_LONG_THRESH));
+    src.grads = GPQ;
+    POI_TRY(launch_rows_update(e, seg_pq, lt, d, alpha, lambda, src, ROW_LONG_THRESH));
+    POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    *loss_host = -e->h_out[0];
+    return 0;
 }
-int poi_geoie_train(poi_engine* e, const poi_geoie_params*, int32_t, const int32_t*, const int32_t*, int32_t,
-                    const float*, const float*, const int32_t*, int32_t, float, float, double*) {
-    POI_FAIL(e, "poi_geoie_train: not implemented yet");
+
+int poi_geoie_train(poi_engine* e, const poi_geoie_params* prm, int32_t uidx, const int32_t* p_row,
+                    const int32_t* q_row, int32_t lmax, const float* dist_pos, const float* dist_neg,
+                    const int32_t* msk, int32_t n, float alpha, float lambda, double* out_host) {
+    POI_TRY(begin_call(e));
+    if (!prm || !prm->g || !prm->h || !prm->z || !prm->t || !prm->ab) POI_FAIL(e, "geoie params: null pointer");
+    const int H = prm->H;
+    if (H <= 0 || H % 4) POI_FAIL(e, "n_hidden must be a positive multiple of 4");
+    if (n <= 0 || n + 1 > lmax) POI_FAIL(e, "bad n (%d) for lmax %d", n, lmax);
+    (void)uidx;     // t[uidx] receives an exactly-zero gradient (t.z cancels): its "update" is a no-op
+    const size_t nn = (size_t)n * n;
+    const void* hs[5] = {p_row, q_row, dist_pos, dist_neg, msk};
+    size_t bs[5] = {(size_t)lmax * 4, (size_t)lmax * 4, nn * 4, nn * 4, nn * 4};
+    void* ds[5];
+    // [p_row ; q_row] must be contiguous on the device: it is the key vector of the h/z segments
+    int32_t* pq_dev = nullptr;
+    POI_TRY(arena_get(e, (size_t)2 * lmax, &pq_dev));
+    POI_TRY(upload_many(e, hs, bs, 5, ds));
+    POI_CK(e, cudaMemcpyAsync(pq_dev, ds[0], (size_t)lmax * 4, cudaMemcpyDeviceToDevice, e->stream));
+    POI_CK(e, cudaMemcpyAsync(pq_dev + lmax, ds[1], (size_t)lmax * 4, cudaMemcpyDeviceToDevice, e->stream));
+    const int32_t* p_dev = pq_dev; const int32_t* q_dev = pq_dev + lmax;
+    const float* dpos = (const float*)ds[2]; const float* dneg = (const float*)ds[3]; const int32_t* mk = (const int32_t*)ds[4];
+    float *G, *Hp, *Hq, *GG, *GH, *GZ; double *CWp, *CWq, *per_i, *out_dev;
+    POI_TRY(arena_get(e, (size_t)n * H, &G)); POI_TRY(arena_get(e, (size_t)n * H, &Hp)); POI_TRY(arena_get(e, (size_t)n * H, &Hq));
+    POI_TRY(arena_get(e, (size_t)lmax * H, &GG));
+    POI_TRY(arena_get(e, (size_t)2 * lmax * H, &GH)); POI_TRY(arena_get(e, (size_t)2 * lmax * H, &GZ));
+    POI_TRY(arena_get(e, nn, &CWp)); POI_TRY(arena_get(e, nn, &CWq));
+    POI_TRY(arena_get(e, (size_t)n * 4, &per_i)); POI_TRY(arena_get(e, 1, &out_dev));
+    POI_CK(e, cudaMemsetAsync(GG, 0, (size_t)lmax * H * 4, e->stream));
+    POI_CK(e, cudaMemsetAsync(GH, 0, (size_t)2 * lmax * H * 4, e->stream));
+    POI_CK(e, cudaMemsetAsync(GZ, 0, (size_t)2 * lmax * H * 4, e->stream));
+    SegList seg_p, seg_pq;
+    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(p_dev), lmax, (uint32_t)prm->n_rows, false, &seg_p));
+    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(pq_dev), 2 * lmax, (uint32_t)prm->n_rows, false, &seg_pq));
+    POI_CAT(e, CAT_GEOIE, 0, 0);
+    unsigned gnh = (unsigned)poi_cdiv((int64_t)n * H, 256);
+    POI_LAUNCH(e, k_geoie_gather, gnh, 256, 0, prm->g, prm->h, p_dev, q_dev, n, H, G, Hp, Hq);
+    POI_LAUNCH(e, k_geoie_fwd, n, 128, (size_t)(2 * H + 20) * sizeof(double), G, Hp, Hq, n, H, dpos, dneg, mk, prm->ab, CWp, CWq, per_i);
+    POI_LAUNCH(e, k_geoie_bwd_h, n, 128, 0, G, Hp, Hq, n, H, CWp, CWq, lambda, lmax, GH);
+    POI_LAUNCH(e, k_geoie_bwd_g, n, 128, 0, G, Hp, Hq, n, H, CWp, CWq, lambda, GG);
+    POI_LAUNCH(e, k_geoie_zgrad, gnh, 256, 0, prm->z, p_dev, q_dev, n, H, lmax, lambda, GZ);
+    POI_LAUNCH(e, k_geoie_finalize, 1, 32, 0, per_i, n, prm->ab, alpha, out_dev);
+    // sparse updates: g[unique(p_full)], h/z[unique(p_full u q_full)] (GeoIE.py:147-153,174-181); the L2
+    // terms are already inside the occurrence gradients (they cover only the n gathered rows), so lambda = 0
+    RowSrc src; memset(&src, 0, sizeof(src));
+    src.mode = SRC_DENSE_GRADS; src.dim = H;
+    src.grads = GG; POI_TRY(launch_rows_update(e, seg_p, prm->g, H, alpha, 0.f, src, ROW_LONG_THRESH));
+    src.grads = GH; POI_TRY(launch_rows_update(e, seg_pq, prm->h, H, alpha, 0.f, src, ROW_LONG_THRESH));
+    src.grads = GZ; POI_TRY(launch_rows_update(e, seg_pq, prm->z, H, alpha, 0.f, src, ROW_LONG_THRESH));
+    POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    *out_host = e->h_out[0];
+    return 0;
 }
-int poi_score_topk(poi_engine* e, const float*, int32_t, const float*, int64_t, int32_t, const float*, float,
-                   int32_t, int32_t*) {
-    POI_FAIL(e, "poi_score_topk: not implemented yet");
+
+int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* items, int64_t n_item, int32_t H,
+                   const float* prob, float wd, int32_t top_k, int32_t* topk_dev) {
+    POI_TRY(begin_call(e));
+    if (B <= 0 || n_item <= 0) return 0;
+    if (H % 4) POI_FAIL(e, "H must be a multiple of 4");
+    if (top_k <= 0 || top_k > 256 || top_k > n_item) POI_FAIL(e, "top_k out of range");
+    const int chunk = (int)std::min<int64_t>(n_item, 8192);
+    const int lds = (chunk + 3) / 4 * 4;
+    float *S = nullptr, *best_val = nullptr;
+    POI_TRY(arena_get(e, (size_t)B * lds, &S));
+    POI_TRY(arena_get(e, (size_t)B * top_k, &best_val));
+    size_t smem = (size_t)(chunk + top_k) * 4 + (size_t)top_k * 4;
+    if (smem > 48 * 1024)
+        POI_CK(e, cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t i0 = 0; i0 < n_item; i0 += chunk) {
+        int cur = (int)std::min<int64_t>(chunk, n_item - i0);
+        POI_TRY(launch_gemm_tn(e, users, H, items + (size_t)i0 * H, H, B, cur, H, EpiScore{S, lds, prob, n_item, i0, wd, cur}));
+        POI_CAT(e, CAT_EVAL, 0, 0);
+        POI_LAUNCH(e, k_topk_merge, B, 256, smem, S, lds, cur, i0, top_k, best_val, topk_dev, i0 == 0 ? 1 : 0);
+    }
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    return 0;
 }
-}
+
+}  // extern "C"

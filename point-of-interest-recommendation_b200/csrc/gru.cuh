@@ -310,12 +310,22 @@ k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc
 
 // Final scalars + the scalar parameters' SGD step (wd, loss_weight; GRU_Spatial.py:210-211).
 // out[0..4] = los, sur, upq, w0, w1 (plain GRU: out[0] = upq)
-__global__ void k_finalize_gru(const double* __restrict__ part, int nblocks, float* scal, int head,
+__global__ void __launch_bounds__(256)
+k_finalize_gru(const double* __restrict__ part, int nblocks, float* scal, int head,
                                double extra_upq, double scale, float alpha, float lambda,
                                double* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // fixed-shape tree over the block partials: thread t sums entries t, t+256, ... then a fixed
+    // shuffle/shared tree -> deterministic for a given grid size
+    __shared__ double sh[8][3];
+    double s3[3] = {0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += 256)
+        for (int k = 0; k < 3; ++k) s3[k] += part[(size_t)i * 4 + k];
+    for (int k = 0; k < 3; ++k) s3[k] = warp_sum_d(s3[k]);
+    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) sh[threadIdx.x >> 5][k] = s3[k];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     double sur = 0.0, bpr = 0.0, gwd = 0.0;
-    for (int i = 0; i < nblocks; ++i) { sur += part[(size_t)i * 4]; bpr += part[(size_t)i * 4 + 1]; gwd += part[(size_t)i * 4 + 2]; }
+    for (int w = 0; w < 8; ++w) { sur += sh[w][0]; bpr += sh[w][1]; gwd += sh[w][2]; }
     double upq = -bpr + extra_upq;
     if (!head) { out[0] = upq; out[1] = 0.0; out[2] = upq; out[3] = 0.0; out[4] = 1.0; return; }
     float a = scal[1], b = scal[2], mx = fmaxf(a, b);
@@ -495,7 +505,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
         POI_TRY(launch_reduce_update(e, g_bs, p->bs, nD, 1, nD, alpha, lambda));
     }
     POI_CAT(e, CAT_REDUCE, 0, 0);
-    POI_LAUNCH(e, k_finalize_gru, 1, 32, 0, part, loss_blocks, p->scal, head ? 1 : 0,
+    POI_LAUNCH(e, k_finalize_gru, 1, 256, 0, part, loss_blocks, p->scal, head ? 1 : 0,
                (double)n_nonempty * 0.6931471805599453, (double)scale, alpha, lambda, out_dev);
     phase_mark(e, 6);
 

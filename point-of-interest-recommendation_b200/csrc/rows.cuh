@@ -194,17 +194,40 @@ k_rows_update_warp(SegList seg, float* __restrict__ table, int dim4, float alpha
     }
 }
 
-// long segments: one CTA per listed segment; warp w sums occurrences s0+w, s0+w+8, ...;
-// the 8 partial rows are then added in warp order.  Fixed order -> deterministic.
+// long segments (hot rows: the pad row, popular POIs, every distance interval): split into chunks of
+// ROW_CHUNK occurrences; one CTA reduces one chunk to a partial row (warp w takes occurrences
+// w, w+8, ... of the chunk, the 8 warp rows are then added in warp order), a second kernel adds the
+// chunk partials of a segment in chunk order and applies the SGD step.  Fixed order -> deterministic.
+constexpr int ROW_CHUNK = 256;
+
+__global__ void k_long_offsets(SegList seg, const uint32_t* __restrict__ long_list,
+                               const uint32_t* __restrict__ long_count, uint32_t* __restrict__ chunk_off) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t nl = *long_count;
+    uint32_t run = 0;
+    for (uint32_t li = 0; li < nl; ++li) {
+        chunk_off[li] = run;
+        uint32_t sg = long_list[li];
+        run += (seg.seg_start[sg + 1] - seg.seg_start[sg] + ROW_CHUNK - 1) / ROW_CHUNK;
+    }
+    chunk_off[nl] = run;
+}
+
 __global__ void __launch_bounds__(256)
-k_rows_update_long(SegList seg, float* __restrict__ table, int dim4, float alpha, float lambda,
-                   RowSrc src, const uint32_t* long_list, const uint32_t* long_count) {
+k_long_partial(SegList seg, int dim4, RowSrc src, const uint32_t* __restrict__ long_list,
+               const uint32_t* __restrict__ long_count, const uint32_t* __restrict__ chunk_off,
+               float4* __restrict__ partial) {
     extern __shared__ float4 s_part[];          // [8][dim4]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nl = *long_count;
-    for (uint32_t li = blockIdx.x; li < nl; li += gridDim.x) {
-        const uint32_t sg = long_list[li];
-        const uint32_t s0 = seg.seg_start[sg], s1 = seg.seg_start[sg + 1];
+    const uint32_t total = chunk_off[nl];
+    for (uint32_t ch = blockIdx.x; ch < total; ch += gridDim.x) {
+        // locate the long entry that owns global chunk ch (binary search over chunk_off)
+        uint32_t lo = 0, hi = nl;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (chunk_off[mid] <= ch) lo = mid; else hi = mid; }
+        const uint32_t sg = long_list[lo];
+        const uint32_t s0 = seg.seg_start[sg] + (ch - chunk_off[lo]) * ROW_CHUNK;
+        const uint32_t s1 = min(s0 + ROW_CHUNK, seg.seg_start[sg + 1]);
         for (int c0 = 0; c0 < dim4; c0 += 32) {
             int c = c0 + lane;
             float4 acc = f4zero();
@@ -218,18 +241,34 @@ k_rows_update_long(SegList seg, float* __restrict__ table, int dim4, float alpha
             if (c < dim4) s_part[w * dim4 + c] = acc;
         }
         __syncthreads();
-        float* row = table + (size_t)seg.uniq[sg] * dim4 * 4;
-        const float lc = lambda * (float)(s1 - s0);
         for (int c = threadIdx.x; c < dim4; c += blockDim.x) {
             float4 a = s_part[c];
 #pragma unroll
             for (int ww = 1; ww < 8; ++ww) a = f4add(a, s_part[ww * dim4 + c]);
+            partial[(size_t)ch * dim4 + c] = a;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_long_final(SegList seg, float* __restrict__ table, int dim4, float alpha, float lambda,
+             const uint32_t* __restrict__ long_list, const uint32_t* __restrict__ long_count,
+             const uint32_t* __restrict__ chunk_off, const float4* __restrict__ partial) {
+    const uint32_t nl = *long_count;
+    for (uint32_t li = blockIdx.x; li < nl; li += gridDim.x) {
+        const uint32_t sg = long_list[li];
+        const uint32_t c0 = chunk_off[li], c1 = chunk_off[li + 1];
+        float* row = table + (size_t)seg.uniq[sg] * dim4 * 4;
+        const float lc = lambda * (float)(seg.seg_start[sg + 1] - seg.seg_start[sg]);
+        for (int c = threadIdx.x; c < dim4; c += blockDim.x) {
+            float4 a = f4zero();
+            for (uint32_t ch = c0; ch < c1; ++ch) a = f4add(a, partial[(size_t)ch * dim4 + c]);
             float4 r = ld4(row + 4 * c);
             r.x -= alpha * (a.x + lc * r.x); r.y -= alpha * (a.y + lc * r.y);
             r.z -= alpha * (a.z + lc * r.z); r.w -= alpha * (a.w + lc * r.w);
             st4(row + 4 * c, r);
         }
-        __syncthreads();
     }
 }
 
@@ -250,8 +289,17 @@ static int launch_rows_update(poi_engine* e, const SegList& seg, float* table, i
     else if (dim4 <= 128) POI_LAUNCH(e, (k_rows_update_warp<4>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
     else if (dim4 <= 256) POI_LAUNCH(e, (k_rows_update_warp<8>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
     else POI_FAIL(e, "row dim %d too large (max 1024)", dim);
+    // long segments: chunk partials, then ordered final sum
+    const size_t max_long = (size_t)seg.n / (size_t)std::max(long_thresh, 1) + 2;
+    const size_t max_chunks = (size_t)seg.n / ROW_CHUNK + max_long + 2;
+    uint32_t* chunk_off = nullptr; float4* partial = nullptr;
+    POI_TRY(arena_get(e, max_long + 1, &chunk_off));
+    POI_TRY(arena_get(e, max_chunks * dim4, &partial));
+    POI_LAUNCH(e, k_long_offsets, 1, 32, 0, seg, long_list, long_count, chunk_off);
     size_t smem = (size_t)8 * dim4 * sizeof(float4);
-    unsigned lgrid = (unsigned)std::min<int64_t>(seg.n, (int64_t)e->num_sms * 4);
-    POI_LAUNCH(e, k_rows_update_long, lgrid, 256, smem, seg, table, dim4, alpha, lambda, src, long_list, long_count);
+    unsigned lgrid = (unsigned)std::min<int64_t>((int64_t)max_chunks, (int64_t)e->num_sms * 8);
+    POI_LAUNCH(e, k_long_partial, lgrid, 256, smem, seg, dim4, src, long_list, long_count, chunk_off, partial);
+    unsigned fgrid = (unsigned)std::min<int64_t>((int64_t)max_long, (int64_t)e->num_sms * 8);
+    POI_LAUNCH(e, k_long_final, fgrid, 128, 0, seg, table, dim4, alpha, lambda, long_list, long_count, chunk_off, partial);
     return 0;
 }
