@@ -109,7 +109,7 @@ def obo_gru_train(state, p, q, mask, alpha, lam, dtype=F64, dense=False):
         new["lt"] = lt_new
     else:
         new["lt"], _ = _unique_rows_update(state["lt"], np.concatenate((p, q)), rows.grad, alpha)
-    return float(-upq), new
+    return float(-upq.detach()), new
 
 
 # ----------------------------------------------------------------------------------------------
@@ -142,7 +142,7 @@ def gru_train_batch(state, P, Q, M, alpha, lam, dtype=F64):
     for k, par in (("ui", ui), ("wh", wh), ("bi", bi)):
         new[k] = _np(par - alpha * par.grad).astype(state[k].dtype)
     new["lt"], _ = _unique_rows_update(state["lt"], idx_cat, rows.grad, alpha)
-    return float(-tot), new
+    return float(-tot.detach()), new
 
 
 # ----------------------------------------------------------------------------------------------
@@ -193,7 +193,7 @@ def obo_spatial_gru_train(state, p, q, dp, dq, mask, alpha, lam, dtype=F64, dens
     else:
         new["lt"], _ = _unique_rows_update(state["lt"], np.concatenate((p, q)), rows.grad, alpha)
         new["di"], _ = _unique_rows_update(state["di"], dp, xds.grad, alpha)
-    return (float(los), float(sur), float(upq), _np(ls).astype(np.float64)), new
+    return (float(los.detach()), float(sur.detach()), float(upq.detach()), _np(ls).astype(np.float64)), new
 
 
 def spatial_gru_train_batch(state, P, Q, DP, DQ, M, alpha, lam, dtype=F64):
@@ -243,7 +243,7 @@ def spatial_gru_train_batch(state, P, Q, DP, DQ, M, alpha, lam, dtype=F64):
         new[k] = _np(par - alpha * par.grad).astype(np.asarray(state[k]).dtype)
     new["lt"], _ = _unique_rows_update(state["lt"], idx_cat, rows.grad, alpha)
     new["di"], _ = _unique_rows_update(state["di"], DP.reshape(-1), drows.grad, alpha)
-    return (float(los), float(sur), float(upq), _np(ls).astype(np.float64)), new
+    return (float(los.detach()), float(sur.detach()), float(upq.detach()), _np(ls).astype(np.float64)), new
 
 
 # ----------------------------------------------------------------------------------------------
@@ -301,7 +301,7 @@ def obo_bpr_train(state, uidx, pq, alpha, lam, dtype=F64):
     ux = state["ux"].copy(); ux[uidx] = _np(usr - alpha * usr.grad).astype(ux.dtype)
     new["ux"] = ux
     new["lt"] = _last_writer_set(state["lt"], pq, _np(xpq - alpha * xpq.grad).astype(state["lt"].dtype))
-    return float(-upq), new
+    return float(-upq.detach()), new
 
 
 def bpr_train_batch(state, pidx, qidx, mask, uidxs, alpha, lam, dtype=F64):
@@ -321,7 +321,7 @@ def bpr_train_batch(state, pidx, qidx, mask, uidxs, alpha, lam, dtype=F64):
     # set back per occurrence (identical values for duplicates).
     new["ux"], _ = _unique_rows_update(state["ux"], uidxs, users.grad, alpha)
     new["lt"], _ = _unique_rows_update(state["lt"], np.concatenate((pidx, qidx)), rows.grad, alpha)
-    return float(-upq), new
+    return float(-upq.detach()), new
 
 
 # ----------------------------------------------------------------------------------------------
@@ -351,7 +351,7 @@ def obo_prme_train(state, uidx, pq, dist, gap, alpha, lam, thd, cw, dtype=F64):
     new["du"] = tab
     new["dp"] = _last_writer_set(state["dp"], pq, _np(dppq + alpha * dppq.grad).astype(state["dp"].dtype))
     new["ds"] = _last_writer_set(state["ds"], pq, _np(dspq + alpha * g_ds).astype(state["ds"].dtype))
-    return float(upq), new
+    return float(upq.detach()), new
 
 
 # ----------------------------------------------------------------------------------------------
@@ -400,7 +400,7 @@ def geoie_train(state, uidx, p_full, q_full, dist_pos, dist_neg, msk, alpha, lam
     tg = tu.grad if tu.grad is not None else torch.zeros_like(tu)
     tt = state["t"].copy(); tt[uidx] = _np(tu - alpha * tg).astype(tt.dtype)
     new["t"] = tt
-    return float(loss), new
+    return float(loss.detach()), new
 
 
 # ----------------------------------------------------------------------------------------------

@@ -114,3 +114,39 @@ def init_state(n_item, d, H, dist_num=None, seed=123, n_user=None):
         st["wd"] = np.float64(rs.uniform(0, 0.5))
         st["loss_weight"] = u(2)
     return st
+
+
+def write_sequence_file(path, n_user, n_item, min_len=6, max_len=20, seed=123):
+    """A synthetic dataset in the reference's on-disk sequence format
+    (poidata/extract_whole_user_buys.py:81-90): space separated columns
+    check_times pois_different u_id u_pois u_times u_coordinates, fields joined by '/',
+    coordinates as 'lat,lon'.  Every POI id occurs at least once so that the loaders' alias table has
+    exactly n_item entries."""
+    rs = np.random.RandomState(seed)
+    lat = rs.uniform(1.22, 1.47, n_item)
+    lon = rs.uniform(103.60, 104.04, n_item)
+    rows = []
+    pool = list(rs.permutation(n_item))
+    for u in range(n_user):
+        L = int(rs.randint(min_len, max_len + 1))
+        seq = [int(pool.pop()) if pool else int(rs.randint(0, n_item)) for _ in range(L)]
+        for t in range(1, L):
+            if rs.rand() < 0.15:
+                seq[t] = seq[rs.randint(0, t)]
+        t0 = 1.3e9 / 60.0
+        times = np.cumsum(rs.randint(5, 900, size=L)) + t0          # minutes
+        rows.append((L, '%0.2f' % (len(set(seq)) / L), 'u%d' % u,
+                     '/'.join('p%d' % i for i in seq),
+                     '/'.join('%d' % t for t in times),
+                     '/'.join('%.6f,%.6f' % (lat[i], lon[i]) for i in seq)))
+    used = set(int(x[1:]) for r in rows for x in r[3].split('/'))
+    for i in sorted(set(range(n_item)) - used):                    # POIs not visited yet: append to random users
+        u = rs.randint(0, n_user)
+        L, pd_, uid, ps, ts, cs = rows[u]
+        last_t = int(ts.split('/')[-1]) + int(rs.randint(5, 900))
+        rows[u] = (L + 1, pd_, uid, ps + '/p%d' % i, ts + '/%d' % last_t, cs + '/%.6f,%.6f' % (lat[i], lon[i]))
+    with open(path, 'w') as f:
+        f.write('check_times pois_different u_id u_pois u_times u_coordinates\n')
+        for r in rows:
+            f.write(' '.join(str(x) for x in r) + '\n')
+    return path

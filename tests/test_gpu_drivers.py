@@ -1,0 +1,117 @@
+"""The ported drivers end to end on a synthetic dataset in the reference's on-disk format: loader ->
+model classes -> engine -> Valuate.  For Distance2Pre and the GRU the per-epoch loss (+ l2) and
+Recall@K are compared with the same loop run on the CPU oracle (identical injected initial arrays,
+identical negatives and user order)."""
+import random
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from oracle import driver as OD
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _dataset(tmp_path, n_user=24, n_item=60):
+    import poi_b200  # noqa: F401
+    from poi_b200 import synth
+    d = tmp_path / "Synth" / "sequence"
+    d.mkdir(parents=True)
+    synth.write_sequence_file(str(d / "Synth.txt"), n_user, n_item, 6, 12, seed=11)
+    return str(d)
+
+
+def _oracle_recall(scores, tes, at_nums):
+    ranks = np.argsort(-scores, axis=1, kind="stable")
+    return [float(np.mean([tes[u][0] in ranks[u, :k] for u in range(len(tes))])) for k in at_nums]
+
+
+@pytest.mark.parametrize("gru", [1, 2])
+def test_driver_matches_oracle_loop(engine, tmp_path, gru):
+    from poi_b200 import prog_bpr_gru_spatial as drv
+    from poi_b200 import synth
+    from poi_b200.driver_common import shuffled_users
+    path = _dataset(tmp_path)
+    p = drv.default_params()
+    p.update(dataset="Synth.txt", epochs=2, latent_size=8, gru=gru, at_nums=[5, 10], batch_size_test=7, UD=40, dd=2000)
+    random.seed(5)
+    pas = drv.Params(p=p, path=path)
+    D = pas.dist_num
+    st = synth.init_state(pas.item_num, 8, 8, D if gru == 2 else None, seed=3)
+    tra_neg0 = [list(r) for r in pas.tra_buys_neg_masks]
+    rstate = random.getstate()
+    import os
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        model, best, hist = drv.train_valid_or_test(pas, init=st)
+    finally:
+        os.chdir(cwd)
+    # ---- the same two epochs on the oracle ----
+    random.setstate(rstate)
+    from poi_b200.public import Load_Data_by_length as LD
+    P, M = np.asarray(pas.tra_buys_masks), np.asarray(pas.tra_masks)
+    DP = np.asarray(pas.tra_dist_masks)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    Q = np.asarray(tra_neg0)
+    DQ = np.asarray(pas.tra_dist_neg_masks)
+    for epoch in range(2):
+        if epoch > 0:
+            Q = np.asarray(LD.fun_random_neg_masks_tra(pas.item_num, pas.tra_buys_masks))
+            LD.fun_random_neg_masks_tes(pas.item_num, pas.tra_buys_masks, pas.tes_buys_masks)   # consumes RNG like the driver
+            DQ = np.asarray(LD.fun_compute_dist_neg(pas.tra_buys_masks, pas.tra_masks, Q.tolist(), pas.pois_cordis, p['dd'], D))
+        order = shuffled_users(pas.user_num, epoch)
+        if gru == 2:
+            loss, l2, ref = OD.epoch_distance2pre(ref, order, P, Q, DP, DQ, M, p['alpha'], p['lambda'])
+            scores = OD.user_scores_distance2pre(ref, P, M, DP, pas.ulptai, D)
+        else:
+            loss, l2, ref = OD.epoch_gru(ref, order, P, Q, M, p['alpha'], p['lambda'])
+            scores = OD.user_scores_gru(ref, P, M)
+        assert_close(hist[epoch]["loss"], loss, 1e-4, "epoch %d loss" % epoch)
+        assert_close(hist[epoch]["l2"], l2, 1e-4, "epoch %d l2" % epoch)
+        rec = _oracle_recall(scores, pas.tes_buys_masks, p['at_nums'])
+        assert np.allclose(hist[epoch]["recall"], rec, atol=1e-12), (hist[epoch]["recall"], rec)
+    assert hist[1]["loss"] < hist[0]["loss"]
+
+
+def test_bpr_prme_geoie_drivers_run(engine, tmp_path):
+    from poi_b200 import prog_bpr_gru_spatial as d0
+    from poi_b200 import prog_geoie as d2
+    from poi_b200 import prog_prme as d1
+    path = _dataset(tmp_path)
+    import os
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        p = d0.default_params(); p.update(dataset="Synth.txt", epochs=3, latent_size=8, gru=0, at_nums=[5, 10])
+        random.seed(1)
+        _, _, h0 = d0.train_valid_or_test(d0.Params(p=p, path=path))
+        assert h0[-1]["loss"] < h0[0]["loss"]
+        p = d1.default_params(); p.update(dataset="Synth.txt", epochs=2, latent_size=8, at_nums=[5, 10], batch_size_test=6)
+        random.seed(1)
+        _, _, h1 = d1.train_valid_or_test(d1.Params(p=p, path=path))
+        assert np.isfinite(h1[-1]["loss"]) and h1[-1]["loss"] > h1[0]["loss"]      # PRME ascends log sigmoid
+        p = d2.default_params(); p.update(dataset="Synth.txt", epochs=2, latent_size=8, at_nums=[5, 10], batch_size_test=6)
+        random.seed(1); np.random.seed(4)
+        pas = d2.Params(p=p, path=path)
+        _, _, h2 = d2.train_valid_or_test(pas, init=dict(a=0.3, b=0.2))
+        assert np.isfinite(h2[-1]["loss"])
+    finally:
+        os.chdir(cwd)
+
+
+def test_checkpoint_roundtrip(engine, tmp_path):
+    """The 9-array pickle (prog_bpr_gru_spatial.py:323-330) written and read back."""
+    from poi_b200 import prog_bpr_gru_spatial as drv
+    path = _dataset(tmp_path)
+    p = drv.default_params(); p.update(dataset="Synth.txt", epochs=1, latent_size=8, gru=2, dd=2000)
+    random.seed(2)
+    pas = drv.Params(p=p, path=path)
+    m1, _ = pas.build_model_one_by_one(2)
+    m1.train(0)
+    f = str(tmp_path / "model" / "ck")
+    drv.save_checkpoint(m1, f)
+    m2, _ = pas.build_model_one_by_one(2)
+    drv.load_checkpoint(m2, f)
+    for k in ("loss_weight", "wd", "lt", "di", "ui", "wh", "bi", "vs", "bs"):
+        assert np.array_equal(np.asarray(getattr(m1, k).get_value(), dtype=np.float32), np.asarray(getattr(m2, k).get_value(), dtype=np.float32)), k

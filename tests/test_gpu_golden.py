@@ -1,0 +1,95 @@
+"""The CUDA path against the committed golden vectors (tests/golden/*.npz): per-call losses and the
+final parameter state after a short trajectory, 1e-4 relative (fp32 device arithmetic, float64 goldens)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+A, L, RTOL = 0.01, 0.001, 1e-4
+
+
+def _load(name):
+    z = np.load(os.path.join(G, name + ".npz"))
+    init = {k[5:]: np.asarray(z[k]) for k in z.files if k.startswith("init_")}
+    final = {k[6:]: np.asarray(z[k], dtype=np.float64) for k in z.files if k.startswith("final_")}
+    return z, init, final
+
+
+def _test_side(n_user, n_item):
+    tes = [[n_item]] * n_user
+    return [tes, [[0]] * n_user, tes]
+
+
+@pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape"])
+def test_gru_golden(engine, name):
+    from poi_b200.public.GRU import Gru, OboGru
+    z, init, final = _load(name)
+    P, Q, M, B = z["P"], z["Q"], z["M"], int(z["batch"])
+    n_user, n_item, d = P.shape[0], init["lt"].shape[0] - 1, init["lt"].shape[1]
+    cls = OboGru if B == 0 else Gru
+    m = cls([P, M, Q], _test_side(n_user, n_item), [A, L], n_user, n_item, d, d, init=init)
+    if B == 0:
+        losses = [m.train(int(u)) for u in z["order"]]
+    else:
+        losses = [m.train(np.arange(s, min(s + B, n_user), dtype=np.int32)) for s in range(0, n_user, B)]
+    assert_close(losses, z["losses"], RTOL, "losses")
+    for k in ("lt", "ui", "wh", "bi"):
+        assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
+
+
+@pytest.mark.parametrize("name", ["obo_spatial_tiny", "obo_spatial_d20_D200", "spatial_batch4"])
+def test_spatial_golden(engine, name):
+    from poi_b200.public.GRU_Spatial import OboSpatialGru, SpatialGru
+    z, init, final = _load(name)
+    P, Q, M, DP, DQ, B, nD = z["P"], z["Q"], z["M"], z["DP"], z["DQ"], int(z["batch"]), int(z["n_dist"])
+    n_user, n_item, d = P.shape[0], init["lt"].shape[0] - 1, init["lt"].shape[1]
+    cls = OboSpatialGru if B == 0 else SpatialGru
+    m = cls([P, M, Q], _test_side(n_user, n_item), [DP, [[nD]] * n_user, DQ], [A, L], n_user, n_item, [nD, 0.2], d, d, init=init)
+    outs = []
+    if B == 0:
+        for u in z["order"]:
+            los, sur, upq, w = m.train(int(u)); outs.append([los, sur, upq, w[0], w[1]])
+    else:
+        for s in range(0, n_user, B):
+            los, sur, upq, w = m.train(np.arange(s, min(s + B, n_user), dtype=np.int32)); outs.append([los, sur, upq, w[0], w[1]])
+    assert_close(outs, z["outs"], RTOL, "outs")
+    for k in ("lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"):
+        assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
+    m.update_trained_items(); m.update_trained_dists()
+    hts, sts = m.predict(np.arange(n_user, dtype=np.int32))
+    assert_close(hts, z["hts"], RTOL, "hts"); assert_close(sts, z["sts"], RTOL, "sts")
+
+
+def test_mf_geoie_golden(engine):
+    from poi_b200.public.BPR import OboBpr
+    from poi_b200.public.GeoIE import GeoIE
+    from poi_b200.public.PRME import OboPrme
+    z, init, final = _load("obo_bpr_tiny")
+    n_user, n_item, d = init["ux"].shape[0], int(z["n_item"]), init["ux"].shape[1]
+    t = _test_side(n_user, n_item)
+    m = OboBpr([t[0], t[1], t[2]], t, [A, L], n_user, n_item, d, d, init=init)
+    c = z["calls"]
+    assert_close(m.train_sequence(c[:, 0], c[:, 1], c[:, 2]), z["losses"], RTOL, "bpr losses")
+    for k in ("ux", "lt"):
+        assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
+    z, init, final = _load("obo_prme_tiny")
+    n_user, n_item, d = init["du"].shape[0], int(z["n_item"]), init["du"].shape[1]
+    t = _test_side(n_user, n_item)
+    m = OboPrme([t[0], t[1], [[0.0]] * n_user, t[1], t[2]], [t[0], t[1], [[0.0]] * n_user, t[1], t[2]], [A, L], 360, 0.2,
+                np.zeros((n_item + 1, 2)), n_user, n_item, d, init=init)
+    c = z["calls"]
+    assert_close(m.train_sequence(c[:, 0], c[:, 1], c[:, 2], c[:, 3], c[:, 4], c[:, 5]), z["losses"], RTOL, "prme losses")
+    for k in ("du", "dp", "ds"):
+        assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
+    z, init, final = _load("geoie_tiny")
+    P, Q, M = z["P"], z["Q"], z["M"]
+    n_user, n_item, H = P.shape[0], init["g"].shape[0] - 1, init["g"].shape[1]
+    m = GeoIE([P, Q, np.ones_like(P), M], [[[n_item]] * n_user] * 2, [A, L], n_user, n_item, H, H, None, init=init)
+    losses = [m.train(int(u), z["dpos%d" % k], z["dneg%d" % k], z["msk%d" % k]) for k, u in enumerate(z["order"])]
+    assert_close(losses, z["losses"], RTOL, "geoie losses")
+    for k in ("g", "h", "z", "t"):
+        assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
