@@ -45,7 +45,9 @@ def shuffled_users(user_num, epoch):
     return idx
 
 
-def results_dir(script_file, data_path):
+def results_dir(script_file, data_path, p=None):
+    if p is not None and p.get('results_dir'):
+        return p['results_dir']
     return os.path.join(os.path.split(os.path.abspath(script_file))[0], '..', 'Results_best_and_losses',
                         data_path.rstrip('/').split('/')[-2] if '/' in data_path.rstrip('/') else 'data')
 

@@ -215,7 +215,7 @@ def train_valid_or_test(pas, init=None, device=None):
         history.append(dict(epoch=int(epoch), loss=float(loss), l2=float(rnn_l2_sqr), recall=res["recall"].tolist(), auc=float(res["auc"])))
         if epoch == p['epochs'] - 1:
             print("\tBest and losses saving ...")
-            path = results_dir(__file__, pas.path)
+            path = results_dir(__file__, pas.path, p)
             fun_save_best_and_losses(path, model_name, epoch, p, best, losses)
             if 2 == p['gru']:
                 fil_name = 'size' + str(p['latent_size']) + 'UD' + str(p['UD']) + 'dd' + str(p['dd']) + 'loss.txt'

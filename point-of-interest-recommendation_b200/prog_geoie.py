@@ -123,7 +123,7 @@ def train_valid_or_test(pas, init=None, device=None):
         history.append(dict(epoch=int(epoch), loss=float(loss), l2=float(rnn_l2_sqr), recall=res["recall"].tolist()))
         if epoch == p['epochs'] - 1:
             print("\tBest and losses saving ...")
-            fun_save_best_and_losses(results_dir(__file__, pas.path), model_name, epoch, p, best, losses)
+            fun_save_best_and_losses(results_dir(__file__, pas.path, p), model_name, epoch, p, best, losses)
     for i in p.items():
         print(i)
     print('\t the current Class name is: {val}'.format(val=model_name))
