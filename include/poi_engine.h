@@ -80,6 +80,13 @@ int poi_scatter_sgd(poi_engine* e, float* table_dev, int64_t n_rows, int dim,
                     const int32_t* idx_dev, int64_t n, const float* grad_dev,
                     float alpha, float lambda);
 
+/* C[m, n] = sum_k A[m*lda + k] * W[n*ldw + k] (+ bias[n]) -- the dense contraction every
+ * `T.dot(ui, x)`, `T.dot(wh, h)`, `T.dot(vs, h)` of the reference lowers to (GRU.py:346-350,
+ * GRU_Spatial.py:173-180), batched over rows.  mode as in poi_set_gemm_mode (0 fp32 FMA, 1 tcgen05
+ * 3xTF32, 2 tcgen05 1xTF32).  Exposed so the tensor-core kernels can be tested in isolation. */
+int poi_gemm_tn(poi_engine* e, const float* A_dev, int lda, const float* W_dev, int ldw,
+                int64_t M, int N, int K, const float* bias_dev, float* C_dev, int ldc, int mode);
+
 /* sum of squares of n floats, fp64 accumulation -- building block of `model.l2.eval()`
  * (GRU.py:305-309, GRU_Spatial.py:83-88, BPR.py:195-198, PRME.py:166-169, GeoIE.py:92-98). */
 int poi_sumsq(poi_engine* e, const float* x_dev, int64_t n, double* out_host);

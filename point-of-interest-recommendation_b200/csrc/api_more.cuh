@@ -135,6 +135,21 @@ int poi_geoie_train(poi_engine* e, const poi_geoie_params* prm, int32_t uidx, co
     return 0;
 }
 
+int poi_gemm_tn(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K,
+                const float* bias, float* C, int ldc, int mode) {
+    POI_TRY(begin_call(e));
+    if (mode < 0 || mode > 2) POI_FAIL(e, "bad gemm mode");
+    if ((K % 4) || (lda % 4) || (ldw % 4) || (ldc % 4)) POI_FAIL(e, "K, lda, ldw, ldc must be multiples of 4");
+    int saved = e->gemm_mode;
+    e->gemm_mode = mode;
+    int rc = gemm_tn(e, A, lda, W, ldw, M, N, K, EpiBiasStore{C, ldc, bias, N});
+    e->gemm_mode = saved;
+    if (rc) return rc;
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    return 0;
+}
+
 int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* items, int64_t n_item, int32_t H,
                    const float* prob, float wd, int32_t top_k, int32_t* topk_dev) {
     POI_TRY(begin_call(e));

@@ -1,13 +1,265 @@
-// gemm_tc.cuh -- tcgen05 (5th-gen tensor core) GEMM path, gemm modes 1 (3xTF32) and 2 (1xTF32).
-// Placeholder until the UMMA kernel lands: reports "unsupported" so gemm_tn() falls back to the
-// fp32 FMA kernel in gemm_simt.cuh.
+// gemm_tc.cuh -- tcgen05 (5th-gen tensor core) GEMM:  C[m,n] = sum_k A[m*lda+k] * W[n*ldw+k]
+//
+// fp32 operands in global memory, TF32 tensor-core products, fp32 accumulation in TMEM.
+//   mode 1 (SPLIT3): error-compensated 3xTF32.  Each fp32 x is split while it is staged into shared
+//                    memory into hi = rn_tf32(x) and lo = rn_tf32(x - hi), and
+//                    D += A_lo.W_hi + A_hi.W_lo + A_hi.W_hi  -> ~2^-21 relative error, fp32-faithful.
+//   mode 2         : single-pass TF32 (the tensor core truncates the fp32 words itself).
+//
+// One CTA = one 128 x BN output tile: all 8 warps stage 128x32 / BNx32 fp32 tiles (global -> regs ->
+// split -> 128B-swizzled K-major shared memory, the canonical UMMA layout), one elected thread issues
+// tcgen05.mma (M=128, N=BN, K=8 per instruction), tcgen05.commit releases the stage through an
+// mbarrier; the epilogue reads the accumulator with tcgen05.ld (32 lanes x 16 columns per warp) and
+// calls the same fused epilogue functors as the FMA path (gemm_simt.cuh / gru.cuh).
 #pragma once
 #include "common.cuh"
 
-static inline bool tc_gemm_supported(int64_t, int, int, int, int) { return false; }
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//  [0,14) start>>4 | [16,30) LBO>>4 (=1, unused when swizzled) | [32,46) SBO>>4 (1024 B between 8-row
+//  groups) | [46,48) version=1 | [61,64) layout type 2 = SWIZZLE_128B.  Tile base 1024-B aligned.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: c=F32 (bit 4), a=b=TF32 (2 at bits 7, 10), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// round-to-nearest TF32 (low 13 mantissa bits zero): what the tensor core then reads exactly
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
+    hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+    lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+}
+
+constexpr int BM = 128;
+constexpr int BK = 32;            // 32 fp32 = 128 B = one swizzle row
+constexpr int THREADS = 256;
+
+template <int BN, bool SPLIT3>
+struct Cfg {
+    static constexpr int STAGES = SPLIT3 ? 3 : 4;
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int W_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (SPLIT3 ? 2 : 1);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int LA = BM * 8 / THREADS;     // 16-byte chunks per thread, A tile
+    static constexpr int LW = BN * 8 / THREADS;     // W tile
+};
+
+template <int BN, bool SPLIT3, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+             int M, int N, int K, Epi epi) {
+    using C = Cfg<BN, SPLIT3>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t mbar_empty[C::STAGES];
+    __shared__ uint64_t mbar_done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::STAGES; ++s) mbar_init(&mbar_empty[s], 1);
+        mbar_init(&mbar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    float4 ra[C::LA], rw[C::LW];
+    auto gload = [&](int kb) {
+        const int k0 = kb * BK;
+#pragma unroll
+        for (int i = 0; i < C::LA; ++i) {
+            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + row < M && k0 + c * 4 < K) v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + k0 + c * 4);
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < C::LW; ++i) {
+            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + row < N && k0 + c * 4 < K) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * ldw + k0 + c * 4));
+            rw[i] = v;
+        }
+    };
+    auto sstore = [&](int s) {
+        const uint32_t sA = sbase + s * C::STAGE_BYTES, sW = sA + C::A_BYTES;
+        const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
+#pragma unroll
+        for (int i = 0; i < C::LA; ++i) {
+            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
+            uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);        // Swizzle<3,4,3>
+            float4 v = ra[i];
+            if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); sts4(sA + off, hi); sts4(sAl + off, lo); }
+            else sts4(sA + off, v);
+        }
+#pragma unroll
+        for (int i = 0; i < C::LW; ++i) {
+            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
+            uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+            float4 v = rw[i];
+            if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); sts4(sW + off, hi); sts4(sWl + off, lo); }
+            else sts4(sW + off, v);
+        }
+    };
+
+    const int KB = (K + BK - 1) / BK;
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    gload(0);
+    for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % C::STAGES;
+        if (kb >= C::STAGES) mbar_wait(&mbar_empty[s], ((kb / C::STAGES) - 1) & 1);   // MMAs that read this stage are done
+        sstore(s);
+        if (kb + 1 < KB) gload(kb + 1);
+        fence_async_smem();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t sA = sbase + s * C::STAGE_BYTES, sW = sA + C::A_BYTES;
+            const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
+            const uint64_t dA = make_sdesc(sA), dW = make_sdesc(sW);
+            uint32_t acc = kb > 0 ? 1u : 0u;
+            if (SPLIT3) {
+                const uint64_t dAl = make_sdesc(sAl), dWl = make_sdesc(sWl);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) { umma_tf32(tmem, dAl + 2 * k, dW + 2 * k, idesc, acc); acc = 1u; }
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem, dA + 2 * k, dWl + 2 * k, idesc, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) { umma_tf32(tmem, dA + 2 * k, dW + 2 * k, idesc, acc); acc = 1u; }
+            umma_commit(&mbar_empty[s]);
+            if (kb == KB - 1) umma_commit(&mbar_done);
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> fused functor ----
+    mbar_wait(&mbar_done, 0);
+    tc_fence_after();
+    const int row = m0 + (warp & 3) * 32 + lane;
+    const int cbeg = (warp >> 2) * (BN / 2);
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+        if (row < M) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = n0 + c0 + 4 * j;
+                if (n < N) { float q[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]}; epi(row, n, q); }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, BN);
+}
+
+}  // namespace tc
+
+static inline bool tc_gemm_supported(int64_t M, int N, int K, int lda, int ldw) {
+    return K >= 32 && (K % 4) == 0 && (lda % 4) == 0 && (ldw % 4) == 0 && M >= 32 && N >= 16 && M <= 0x7fffffffLL;
+}
+
+template <int BN, bool SPLIT3, class Epi>
+static int launch_tc_inst(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K, const Epi& epi) {
+    using C = tc::Cfg<BN, SPLIT3>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_tn_tc<BN, SPLIT3, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)poi_cdiv(N, BN), (unsigned)poi_cdiv(M, tc::BM));
+    POI_LAUNCH(e, (tc::k_gemm_tn_tc<BN, SPLIT3, Epi>), grid, tc::THREADS, C::SMEM_BYTES, A, lda, W, ldw, (int)M, N, K, epi);
+    return 0;
+}
 
 template <class Epi>
-static int launch_gemm_tn_tc(poi_engine* e, const float*, int, const float*, int, int64_t, int, int,
-                             const Epi&, bool) {
-    POI_FAIL(e, "tcgen05 GEMM path not built");
+static int launch_gemm_tn_tc(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K,
+                             const Epi& epi, bool split3) {
+    // 3xTF32 performs 3 MMAs per staged tile, 1xTF32 one: count what the tensor pipe executes
+    POI_CAT(e, CAT_GEMM, 2.0 * (double)M * N * K, 0);
+    const bool wide = poi_cdiv(M, tc::BM) * poi_cdiv(N, 128) >= e->num_sms;
+    if (split3) {
+        if (wide) return launch_tc_inst<128, true>(e, A, lda, W, ldw, M, N, K, epi);
+        return launch_tc_inst<64, true>(e, A, lda, W, ldw, M, N, K, epi);
+    }
+    if (wide) return launch_tc_inst<128, false>(e, A, lda, W, ldw, M, N, K, epi);
+    return launch_tc_inst<64, false>(e, A, lda, W, ldw, M, N, K, epi);
 }

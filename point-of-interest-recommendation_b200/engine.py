@@ -137,6 +137,16 @@ class Engine:
         self._ck(lib.poi_scatter_sgd(self._h, _dev_f32(table, "table"), table.shape[0], table.shape[1],
                                      _dev_i32(idx, "idx"), idx.numel(), _dev_f32(grad, "grad"), alpha, lam))
 
+    def gemm_tn(self, A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = None, mode: int = 0):
+        """C = A @ W.T (+ bias); A [M, K], W [N, K] float32 CUDA, row-major."""
+        M, K = A.shape
+        N = W.shape[0]
+        ldc = (N + 3) // 4 * 4
+        C = torch.empty((M, ldc), dtype=torch.float32, device=A.device)
+        self._ck(lib.poi_gemm_tn(self._h, _dev_f32(A, "A"), K, _dev_f32(W, "W"), K, M, N, K, _dev_f32(bias, "bias"),
+                                 C.data_ptr(), ldc, int(mode)))
+        return C[:, :N]
+
     def sumsq(self, x: torch.Tensor) -> float:
         out = c_double()
         self._ck(lib.poi_sumsq(self._h, _dev_f32(x, "x"), x.numel(), byref(out)))

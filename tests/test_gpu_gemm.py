@@ -1,0 +1,29 @@
+"""The GEMM kernels in isolation (poi_gemm_tn): fp32 FMA path (mode 0), tcgen05 3xTF32 (mode 1,
+fp32-faithful) and tcgen05 1xTF32 (mode 2) against a float64 reference."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 128, 32), (128, 64, 64), (256, 384, 256), (1000, 201, 128), (4096, 256, 128), (4096, 128, 204),
+          (130, 72, 36), (33, 16, 32), (20000, 384, 256), (777, 130, 100)]
+
+
+def _ref(A, W, b):
+    return A.astype(np.float64) @ W.astype(np.float64).T + (b.astype(np.float64) if b is not None else 0.0)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("mode,tol", [(0, 1e-5), (1, 2e-5), (2, 5e-3)])
+def test_gemm_tn(engine, M, N, K, mode, tol):
+    rs = np.random.RandomState(M + N + K)
+    A = rs.uniform(-0.5, 0.5, (M, K)).astype(np.float32)
+    W = rs.uniform(-0.5, 0.5, (N, K)).astype(np.float32)
+    b = rs.uniform(-0.5, 0.5, (N + 3,)).astype(np.float32)[:N].copy() if N % 4 == 0 else None
+    C = engine.gemm_tn(torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda(),
+                       torch.from_numpy(b).cuda() if b is not None else None, mode).cpu().numpy()
+    ref = _ref(A, W, b)
+    scale = np.sqrt(K) * 0.25 / 3.0 + 0.5          # typical magnitude of an entry
+    err = np.max(np.abs(C - ref)) / scale
+    assert err < tol, "mode %d max scaled error %.3e" % (mode, err)
