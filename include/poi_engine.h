@@ -147,6 +147,35 @@ int poi_gru_predict(poi_engine* e, const poi_gru_params* params, const poi_seq_i
                     const int32_t* uidx_host, int32_t B, int32_t max_len_host,
                     float* hts_dev, float* sts_dev);
 
+/* ---- multi-GPU mini-batch step (no reference counterpart -- the reference is single
+ * process).  Users are sharded over ranks, the item table `lt` is row-sharded (owner = row % world),
+ * dense weights and `di` are replicated.  The caller (Python, torch.distributed over NCCL) moves
+ * rows and gradients between ranks; the engine does the arithmetic in two calls:
+ *
+ *  poi_gru_train_mg : forward + backward for this rank's B users, gathering item rows from
+ *      rows_dev = the rows of sorted-unique(p u q of the batch) fetched from their owners
+ *      ([n_unique x d], same order as poi_unique returns).  Nothing is updated; it emits
+ *        dense_grads_dev  float[poi_gru_mg_dense_size]: loss gradients of ui, wh, bi, vs, bs, then a
+ *                         dense [n_dist+1 x d] gradient of di and its [n_dist+1] occurrence counts
+ *        row_grads_dev    [n_unique x d] duplicate-summed loss gradient per unique row
+ *        row_cnt_dev      float[n_unique] occurrence counts (L2 multiplicity)
+ *        loss_sums_dev    double[3] = sum sur, sum log-sigmoid, sum d/d wd
+ *      (params->lt may be NULL; params->n_rows_lt must be the GLOBAL row count.)
+ *  poi_gru_apply_mg : after all-reduce(dense_grads, loss_sums) and the all-to-all of (row id, row_grads,
+ *      row_cnt) to the owners: dense SGD, scalar SGD, and the owner's sparse SGD on its shard
+ *      lt_local_dev [n_local_rows x d] with recv_local_ids (= global id / world), duplicate ids from
+ *      different ranks summed in arrival order.  out_host as poi_gru_train (global sums). */
+int poi_gru_mg_dense_size(const poi_gru_params* params, int64_t* n_floats);
+int poi_gru_train_mg(poi_engine* e, const poi_gru_params* params, const poi_seq_index* index,
+                     const int32_t* uidx_host, int32_t B, int32_t max_len_host, int32_t global_batch,
+                     const float* rows_dev, int64_t n_unique, float* dense_grads_dev,
+                     float* row_grads_dev, float* row_cnt_dev, double* loss_sums_dev);
+int poi_gru_apply_mg(poi_engine* e, const poi_gru_params* params, const float* dense_grads_dev,
+                     const double* loss_sums_dev, int32_t global_batch, int64_t n_nonempty_global,
+                     float* lt_local_dev, int64_t n_local_rows, const int32_t* recv_local_ids_dev,
+                     const float* recv_grads_dev, const float* recv_cnts_dev, int64_t n_recv,
+                     float alpha, float lambda, double* out_host);
+
 /* ---- BPR-MF: OboBpr.bpr_train (BPR.py:234-241) / Bpr.bpr_train (BPR.py:389-397) --------- */
 /* n sequential (u, p, q) SGD steps in the order given -- exactly n back-to-back
  * `model.train(uidx, [p, q])` calls (prog_bpr_gru_spatial.py:240-244); per-occurrence

@@ -61,6 +61,11 @@ _PROTOS = {
                                         c_void_p, c_int32, c_int32, c_float, c_float, POINTER(c_double)]),
     "poi_gru_predict": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32,
                                 c_void_p, c_void_p]),
+    "poi_gru_mg_dense_size": (c_int, [POINTER(PoiGruParams), POINTER(c_int64)]),
+    "poi_gru_train_mg": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32, c_int32,
+                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "poi_gru_apply_mg": (c_int, [_E, POINTER(PoiGruParams), c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int64,
+                                 c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, POINTER(c_double)]),
     "poi_bpr_train_seq": (c_int, [_E, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_void_p]),
     "poi_bpr_train_batch": (c_int, [_E, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p,

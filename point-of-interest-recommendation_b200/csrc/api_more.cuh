@@ -135,6 +135,92 @@ int poi_geoie_train(poi_engine* e, const poi_geoie_params* prm, int32_t uidx, co
     return 0;
 }
 
+// theta <- theta - alpha (g + lambda theta) over a flat region
+__global__ void k_dense_apply(float* __restrict__ theta, const float* __restrict__ g, int64_t n, float alpha, float lambda) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float t = theta[i]; theta[i] = t - alpha * (g[i] + lambda * t); }
+}
+// di[k,:] <- di[k,:] - alpha (G[k,:] + lambda cnt[k] di[k,:])
+__global__ void k_di_apply(float* __restrict__ di, const float* __restrict__ g, const float* __restrict__ cnt,
+                           int nD, int d, float alpha, float lambda) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)nD * d) { float t = di[i]; di[i] = t - alpha * (g[i] + lambda * cnt[i / d] * t); }
+}
+
+int poi_gru_mg_dense_size(const poi_gru_params* p, int64_t* n_floats) {
+    const bool head = p->di != nullptr;
+    *n_floats = mg_layout(p->H, head ? 2 * p->d : p->d, head ? p->n_rows_di : 0, p->d).total;
+    return 0;
+}
+
+int poi_gru_train_mg(poi_engine* e, const poi_gru_params* p, const poi_seq_index* index, const int32_t* uidx_host,
+                     int32_t B, int32_t max_len, int32_t global_batch, const float* rows_dev, int64_t n_unique,
+                     float* dense_grads, float* row_grads, float* row_cnt, double* loss_sums) {
+    POI_TRY(begin_call(e));
+    if (!p || !p->ui || !p->wh || !p->bi) POI_FAIL(e, "gru params: null pointer");
+    if (p->d <= 0 || p->d % 4 || p->H != p->d) POI_FAIL(e, "n_in must equal n_hidden and be a multiple of 4");
+    const bool head = p->di != nullptr;
+    if (!index || !index->p || !index->q || !index->lens || (head && (!index->dp || !index->dq))) POI_FAIL(e, "index matrices missing");
+    if (B <= 0 || global_batch < B) POI_FAIL(e, "bad batch sizes");
+    if (!rows_dev || !dense_grads || !row_grads || !row_cnt || !loss_sums) POI_FAIL(e, "null exchange buffer");
+    (void)n_unique;
+    phase_mark(e, 0);
+    POI_TRY(stage_reserve(e, (size_t)B * 4 + 256));
+    size_t so = 0;
+    int32_t* uidx_dev = nullptr;
+    POI_TRY(gru_upload_i32(e, uidx_host, (size_t)B, &uidx_dev, &so));
+    GruIdx ix;
+    POI_TRY(gru_alloc_idx(e, B, index->lmax, head, &ix));
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv((int64_t)B * index->lmax, 256), 256, 0, index->p, index->q,
+               head ? index->dp : nullptr, head ? index->dq : nullptr, index->lens, index->lmax, uidx_dev, B,
+               ix.PQt, ix.DPt, ix.DQt, ix.lensB);
+    MgCtx mg; mg.rows = rows_dev; mg.global_batch = global_batch; mg.dense_grads = dense_grads;
+    mg.row_grads = row_grads; mg.row_cnt = row_cnt; mg.loss_sums = loss_sums;
+    return gru_train_core(e, p, ix, B, index->lmax, max_len, 0, 0.f, 0.f, nullptr, &mg);
+}
+
+int poi_gru_apply_mg(poi_engine* e, const poi_gru_params* p, const float* dg, const double* loss_sums,
+                     int32_t global_batch, int64_t n_nonempty_global, float* lt_local, int64_t n_local_rows,
+                     const int32_t* recv_ids, const float* recv_grads, const float* recv_cnts, int64_t n_recv,
+                     float alpha, float lambda, double* out_host) {
+    POI_TRY(begin_call(e));
+    const bool head = p->di != nullptr;
+    const int d = p->d, H = p->H, din = head ? 2 * d : d, nD = head ? p->n_rows_di : 0;
+    const MgLayout ML = mg_layout(H, din, nD, d);
+    POI_CAT(e, CAT_WGRAD, 0, 0);
+    auto apply = [&](float* theta, int64_t off, int64_t n) -> int {
+        if (n <= 0) return 0;
+        POI_LAUNCH(e, k_dense_apply, (unsigned)poi_cdiv(n, 256), 256, 0, theta, dg + off, n, alpha, lambda);
+        return 0;
+    };
+    POI_TRY(apply(p->ui, ML.ui, (int64_t)3 * H * din));
+    POI_TRY(apply(p->wh, ML.wh, (int64_t)3 * H * H));
+    POI_TRY(apply(p->bi, ML.bi, 3 * H));
+    if (head) {
+        POI_TRY(apply(p->vs, ML.vs, (int64_t)nD * H));
+        POI_TRY(apply(p->bs, ML.bs, nD));
+        POI_LAUNCH(e, k_di_apply, (unsigned)poi_cdiv((int64_t)nD * d, 256), 256, 0, p->di, dg + ML.di, dg + ML.dicnt, nD, d, alpha, lambda);
+    }
+    double* out_dev = nullptr;
+    POI_TRY(arena_get(e, 8, &out_dev));
+    POI_CAT(e, CAT_REDUCE, 0, 0);
+    POI_LAUNCH(e, k_finalize_from_sums, 1, 32, 0, loss_sums, p->scal, head ? 1 : 0,
+               (double)n_nonempty_global * 0.6931471805599453, 1.0 / (double)global_batch, alpha, lambda, out_dev);
+    if (n_recv > 0) {
+        SegList seg;
+        POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(recv_ids), n_recv, (uint32_t)n_local_rows, false, &seg));
+        RowSrc src; memset(&src, 0, sizeof(src));
+        src.mode = SRC_DENSE_GRADS; src.grads = recv_grads; src.dim = d; src.weights = recv_cnts;
+        POI_TRY(launch_rows_update(e, seg, lt_local, d, alpha, lambda, src, ROW_LONG_THRESH, (double)n_recv * d * 4 * 3));
+    }
+    POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];
+    return 0;
+}
+
 int poi_gemm_tn(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K,
                 const float* bias, float* C, int ldc, int mode) {
     POI_TRY(begin_call(e));

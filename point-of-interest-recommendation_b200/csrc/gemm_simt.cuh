@@ -274,6 +274,21 @@ __global__ void k_reduce_update(const float* __restrict__ part, int splits, int 
     theta[(size_t)i * ldt + j] = th - alpha * (g + lambda * th);
 }
 
+// multi-GPU: only sum the split partials into a gradient buffer (the SGD step happens after the all-reduce)
+__global__ void k_reduce_only(const float* __restrict__ part, int splits, int N1, int N2,
+                              float* __restrict__ out, int ldo, int n1_true, int n2_true) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n1_true * n2_true) return;
+    int i = (int)(idx / n2_true), j = (int)(idx % n2_true);
+    float g = 0.f;
+    for (int s = 0; s < splits; ++s) g += part[((size_t)s * N1 + i) * N2 + j];
+    out[(size_t)i * ldo + j] = g;
+}
+
+// theta or gradient buffer, depending on `grad_out`
+static int launch_reduce_to(poi_engine* e, const AtbPlan& p, float* theta, int ldt, int n1_true, int n2_true,
+                            float alpha, float lambda, float* grad_out);
+
 static int launch_reduce_update(poi_engine* e, const AtbPlan& p, float* theta, int ldt,
                                 int n1_true, int n2_true, float alpha, float lambda) {
     int64_t n = (int64_t)n1_true * n2_true;
@@ -314,5 +329,15 @@ static int launch_colsum(poi_engine* e, const float* A, int lda, int64_t M, int 
     dim3 grid((unsigned)colblocks, (unsigned)splits);
     POI_CAT(e, CAT_WGRAD, 0, (double)M * N * 4);
     POI_LAUNCH(e, k_colsum_partial, grid, 256, 0, A, lda, M, N, mps, plan->part);
+    return 0;
+}
+
+static int launch_reduce_to(poi_engine* e, const AtbPlan& p, float* theta, int ldt, int n1_true, int n2_true,
+                            float alpha, float lambda, float* grad_out) {
+    if (!grad_out) return launch_reduce_update(e, p, theta, ldt, n1_true, n2_true, alpha, lambda);
+    int64_t n = (int64_t)n1_true * n2_true;
+    POI_CAT(e, CAT_WGRAD, 0, 0);
+    POI_LAUNCH(e, k_reduce_only, (unsigned)poi_cdiv(n, 256), 256, 0, p.part, p.splits, p.N1, p.N2, grad_out, ldt,
+               n1_true, n2_true);
     return 0;
 }

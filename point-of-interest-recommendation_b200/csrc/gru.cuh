@@ -16,6 +16,7 @@
 #include "rows.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include <string.h>
 
 // ---------------------------------------------------------------------------------------------
 // index preparation: user-major [n_user x lmax] rows -> time-major [lmax x B]
@@ -310,22 +311,8 @@ k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc
 
 // Final scalars + the scalar parameters' SGD step (wd, loss_weight; GRU_Spatial.py:210-211).
 // out[0..4] = los, sur, upq, w0, w1 (plain GRU: out[0] = upq)
-__global__ void __launch_bounds__(256)
-k_finalize_gru(const double* __restrict__ part, int nblocks, float* scal, int head,
-                               double extra_upq, double scale, float alpha, float lambda,
-                               double* __restrict__ out) {
-    // fixed-shape tree over the block partials: thread t sums entries t, t+256, ... then a fixed
-    // shuffle/shared tree -> deterministic for a given grid size
-    __shared__ double sh[8][3];
-    double s3[3] = {0.0, 0.0, 0.0};
-    for (int i = threadIdx.x; i < nblocks; i += 256)
-        for (int k = 0; k < 3; ++k) s3[k] += part[(size_t)i * 4 + k];
-    for (int k = 0; k < 3; ++k) s3[k] = warp_sum_d(s3[k]);
-    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) sh[threadIdx.x >> 5][k] = s3[k];
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    double sur = 0.0, bpr = 0.0, gwd = 0.0;
-    for (int w = 0; w < 8; ++w) { sur += sh[w][0]; bpr += sh[w][1]; gwd += sh[w][2]; }
+__device__ void finalize_apply(double sur, double bpr, double gwd, float* scal, int head, double extra_upq,
+                               double scale, float alpha, float lambda, double* out) {
     double upq = -bpr + extra_upq;
     if (!head) { out[0] = upq; out[1] = 0.0; out[2] = upq; out[3] = 0.0; out[4] = 1.0; return; }
     float a = scal[1], b = scal[2], mx = fmaxf(a, b);
@@ -338,6 +325,33 @@ k_finalize_gru(const double* __restrict__ part, int nblocks, float* scal, int he
     scal[0] = (float)(wd - (double)alpha * g_wd);
     scal[1] = (float)((double)a - (double)alpha * w0 * (dw0 - dot));
     scal[2] = (float)((double)b - (double)alpha * w1 * (dw1 - dot));
+}
+
+// sums_out != NULL (multi-GPU): only publish the three partial sums; the step is applied after the all-reduce
+__global__ void __launch_bounds__(256)
+k_finalize_gru(const double* __restrict__ part, int nblocks, float* scal, int head,
+               double extra_upq, double scale, float alpha, float lambda,
+               double* __restrict__ out, double* __restrict__ sums_out) {
+    // fixed-shape tree over the block partials: thread t sums entries t, t+256, ... then a fixed
+    // shuffle/shared tree -> deterministic for a given grid size
+    __shared__ double sh[8][3];
+    double s3[3] = {0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += 256)
+        for (int k = 0; k < 3; ++k) s3[k] += part[(size_t)i * 4 + k];
+    for (int k = 0; k < 3; ++k) s3[k] = warp_sum_d(s3[k]);
+    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) sh[threadIdx.x >> 5][k] = s3[k];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double sur = 0.0, bpr = 0.0, gwd = 0.0;
+    for (int w = 0; w < 8; ++w) { sur += sh[w][0]; bpr += sh[w][1]; gwd += sh[w][2]; }
+    if (sums_out) { sums_out[0] = sur; sums_out[1] = bpr; sums_out[2] = gwd; return; }
+    finalize_apply(sur, bpr, gwd, scal, head, extra_upq, scale, alpha, lambda, out);
+}
+
+__global__ void k_finalize_from_sums(const double* __restrict__ sums, float* scal, int head, double extra_upq,
+                                     double scale, float alpha, float lambda, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        finalize_apply(sums[0], sums[1], sums[2], scal, head, extra_upq, scale, alpha, lambda, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,6 +368,27 @@ static int gemm_tn(poi_engine* e, const float* A, int lda, const float* W, int l
 // ---------------------------------------------------------------------------------------------
 // the step
 // ---------------------------------------------------------------------------------------------
+// multi-GPU step context: users are sharded over ranks, the item table row-sharded.
+// The step gathers from `rows` (the unique rows this rank needs, fetched from their owners, sorted
+// by row id) and, instead of applying updates, emits gradients to be exchanged / all-reduced.
+struct MgCtx {
+    const float* rows;       // [n_unique x d]
+    int global_batch;        // sum of B over ranks (loss normalisation)
+    float* dense_grads;      // flat buffer, layout MgLayout
+    float* row_grads;        // [n_unique x d] duplicate-summed loss gradient per unique row
+    float* row_cnt;          // [n_unique] occurrences (L2 multiplicity)
+    double* loss_sums;       // device double[3]: sur, bpr, gwd
+};
+struct MgLayout { int64_t ui, wh, bi, vs, bs, di, dicnt, total; };
+static MgLayout mg_layout(int H, int din, int nD, int d) {
+    MgLayout L; int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t at = o; o += (n + 3) / 4 * 4; return at; };
+    L.ui = take((int64_t)3 * H * din); L.wh = take((int64_t)3 * H * H); L.bi = take(3 * H);
+    L.vs = take((int64_t)nD * H); L.bs = take(nD); L.di = take((int64_t)nD * d); L.dicnt = take(nD);
+    L.total = o;
+    return L;
+}
+
 struct GruIdx {              // time-major device index arrays for this batch
     int32_t* PQt; int32_t* DPt; int32_t* DQt; int32_t* lensB;
 };
@@ -409,23 +444,27 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
 }
 
 static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& ix, int B, int lmax,
-                          int max_len, int64_t n_nonempty, float alpha, float lambda, double* out_host) {
+                          int max_len, int64_t n_nonempty, float alpha, float lambda, double* out_host,
+                          const MgCtx* mg = nullptr) {
     const bool head = p->di != nullptr;
     const int d = p->d, H = p->H, din = head ? 2 * d : d;
     const int nD = head ? p->n_rows_di : 0, nDp = (nD + 3) / 4 * 4;
     const int T = std::max(std::min(max_len, lmax) - 1, 0);
     const int64_t LB = (int64_t)lmax * B, TB = (int64_t)T * B;
-    const float scale = 1.0f / (float)B;
+    const float scale = 1.0f / (float)(mg ? mg->global_batch : B);
+    const MgLayout ML = mg_layout(H, din, nD, d);
 
     // ---- integer work: sorted-unique segments of the gathered row ids (pad rows included) ----
     SegList seg_lt, seg_di;
-    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.PQt), 2 * LB, (uint32_t)p->n_rows_lt, false, &seg_lt));
+    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.PQt), 2 * LB, (uint32_t)p->n_rows_lt, mg != nullptr, &seg_lt));
     if (head) POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.DPt), LB, (uint32_t)nD, false, &seg_di));
     phase_mark(e, 1);
 
     // ---- forward ----
     float *X, *XDiff, *AX, *Hs, *Z, *R, *C, *RH;
-    POI_TRY(gru_forward(e, p, ix, B, lmax, T, true, &X, &XDiff, &AX, &Hs, &Z, &R, &C, &RH));
+    poi_gru_params pf = *p; GruIdx ixf = ix;
+    if (mg) { pf.lt = const_cast<float*>(mg->rows); ixf.PQt = reinterpret_cast<int32_t*>(seg_lt.seg_of_occ); }   // gather by slot
+    POI_TRY(gru_forward(e, &pf, ixf, B, lmax, T, true, &X, &XDiff, &AX, &Hs, &Z, &R, &C, &RH));
     if (T <= 0) phase_mark(e, 2);
     phase_mark(e, 3);
     const float* Hc = Hs + (size_t)B * H;
@@ -496,29 +535,36 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
         POI_TRY(launch_gemm_atb(e, S, nDp, Hc, H, TB, nDp, H, &g_vs));
         POI_TRY(launch_colsum(e, S, nDp, TB, nDp, &g_bs));
     }
-    POI_TRY(launch_reduce_update(e, g_ui, p->ui, din, 3 * H, din, alpha, lambda));
-    POI_TRY(launch_reduce_update(e, g_whzr, p->wh, H, 2 * H, H, alpha, lambda));
-    POI_TRY(launch_reduce_update(e, g_whc, p->wh + (size_t)2 * H * H, H, H, H, alpha, lambda));
-    POI_TRY(launch_reduce_update(e, g_bi, p->bi, 3 * H, 1, 3 * H, alpha, lambda));
+    float* dg = mg ? mg->dense_grads : nullptr;
+    POI_TRY(launch_reduce_to(e, g_ui, p->ui, din, 3 * H, din, alpha, lambda, dg ? dg + ML.ui : nullptr));
+    POI_TRY(launch_reduce_to(e, g_whzr, p->wh, H, 2 * H, H, alpha, lambda, dg ? dg + ML.wh : nullptr));
+    POI_TRY(launch_reduce_to(e, g_whc, p->wh + (size_t)2 * H * H, H, H, H, alpha, lambda, dg ? dg + ML.wh + (size_t)2 * H * H : nullptr));
+    POI_TRY(launch_reduce_to(e, g_bi, p->bi, 3 * H, 1, 3 * H, alpha, lambda, dg ? dg + ML.bi : nullptr));
     if (head) {
-        POI_TRY(launch_reduce_update(e, g_vs, p->vs, H, nD, H, alpha, lambda));
-        POI_TRY(launch_reduce_update(e, g_bs, p->bs, nD, 1, nD, alpha, lambda));
+        POI_TRY(launch_reduce_to(e, g_vs, p->vs, H, nD, H, alpha, lambda, dg ? dg + ML.vs : nullptr));
+        POI_TRY(launch_reduce_to(e, g_bs, p->bs, nD, 1, nD, alpha, lambda, dg ? dg + ML.bs : nullptr));
     }
     POI_CAT(e, CAT_REDUCE, 0, 0);
     POI_LAUNCH(e, k_finalize_gru, 1, 256, 0, part, loss_blocks, p->scal, head ? 1 : 0,
-               (double)n_nonempty * 0.6931471805599453, (double)scale, alpha, lambda, out_dev);
+               (double)n_nonempty * 0.6931471805599453, (double)scale, alpha, lambda, out_dev,
+               mg ? mg->loss_sums : (double*)nullptr);
     phase_mark(e, 6);
 
     // ---- sparse row SGD: lt[unique(p u q)], di[unique(dp)] ----
-    RowSrc src;
+    RowSrc src; memset(&src, 0, sizeof(src));
     src.mode = SRC_GRU_LT; src.grads = nullptr; src.DX = DX; src.ldx = din; src.Hc = Hc; src.ev = ev;
     src.B = B; src.T = T; src.LB = LB; src.dim = d;
+    if (mg) { src.emit_rows = mg->row_grads; src.emit_cnt = mg->row_cnt; src.emit_by_key = 0; }
     // algorithmic bytes of the sparse step: 2 table rows per check-in, read + written,
     // plus the gradient rows that feed them (dx, and e*h for p and q)
     POI_TRY(launch_rows_update(e, seg_lt, p->lt, d, alpha, lambda, src, ROW_LONG_THRESH,
                                (double)TB * d * 4 * (4.0 + 3.0) + 8.0 * (double)LB));
     if (head) {
         src.mode = SRC_GRU_DI;
+        if (mg) {   // di is replicated: emit a dense [nD x d] gradient + counts (all-reduced by the caller)
+            POI_CK(e, cudaMemsetAsync(mg->dense_grads + ML.di, 0, (size_t)(ML.total - ML.di) * sizeof(float), e->stream));
+            src.emit_rows = mg->dense_grads + ML.di; src.emit_cnt = mg->dense_grads + ML.dicnt; src.emit_by_key = 1;
+        }
         POI_TRY(launch_rows_update(e, seg_di, p->di, d, alpha, lambda, src, ROW_LONG_THRESH,
                                    (double)TB * d * 4 + 4.0 * (double)LB));
     }
@@ -528,7 +574,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
     phase_mark(e, 8);
     POI_CK(e, cudaStreamSynchronize(e->stream));
     if (e->kprof) prof_harvest(e);
-    for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];
+    if (out_host) for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];
     if (e->timing) {
         cudaEventElapsedTime(&e->phase_ms[0], e->ev[0], e->ev[8]);
         for (int i = 1; i <= 7; ++i) cudaEventElapsedTime(&e->phase_ms[i], e->ev[i - 1], e->ev[i]);

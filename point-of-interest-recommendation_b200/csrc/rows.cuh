@@ -122,7 +122,29 @@ struct RowSrc {
     const float* DX; int ldx; const float* Hc; const float* ev;
     int B; int T; int64_t LB;   // LB = lmax * B  (p occurrences [0,LB), q occurrences [LB,2LB))
     int dim;
+    // optional per-occurrence L2 multiplicities (multi-GPU owner side: each received gradient row stands
+    // for `weights[occ]` gathered occurrences on the sending rank); NULL = 1 each
+    const float* weights;
+    // emit mode (multi-GPU sender side): instead of updating the table, write the duplicate-summed
+    // gradient of segment sg to emit_rows[(emit_by_key ? key : sg) * dim] and its count to emit_cnt[.]
+    float* emit_rows; float* emit_cnt; int emit_by_key;
 };
+
+__device__ __forceinline__ void row_finish(const RowSrc& src, float* table, int dim4, uint32_t key, uint32_t sg,
+                                           int c, float4 a, float cntf, float alpha, float lambda) {
+    if (src.emit_rows) {
+        size_t slot = src.emit_by_key ? key : sg;
+        st4(src.emit_rows + (slot * dim4 + c) * 4, a);
+        if (c == 0) src.emit_cnt[slot] = cntf;
+    } else {
+        float* row = table + ((size_t)key * dim4 + c) * 4;
+        const float lc = lambda * cntf;
+        float4 r = ld4(row);
+        r.x -= alpha * (a.x + lc * r.x); r.y -= alpha * (a.y + lc * r.y);
+        r.z -= alpha * (a.z + lc * r.z); r.w -= alpha * (a.w + lc * r.w);
+        st4(row, r);
+    }
+}
 
 struct OccPair { const float* p1; const float* p2; float s2; };
 
@@ -168,6 +190,8 @@ k_rows_update_warp(SegList seg, float* __restrict__ table, int dim4, float alpha
         float4 acc[NCH];
 #pragma unroll
         for (int k = 0; k < NCH; ++k) acc[k] = f4zero();
+        float cntf = (float)cnt;
+        if (src.weights) { cntf = 0.f; for (uint32_t i = s0; i < s1; ++i) cntf += src.weights[seg.vals[i]]; }
         for (uint32_t i = s0; i < s1; ++i) {
             OccPair o = occ_begin(src, seg.vals[i]);
 #pragma unroll
@@ -179,17 +203,10 @@ k_rows_update_warp(SegList seg, float* __restrict__ table, int dim4, float alpha
                 }
             }
         }
-        float* row = table + (size_t)seg.uniq[sg] * dim4 * 4;
-        const float lc = lambda * (float)cnt;
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
             int c = lane + 32 * k;
-            if (c < dim4) {
-                float4 r = ld4(row + 4 * c);
-                r.x -= alpha * (acc[k].x + lc * r.x); r.y -= alpha * (acc[k].y + lc * r.y);
-                r.z -= alpha * (acc[k].z + lc * r.z); r.w -= alpha * (acc[k].w + lc * r.w);
-                st4(row + 4 * c, r);
-            }
+            if (c < dim4) row_finish(src, table, dim4, seg.uniq[sg], (uint32_t)sg, c, acc[k], cntf, alpha, lambda);
         }
     }
 }
@@ -216,7 +233,7 @@ __global__ void k_long_offsets(SegList seg, const uint32_t* __restrict__ long_li
 __global__ void __launch_bounds__(256)
 k_long_partial(SegList seg, int dim4, RowSrc src, const uint32_t* __restrict__ long_list,
                const uint32_t* __restrict__ long_count, const uint32_t* __restrict__ chunk_off,
-               float4* __restrict__ partial) {
+               float4* __restrict__ partial, float* __restrict__ partial_w) {
     extern __shared__ float4 s_part[];          // [8][dim4]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nl = *long_count;
@@ -228,6 +245,12 @@ k_long_partial(SegList seg, int dim4, RowSrc src, const uint32_t* __restrict__ l
         const uint32_t sg = long_list[lo];
         const uint32_t s0 = seg.seg_start[sg] + (ch - chunk_off[lo]) * ROW_CHUNK;
         const uint32_t s1 = min(s0 + ROW_CHUNK, seg.seg_start[sg + 1]);
+        if (w == 0) {                               // L2 multiplicity of this chunk
+            float wsum = 0.f;
+            for (uint32_t i = s0 + lane; i < s1; i += 32) wsum += src.weights ? src.weights[seg.vals[i]] : 1.f;
+            wsum = warp_sum(wsum);
+            if (lane == 0) partial_w[ch] = wsum;
+        }
         for (int c0 = 0; c0 < dim4; c0 += 32) {
             int c = c0 + lane;
             float4 acc = f4zero();
@@ -252,22 +275,20 @@ k_long_partial(SegList seg, int dim4, RowSrc src, const uint32_t* __restrict__ l
 }
 
 __global__ void __launch_bounds__(128)
-k_long_final(SegList seg, float* __restrict__ table, int dim4, float alpha, float lambda,
+k_long_final(SegList seg, float* __restrict__ table, int dim4, float alpha, float lambda, RowSrc src,
              const uint32_t* __restrict__ long_list, const uint32_t* __restrict__ long_count,
-             const uint32_t* __restrict__ chunk_off, const float4* __restrict__ partial) {
+             const uint32_t* __restrict__ chunk_off, const float4* __restrict__ partial,
+             const float* __restrict__ partial_w) {
     const uint32_t nl = *long_count;
     for (uint32_t li = blockIdx.x; li < nl; li += gridDim.x) {
         const uint32_t sg = long_list[li];
         const uint32_t c0 = chunk_off[li], c1 = chunk_off[li + 1];
-        float* row = table + (size_t)seg.uniq[sg] * dim4 * 4;
-        const float lc = lambda * (float)(seg.seg_start[sg + 1] - seg.seg_start[sg]);
+        float cntf = 0.f;
+        for (uint32_t ch = c0; ch < c1; ++ch) cntf += partial_w[ch];
         for (int c = threadIdx.x; c < dim4; c += blockDim.x) {
             float4 a = f4zero();
             for (uint32_t ch = c0; ch < c1; ++ch) a = f4add(a, partial[(size_t)ch * dim4 + c]);
-            float4 r = ld4(row + 4 * c);
-            r.x -= alpha * (a.x + lc * r.x); r.y -= alpha * (a.y + lc * r.y);
-            r.z -= alpha * (a.z + lc * r.z); r.w -= alpha * (a.w + lc * r.w);
-            st4(row + 4 * c, r);
+            row_finish(src, table, dim4, seg.uniq[sg], sg, c, a, cntf, alpha, lambda);
         }
     }
 }
@@ -292,14 +313,15 @@ static int launch_rows_update(poi_engine* e, const SegList& seg, float* table, i
     // long segments: chunk partials, then ordered final sum
     const size_t max_long = (size_t)seg.n / (size_t)std::max(long_thresh, 1) + 2;
     const size_t max_chunks = (size_t)seg.n / ROW_CHUNK + max_long + 2;
-    uint32_t* chunk_off = nullptr; float4* partial = nullptr;
+    uint32_t* chunk_off = nullptr; float4* partial = nullptr; float* partial_w = nullptr;
     POI_TRY(arena_get(e, max_long + 1, &chunk_off));
     POI_TRY(arena_get(e, max_chunks * dim4, &partial));
+    POI_TRY(arena_get(e, max_chunks, &partial_w));
     POI_LAUNCH(e, k_long_offsets, 1, 32, 0, seg, long_list, long_count, chunk_off);
     size_t smem = (size_t)8 * dim4 * sizeof(float4);
     unsigned lgrid = (unsigned)std::min<int64_t>((int64_t)max_chunks, (int64_t)e->num_sms * 8);
-    POI_LAUNCH(e, k_long_partial, lgrid, 256, smem, seg, dim4, src, long_list, long_count, chunk_off, partial);
+    POI_LAUNCH(e, k_long_partial, lgrid, 256, smem, seg, dim4, src, long_list, long_count, chunk_off, partial, partial_w);
     unsigned fgrid = (unsigned)std::min<int64_t>((int64_t)max_long, (int64_t)e->num_sms * 8);
-    POI_LAUNCH(e, k_long_final, fgrid, 128, 0, seg, table, dim4, alpha, lambda, long_list, long_count, chunk_off, partial);
+    POI_LAUNCH(e, k_long_final, fgrid, 128, 0, seg, table, dim4, alpha, lambda, src, long_list, long_count, chunk_off, partial, partial_w);
     return 0;
 }

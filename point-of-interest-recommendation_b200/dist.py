@@ -1,0 +1,176 @@
+"""Multi-GPU mini-batch training: one process per GPU, `torch.distributed`
+(NCCL over NVLink / NVSwitch) as the plumbing.
+
+Partitioning
+  * users (and their index-matrix rows) are split over ranks -- each rank trains its own B users per
+    step, the step's loss is normalised by the global batch;
+  * the item table `lt` is ROW-SHARDED, owner(row) = row % world, local index = row // world
+    (interleaved, so Zipf-hot rows spread evenly);
+  * dense weights (ui, wh, bi, vs, bs, wd, loss_weight) and the small interval table `di` are
+    replicated and kept identical by all-reducing their gradients.
+
+Per step (the reference has no counterpart -- it is single process):
+  1. sorted-unique row ids of the local batch (engine, bit-exact integer work);
+  2. all-to-all: ids -> owners, owners gather their rows (engine), all-to-all rows back;
+  3. forward + backward on the fetched rows (engine, `poi_gru_train_mg`): emits dense gradients and one
+     duplicate-summed gradient row + occurrence count per unique id;
+  4. all-reduce(dense gradients, loss sums); all-to-all (gradient rows, counts) -> owners;
+  5. every rank applies the dense SGD step; each owner applies the sparse SGD step to its shard
+     (`poi_gru_apply_mg`).
+G ranks x batch B is the same update as 1 rank x batch G*B up to floating-point summation order.
+
+`RowExchange` is device-agnostic (CPU tensors + gloo work too) so the routing logic is testable
+without GPUs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class RowExchange:
+    """Routing of unique row ids to their owners and back.  Built once per step from the sorted unique
+    ids this rank needs; `fetch` pulls the rows, `push` sends per-row payloads (gradients, counts) to
+    the owners.  Deterministic: payloads arrive grouped by source rank, in ascending id order."""
+
+    def __init__(self, uniq_ids: torch.Tensor, world: int, group=None):
+        self.world, self.group = world, group
+        self.n = uniq_ids.numel()
+        dev = uniq_ids.device
+        ids = uniq_ids.to(torch.int64)
+        owner = ids % world
+        # stable sort by owner keeps ascending id order inside each destination bucket
+        self.order = torch.sort(owner, stable=True).indices
+        self.send_ids = ids[self.order].contiguous()
+        self.send_counts = torch.bincount(owner, minlength=world).to(torch.int64)
+        if world > 1:
+            rc = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_to_all_single(rc, self.send_counts, group=group)
+            self.recv_counts = rc
+        else:
+            self.recv_counts = self.send_counts.clone()
+        self.send_split = self.send_counts.cpu().tolist()
+        self.recv_split = self.recv_counts.cpu().tolist()
+        self.n_recv = int(sum(self.recv_split))
+        self.recv_ids = self._a2a(self.send_ids, self.send_split, self.recv_split)       # global ids I own
+        self.recv_local = (self.recv_ids // world).to(torch.int32).contiguous()
+
+    def _a2a(self, send: torch.Tensor, send_split, recv_split) -> torch.Tensor:
+        out = torch.empty((int(sum(recv_split)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        if self.world > 1:
+            dist.all_to_all_single(out, send.contiguous(), output_split_sizes=recv_split, input_split_sizes=send_split,
+                                   group=self.group)
+        else:
+            out.copy_(send)
+        return out
+
+    def fetch(self, gather_local) -> torch.Tensor:
+        """gather_local(local_ids int32 [m]) -> rows [m, d] of this rank's shard.  Returns the rows of
+        `uniq_ids`, in that order."""
+        mine = gather_local(self.recv_local)
+        back = self._a2a(mine, self.recv_split, self.send_split)
+        rows = torch.empty_like(back)
+        rows[self.order] = back
+        return rows
+
+    def push(self, payload: torch.Tensor) -> torch.Tensor:
+        """payload [n, ...] aligned with `uniq_ids` -> rows received by the owner, aligned with
+        `recv_local` / `recv_ids`."""
+        return self._a2a(payload[self.order].contiguous(), self.send_split, self.recv_split)
+
+
+def shard_rows(table: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Rows owned by `rank`: table[rank::world] (local index = global // world)."""
+    return np.ascontiguousarray(table[rank::world])
+
+
+def unshard_rows(shards, n_rows: int) -> np.ndarray:
+    out = np.empty((n_rows,) + shards[0].shape[1:], dtype=shards[0].dtype)
+    for r, s in enumerate(shards):
+        out[r::len(shards)] = s
+    return out
+
+
+class ShardedSpatialGru:
+    """Mini-batch Distance2Pre (or plain GRU when `dist_masks` is None) over `world` GPUs.
+
+    Index matrices hold THIS rank's users only ([n_local_user x lmax]); `init['lt']` may be the full
+    table (it is sharded here) or already this rank's shard (pass lt_is_shard=True)."""
+
+    def __init__(self, train, dist_masks, alpha_lambda, n_item, n_dist, n_in, n_hidden, init, rank=None, world=None,
+                 device=None, lt_is_shard=False, group=None):
+        from .engine import Engine
+        from .public.GRU import _lens_from_masks
+        from .shared import Shared
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.group = group
+        self.engine = Engine.get(device)
+        dev = self.engine.torch_device
+        self.n_item, self.n_rows = n_item, n_item + 1
+        self.head = dist_masks is not None
+        P, M, Q = train
+        self.P, self.Q = Shared(P, "int32", dev), Shared(Q, "int32", dev)
+        self._lens_host = _lens_from_masks(M, "tra_masks")
+        self._lens = torch.from_numpy(self._lens_host).to(dev)
+        if self.head:
+            self.DP, self.DQ = Shared(dist_masks[0], "int32", dev), Shared(dist_masks[1], "int32", dev)
+        self._alpha, self._lambda = float(alpha_lambda[0]), float(alpha_lambda[1])
+        lt = init["lt"]
+        if not lt_is_shard:
+            lt = lt[self.rank::self.world] if isinstance(lt, torch.Tensor) else shard_rows(np.asarray(lt), self.rank, self.world)
+        self.lt_local = Shared(lt, "float32", dev)
+        f = lambda k: Shared(init[k], "float32", dev)
+        self.ui, self.wh, self.bi = f("ui"), f("wh"), f("bi")
+        if self.head:
+            self.di, self.vs, self.bs = f("di"), f("vs"), f("bs")
+            lw = np.asarray(init["loss_weight"], dtype=np.float32)
+            self._scal = Shared(np.array([float(np.asarray(init["wd"])), lw[0], lw[1]], dtype=np.float32), "float32", dev)
+        self.d = self.lt_local.t.shape[1]
+        self._dense = torch.zeros(Engine.gru_mg_dense_size(self._params()), dtype=torch.float32, device=dev)
+        self._sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.last_exchange_rows = 0
+
+    def _params(self):
+        from .engine import Engine
+        p = Engine.gru_params(self.lt_local.t, self.ui.t, self.wh.t, self.bi.t,
+                              self.di.t if self.head else None, self.vs.t if self.head else None,
+                              self.bs.t if self.head else None, self._scal.t if self.head else None)
+        p.n_rows_lt = self.n_rows          # key bound of the batch's row ids is the GLOBAL row count
+        return p
+
+    def _index(self):
+        from .engine import Engine
+        return Engine.seq_index(self.P.t, self.Q.t, self._lens, self.DP.t if self.head else None,
+                                self.DQ.t if self.head else None)
+
+    def train(self, local_uidx):
+        """One step over this rank's users `local_uidx` (int32 indices into the local index matrices).
+        Every rank must call it in lock-step.  Returns the GLOBAL [los, sur, upq, ls]."""
+        eng, dev = self.engine, self.engine.torch_device
+        uidx = np.asarray(local_uidx, dtype=np.int32).reshape(-1)
+        B = uidx.size
+        meta = torch.tensor([B, int((self._lens_host[uidx] >= 1).sum())], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(meta, group=self.group)
+        global_batch, n_nonempty = int(meta[0].item()), int(meta[1].item())
+        ut = torch.from_numpy(uidx.astype(np.int64)).to(dev)
+        keys = torch.cat((self.P.t[ut].T.reshape(-1), self.Q.t[ut].T.reshape(-1))).contiguous()
+        uniq, _ = eng.unique(keys, self.n_rows)
+        ex = RowExchange(uniq, self.world, self.group)
+        rows = ex.fetch(lambda loc: eng.gather_rows(self.lt_local.t, loc))
+        n_u = uniq.numel()
+        row_grads = torch.empty((n_u, self.d), dtype=torch.float32, device=dev)
+        row_cnt = torch.empty(n_u, dtype=torch.float32, device=dev)
+        eng.gru_train_mg(self._params(), self._index(), uidx, int(self._lens_host[uidx].max()), global_batch, rows,
+                         self._dense, row_grads, row_cnt, self._sums)
+        if self.world > 1:
+            dist.all_reduce(self._dense, group=self.group)
+            dist.all_reduce(self._sums, group=self.group)
+        recv_grads = ex.push(row_grads)
+        recv_cnts = ex.push(row_cnt)
+        self.last_exchange_rows = n_u
+        out = eng.gru_apply_mg(self._params(), self._dense, self._sums, global_batch, 0 if self.head else n_nonempty,
+                               self.lt_local.t, ex.recv_local, recv_grads, recv_cnts, self._alpha, self._lambda)
+        return [out[0], out[1], out[2], np.array([out[3], out[4]])]

@@ -207,6 +207,31 @@ class Engine:
                                      hts.data_ptr(), sts.data_ptr() if sts is not None else 0))
         return hts, sts
 
+    # ---- multi-GPU step (two phases around the collectives) ---------------------------------
+    @staticmethod
+    def gru_mg_dense_size(params: PoiGruParams) -> int:
+        n = c_int64()
+        lib.poi_gru_mg_dense_size(byref(params), byref(n))
+        return n.value
+
+    def gru_train_mg(self, params, index, uidx, max_len, global_batch, rows, dense_grads, row_grads, row_cnt, loss_sums):
+        uidx = _host_i32(uidx, "uidx").reshape(-1)
+        self._ck(lib.poi_gru_train_mg(self._h, byref(params), byref(index), uidx.ctypes.data, uidx.size, int(max_len),
+                                      int(global_batch), _dev_f32(rows, "rows"), rows.shape[0],
+                                      _dev_f32(dense_grads, "dense_grads"), _dev_f32(row_grads, "row_grads"),
+                                      _dev_f32(row_cnt, "row_cnt"), loss_sums.data_ptr()))
+
+    def gru_apply_mg(self, params, dense_grads, loss_sums, global_batch, n_nonempty_global, lt_local, recv_ids,
+                     recv_grads, recv_cnts, alpha, lam):
+        out = (c_double * 5)()
+        n_recv = recv_ids.numel()
+        self._ck(lib.poi_gru_apply_mg(self._h, byref(params), _dev_f32(dense_grads, "dense_grads"), loss_sums.data_ptr(),
+                                      int(global_batch), int(n_nonempty_global), _dev_f32(lt_local, "lt_local"),
+                                      lt_local.shape[0], _dev_i32(recv_ids, "recv_ids") if n_recv else 0,
+                                      _dev_f32(recv_grads, "recv_grads") if n_recv else 0,
+                                      _dev_f32(recv_cnts, "recv_cnts") if n_recv else 0, n_recv, alpha, lam, out))
+        return list(out)
+
     # ---- BPR / PRME -------------------------------------------------------------------------
     def bpr_train_seq(self, ux, lt, u, p, q, alpha, lam) -> np.ndarray:
         u = _host_i32(u, "u").reshape(-1); p = _host_i32(p, "p").reshape(-1); q = _host_i32(q, "q").reshape(-1)
