@@ -145,25 +145,41 @@ class ShardedSpatialGru:
         return Engine.seq_index(self.P.t, self.Q.t, self._lens, self.DP.t if self.head else None,
                                 self.DQ.t if self.head else None)
 
+    def train_host_rows(self, p, q, dp, dq, lens):
+        """End-to-end variant: the step's index rows come from (pinned) host tensors [B x lmax]; they are
+        copied to the device inside the call, then the same step runs on them."""
+        from .engine import Engine
+        dev = self.engine.torch_device
+        B = p.shape[0]
+        idx_p = p.to(dev, non_blocking=True); idx_q = q.to(dev, non_blocking=True)
+        idx_dp = dp.to(dev, non_blocking=True) if self.head else None
+        idx_dq = dq.to(dev, non_blocking=True) if self.head else None
+        lens_host = lens.numpy() if isinstance(lens, torch.Tensor) else np.asarray(lens)
+        index = Engine.seq_index(idx_p, idx_q, lens.to(dev, non_blocking=True), idx_dp, idx_dq)
+        return self._step(np.arange(B, dtype=np.int32), index, idx_p, idx_q, lens_host)
+
     def train(self, local_uidx):
         """One step over this rank's users `local_uidx` (int32 indices into the local index matrices).
         Every rank must call it in lock-step.  Returns the GLOBAL [los, sur, upq, ls]."""
-        eng, dev = self.engine, self.engine.torch_device
         uidx = np.asarray(local_uidx, dtype=np.int32).reshape(-1)
+        return self._step(uidx, self._index(), self.P.t, self.Q.t, self._lens_host)
+
+    def _step(self, uidx, index, Pt, Qt, lens_host):
+        eng, dev = self.engine, self.engine.torch_device
         B = uidx.size
-        meta = torch.tensor([B, int((self._lens_host[uidx] >= 1).sum())], dtype=torch.int64, device=dev)
+        meta = torch.tensor([B, int((lens_host[uidx] >= 1).sum())], dtype=torch.int64, device=dev)
         if self.world > 1:
             dist.all_reduce(meta, group=self.group)
         global_batch, n_nonempty = int(meta[0].item()), int(meta[1].item())
         ut = torch.from_numpy(uidx.astype(np.int64)).to(dev)
-        keys = torch.cat((self.P.t[ut].T.reshape(-1), self.Q.t[ut].T.reshape(-1))).contiguous()
+        keys = torch.cat((Pt[ut].T.reshape(-1), Qt[ut].T.reshape(-1))).contiguous()
         uniq, _ = eng.unique(keys, self.n_rows)
         ex = RowExchange(uniq, self.world, self.group)
         rows = ex.fetch(lambda loc: eng.gather_rows(self.lt_local.t, loc))
         n_u = uniq.numel()
         row_grads = torch.empty((n_u, self.d), dtype=torch.float32, device=dev)
         row_cnt = torch.empty(n_u, dtype=torch.float32, device=dev)
-        eng.gru_train_mg(self._params(), self._index(), uidx, int(self._lens_host[uidx].max()), global_batch, rows,
+        eng.gru_train_mg(self._params(), index, uidx, int(lens_host[uidx].max()), global_batch, rows,
                          self._dense, row_grads, row_cnt, self._sums)
         if self.world > 1:
             dist.all_reduce(self._dense, group=self.group)
