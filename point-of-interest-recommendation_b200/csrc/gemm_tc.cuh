@@ -102,7 +102,12 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
 
 constexpr int BM = 128;
 constexpr int BK = 32;            // 32 fp32 = 128 B = one swizzle row
-constexpr int THREADS = 256;
+constexpr int PRODUCERS = 256;    // warps 0..7: stage operands, later run the epilogue
+constexpr int THREADS = PRODUCERS + 32;   // + warp 8: one elected thread issues the MMAs
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <int BN, bool SPLIT3>
 struct Cfg {
@@ -111,26 +116,33 @@ struct Cfg {
     static constexpr int W_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (SPLIT3 ? 2 : 1);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-    static constexpr int LA = BM * 8 / THREADS;     // 16-byte chunks per thread, A tile
-    static constexpr int LW = BN * 8 / THREADS;     // W tile
+    static constexpr int LA = BM * 8 / PRODUCERS;     // 16-byte chunks per thread, A tile
+    static constexpr int LW = BN * 8 / PRODUCERS;     // W tile
 };
 
+// Warp-specialised: producers run ahead through a STAGES-deep ring (full/empty mbarriers, no block-wide
+// barrier in the main loop) with the next k-block's global loads already in flight in registers;
+// blockIdx.z selects a K range [z*k_per_split, ...) (split-K for the weight-gradient GEMMs).
 template <int BN, bool SPLIT3, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-             int M, int N, int K, Epi epi) {
+             int M, int N, int K, int k_per_split, Epi epi) {
     using C = Cfg<BN, SPLIT3>;
     extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t mbar_full[C::STAGES];
     __shared__ uint64_t mbar_empty[C::STAGES];
     __shared__ uint64_t mbar_done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(K, kbeg + k_per_split);
+    const int KB = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < C::STAGES; ++s) mbar_init(&mbar_empty[s], 1);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&mbar_full[s], PRODUCERS); mbar_init(&mbar_empty[s], 1); }
         mbar_init(&mbar_done, 1);
         fence_barrier_init();
     }
@@ -140,56 +152,63 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
-    float4 ra[C::LA], rw[C::LW];
-    auto gload = [&](int kb) {
-        const int k0 = kb * BK;
+    if (warp < 8) {
+        // ------------------------------ producers ------------------------------
+        float4 ra0[C::LA], rw0[C::LW], ra1[C::LA], rw1[C::LW];
+        auto gload = [&](int kb, float4 (&ra)[C::LA], float4 (&rw)[C::LW]) {
+            const int k0 = kbeg + kb * BK;
 #pragma unroll
-        for (int i = 0; i < C::LA; ++i) {
-            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + row < M && k0 + c * 4 < K) v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + k0 + c * 4);
-            ra[i] = v;
-        }
+            for (int i = 0; i < C::LA; ++i) {
+                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m0 + row < M && k0 + c * 4 < kend) v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + k0 + c * 4);
+                ra[i] = v;
+            }
 #pragma unroll
-        for (int i = 0; i < C::LW; ++i) {
-            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + row < N && k0 + c * 4 < K) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * ldw + k0 + c * 4));
-            rw[i] = v;
-        }
-    };
-    auto sstore = [&](int s) {
-        const uint32_t sA = sbase + s * C::STAGE_BYTES, sW = sA + C::A_BYTES;
-        const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
+            for (int i = 0; i < C::LW; ++i) {
+                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n0 + row < N && k0 + c * 4 < kend) v = *reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * ldw + k0 + c * 4);
+                rw[i] = v;
+            }
+        };
+        auto stage_in = [&](int kb, const float4 (&ra)[C::LA], const float4 (&rw)[C::LW]) {
+            const int s = kb % C::STAGES;
+            if (kb >= C::STAGES) mbar_wait(&mbar_empty[s], ((kb / C::STAGES) - 1) & 1);   // MMAs reading this stage are done
+            const uint32_t sA = sbase + s * C::STAGE_BYTES, sW = sA + C::A_BYTES;
+            const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
 #pragma unroll
-        for (int i = 0; i < C::LA; ++i) {
-            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
-            uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);        // Swizzle<3,4,3>
-            float4 v = ra[i];
-            if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); sts4(sA + off, hi); sts4(sAl + off, lo); }
-            else sts4(sA + off, v);
-        }
+            for (int i = 0; i < C::LA; ++i) {
+                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
+                uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);        // Swizzle<3,4,3>
+                if (SPLIT3) { float4 hi, lo; split4(ra[i], hi, lo); sts4(sA + off, hi); sts4(sAl + off, lo); }
+                else sts4(sA + off, ra[i]);
+            }
 #pragma unroll
-        for (int i = 0; i < C::LW; ++i) {
-            int f = tid + i * THREADS, row = f >> 3, c = f & 7;
-            uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-            float4 v = rw[i];
-            if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); sts4(sW + off, hi); sts4(sWl + off, lo); }
-            else sts4(sW + off, v);
+            for (int i = 0; i < C::LW; ++i) {
+                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
+                uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+                if (SPLIT3) { float4 hi, lo; split4(rw[i], hi, lo); sts4(sW + off, hi); sts4(sWl + off, lo); }
+                else sts4(sW + off, rw[i]);
+            }
+            fence_async_smem();           // generic-proxy writes -> visible to the tensor-core (async) proxy
+            mbar_arrive(&mbar_full[s]);
+        };
+        if (KB > 0) gload(0, ra0, rw0);
+        for (int kb = 0; kb < KB; kb += 2) {
+            if (kb + 1 < KB) gload(kb + 1, ra1, rw1);
+            stage_in(kb, ra0, rw0);
+            if (kb + 1 < KB) {
+                if (kb + 2 < KB) gload(kb + 2, ra0, rw0);
+                stage_in(kb + 1, ra1, rw1);
+            }
         }
-    };
-
-    const int KB = (K + BK - 1) / BK;
-    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-    gload(0);
-    for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % C::STAGES;
-        if (kb >= C::STAGES) mbar_wait(&mbar_empty[s], ((kb / C::STAGES) - 1) & 1);   // MMAs that read this stage are done
-        sstore(s);
-        if (kb + 1 < KB) gload(kb + 1);
-        fence_async_smem();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        __syncthreads();
-        if (tid == 0) {
+    } else if (lane == 0) {
+        // ------------------------------ MMA issuer ------------------------------
+        constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % C::STAGES;
+            mbar_wait(&mbar_full[s], (kb / C::STAGES) & 1);
             tc_fence_after();
             const uint32_t sA = sbase + s * C::STAGE_BYTES, sW = sA + C::A_BYTES;
             const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
@@ -209,20 +228,25 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
         }
     }
 
-    // ---- epilogue: TMEM -> registers -> fused functor ----
-    mbar_wait(&mbar_done, 0);
-    tc_fence_after();
-    const int row = m0 + (warp & 3) * 32 + lane;
-    const int cbeg = (warp >> 2) * (BN / 2);
+    // ---- epilogue (warps 0..7): TMEM -> registers -> fused functor ----
+    if (warp < 8) {
+        if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
+        const int row = m0 + (warp & 3) * 32 + lane;
+        const int cbeg = (warp >> 2) * (BN / 2);
 #pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-        if (row < M) {
+        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 16) {
+            float v[16];
+            if (KB > 0) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+            else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int n = n0 + c0 + 4 * j;
-                if (n < N) { float q[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]}; epi(row, n, q); }
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int n = n0 + c0 + 4 * j;
+                    if (n < N) { float q[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]}; epi(row, n, q); }
+                }
             }
         }
     }
@@ -238,15 +262,18 @@ static inline bool tc_gemm_supported(int64_t M, int N, int K, int lda, int ldw) 
 }
 
 template <int BN, bool SPLIT3, class Epi>
-static int launch_tc_inst(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K, const Epi& epi) {
+static int launch_tc_inst(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K,
+                          const Epi& epi, int splits = 1, int k_per_split = 0) {
     using C = tc::Cfg<BN, SPLIT3>;
     static bool attr_set = false;
     if (!attr_set) {
         POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_tn_tc<BN, SPLIT3, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    dim3 grid((unsigned)poi_cdiv(N, BN), (unsigned)poi_cdiv(M, tc::BM));
-    POI_LAUNCH(e, (tc::k_gemm_tn_tc<BN, SPLIT3, Epi>), grid, tc::THREADS, C::SMEM_BYTES, A, lda, W, ldw, (int)M, N, K, epi);
+    if (splits <= 1) { splits = 1; k_per_split = K; }
+    dim3 grid((unsigned)poi_cdiv(N, BN), (unsigned)poi_cdiv(M, tc::BM), (unsigned)splits);
+    POI_LAUNCH(e, (tc::k_gemm_tn_tc<BN, SPLIT3, Epi>), grid, tc::THREADS, C::SMEM_BYTES, A, lda, W, ldw, (int)M, N, K,
+               k_per_split, epi);
     return 0;
 }
 
@@ -262,4 +289,57 @@ static int launch_gemm_tn_tc(poi_engine* e, const float* A, int lda, const float
     }
     if (wide) return launch_tc_inst<128, false>(e, A, lda, W, ldw, M, N, K, epi);
     return launch_tc_inst<64, false>(e, A, lda, W, ldw, M, N, K, epi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradients on the tensor cores:  C[i,j] = sum_m A[m,i] * Bm[m,j]
+// Both operands are transposed once ([N x Mp], Mp = pad4(M), K-major for the UMMA) and the long
+// reduction over m = (t, b) is split over blockIdx.z; partials are reduced in split order by the
+// same k_reduce_update / k_reduce_only kernels as the FMA path.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_transpose_ld(const float* __restrict__ in, int ld_in, int64_t R, int Cc,
+                               float* __restrict__ out, int64_t ldo) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.y * 32; const int c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int64_t r = r0 + i; int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < Cc) ? in[(size_t)r * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i; int64_t r = r0 + threadIdx.x;
+        if (c < Cc && r < ldo) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
+    }
+}
+
+static int launch_transpose_ld(poi_engine* e, const float* in, int ld_in, int64_t R, int Cc, float* out, int64_t ldo) {
+    dim3 grid((unsigned)poi_cdiv(Cc, 32), (unsigned)poi_cdiv(ldo, 32));
+    POI_CAT(e, CAT_WGRAD, 0, 2.0 * (double)R * Cc * 4);
+    POI_LAUNCH(e, k_transpose_ld, grid, dim3(32, 8), 0, in, ld_in, R, Cc, out, ldo);
+    return 0;
+}
+
+struct EpiPartial {       // split-K partial tile: part[blockIdx.z][m][n]
+    float* part; int N1, N2;
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
+        float* c = part + ((size_t)blockIdx.z * N1 + m) * N2 + n;
+        if (n + 3 < N2) st4(c, make_float4(v[0], v[1], v[2], v[3]));
+        else for (int i = 0; i < 4 && n + i < N2; ++i) c[i] = v[i];
+    }
+};
+
+// At [N1 x Mp], Bt [N2 x Mp] already transposed (leading dimension Mp, zero padded); fills plan
+static int launch_gemm_atb_tc(poi_engine* e, const float* At, const float* Bt, int64_t Mp, int N1, int N2,
+                              bool split3, AtbPlan* plan) {
+    const int tiles = (int)(poi_cdiv(N1, tc::BM) * poi_cdiv(N2, 128));
+    int64_t kblocks = poi_cdiv(Mp, tc::BK);
+    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(e->num_sms / std::max(tiles, 1), kblocks));
+    int64_t kps = poi_cdiv(kblocks, splits) * tc::BK;
+    splits = (int)poi_cdiv(Mp, kps);
+    plan->splits = splits; plan->m_per_split = kps; plan->N1 = N1; plan->N2 = N2;
+    POI_TRY(arena_get(e, (size_t)splits * N1 * N2, &plan->part));
+    POI_CAT(e, CAT_WGRAD, 2.0 * (double)Mp * N1 * N2, 0);
+    EpiPartial epi{plan->part, N1, N2};
+    if (split3) return launch_tc_inst<128, true>(e, At, (int)Mp, Bt, (int)Mp, N1, N2, (int)Mp, epi, splits, (int)kps);
+    return launch_tc_inst<128, false>(e, At, (int)Mp, Bt, (int)Mp, N1, N2, (int)Mp, epi, splits, (int)kps);
 }

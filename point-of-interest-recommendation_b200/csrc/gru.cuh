@@ -527,14 +527,35 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
 
     // ---- weight gradients (split reductions) + dense SGD, all from pre-update values ----
     AtbPlan g_ui, g_whzr, g_whc, g_bi, g_vs, g_bs;
-    POI_TRY(launch_gemm_atb(e, DA, 3 * H, X, din, TB, 3 * H, din, &g_ui));
-    POI_TRY(launch_gemm_atb(e, DA, 3 * H, Hs, H, TB, 2 * H, H, &g_whzr));
-    POI_TRY(launch_gemm_atb(e, DA + 2 * H, 3 * H, RH, H, TB, H, H, &g_whc));
-    POI_TRY(launch_colsum(e, DA, 3 * H, TB, 3 * H, &g_bi));
-    if (head) {
-        POI_TRY(launch_gemm_atb(e, S, nDp, Hc, H, TB, nDp, H, &g_vs));
-        POI_TRY(launch_colsum(e, S, nDp, TB, nDp, &g_bs));
+    const int64_t Mp = (TB + 3) / 4 * 4;
+    if (e->gemm_mode != 0 && TB >= 2048 && Mp < 0x7fffffffLL) {
+        // tensor-core path: one transpose per activation matrix, then split-K UMMA GEMMs
+        const bool s3 = e->gemm_mode == 1;
+        float *DAt, *Xt, *Hpt, *RHt;
+        POI_TRY(arena_get(e, (size_t)3 * H * Mp, &DAt)); POI_TRY(arena_get(e, (size_t)din * Mp, &Xt));
+        POI_TRY(arena_get(e, (size_t)H * Mp, &Hpt)); POI_TRY(arena_get(e, (size_t)H * Mp, &RHt));
+        POI_TRY(launch_transpose_ld(e, DA, 3 * H, TB, 3 * H, DAt, Mp));
+        POI_TRY(launch_transpose_ld(e, X, din, TB, din, Xt, Mp));
+        POI_TRY(launch_transpose_ld(e, Hs, H, TB, H, Hpt, Mp));
+        POI_TRY(launch_transpose_ld(e, RH, H, TB, H, RHt, Mp));
+        POI_TRY(launch_gemm_atb_tc(e, DAt, Xt, Mp, 3 * H, din, s3, &g_ui));
+        POI_TRY(launch_gemm_atb_tc(e, DAt, Hpt, Mp, 2 * H, H, s3, &g_whzr));
+        POI_TRY(launch_gemm_atb_tc(e, DAt + (size_t)2 * H * Mp, RHt, Mp, H, H, s3, &g_whc));
+        if (head) {
+            float *St, *Hct;
+            POI_TRY(arena_get(e, (size_t)nDp * Mp, &St)); POI_TRY(arena_get(e, (size_t)H * Mp, &Hct));
+            POI_TRY(launch_transpose_ld(e, S, nDp, TB, nDp, St, Mp));
+            POI_TRY(launch_transpose_ld(e, Hc, H, TB, H, Hct, Mp));
+            POI_TRY(launch_gemm_atb_tc(e, St, Hct, Mp, nDp, H, s3, &g_vs));
+        }
+    } else {
+        POI_TRY(launch_gemm_atb(e, DA, 3 * H, X, din, TB, 3 * H, din, &g_ui));
+        POI_TRY(launch_gemm_atb(e, DA, 3 * H, Hs, H, TB, 2 * H, H, &g_whzr));
+        POI_TRY(launch_gemm_atb(e, DA + 2 * H, 3 * H, RH, H, TB, H, H, &g_whc));
+        if (head) POI_TRY(launch_gemm_atb(e, S, nDp, Hc, H, TB, nDp, H, &g_vs));
     }
+    POI_TRY(launch_colsum(e, DA, 3 * H, TB, 3 * H, &g_bi));
+    if (head) POI_TRY(launch_colsum(e, S, nDp, TB, nDp, &g_bs));
     float* dg = mg ? mg->dense_grads : nullptr;
     POI_TRY(launch_reduce_to(e, g_ui, p->ui, din, 3 * H, din, alpha, lambda, dg ? dg + ML.ui : nullptr));
     POI_TRY(launch_reduce_to(e, g_whzr, p->wh, H, 2 * H, H, alpha, lambda, dg ? dg + ML.wh : nullptr));
