@@ -348,7 +348,8 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--batch", type=int, default=4096, help="users per step per GPU")
     ap.add_argument("--cpu-batch", type=int, default=512, help="users per CPU-oracle step")
-    ap.add_argument("--gemm-mode", type=int, default=0)
+    ap.add_argument("--gemm-mode", type=int, default=1,
+                    help="0 fp32 FMA, 1 tcgen05 3xTF32 (fp32-faithful, default), 2 tcgen05 1xTF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -58,6 +58,9 @@ int         poi_kprof_get(poi_engine* e, double* out48);
 /* 0 = SIMT fp32 FMA GEMMs, 1 = tcgen05 3xTF32 (fp32-faithful), 2 = tcgen05 1xTF32 */
 int         poi_set_gemm_mode(poi_engine* e, int mode);
 int         poi_get_gemm_mode(poi_engine* e, int* mode);
+/* tensor-core modes only: 1 (default) = the recurrence runs as one persistent fused kernel per
+ * direction, 0 = two GEMM launches per time step (kept for A/B measurements) */
+int         poi_set_fused_recurrence(poi_engine* e, int on);
 
 /* ---- first-slice kernels, individually testable ------------ */
 

@@ -89,15 +89,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 __device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-// round-to-nearest TF32 (low 13 mantissa bits zero): what the tensor core then reads exactly
+// round-to-nearest TF32 (low 13 mantissa bits zero -> exactly what the tensor core reads) with two
+// integer ops; a carry out of the mantissa bumps the exponent, which is the correct rounding
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+// hi = rn_tf32(x); lo = x - hi (exact in fp32; the tensor core truncates it to TF32: second-order error)
 __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
     hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-    lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+    lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
 constexpr int BM = 128;
@@ -154,7 +154,7 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
 
     if (warp < 8) {
         // ------------------------------ producers ------------------------------
-        float4 ra0[C::LA], rw0[C::LW], ra1[C::LA], rw1[C::LW];
+        float4 ra[4][C::LA], rw[4][C::LW];       // 4 register sets: loads run 3 k-blocks ahead of the staging
         auto gload = [&](int kb, float4 (&ra)[C::LA], float4 (&rw)[C::LW]) {
             const int k0 = kbeg + kb * BK;
 #pragma unroll
@@ -194,13 +194,15 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
             fence_async_smem();           // generic-proxy writes -> visible to the tensor-core (async) proxy
             mbar_arrive(&mbar_full[s]);
         };
-        if (KB > 0) gload(0, ra0, rw0);
-        for (int kb = 0; kb < KB; kb += 2) {
-            if (kb + 1 < KB) gload(kb + 1, ra1, rw1);
-            stage_in(kb, ra0, rw0);
-            if (kb + 1 < KB) {
-                if (kb + 2 < KB) gload(kb + 2, ra0, rw0);
-                stage_in(kb + 1, ra1, rw1);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) if (u < KB) gload(u, ra[u], rw[u]);
+        for (int kb = 0; kb < KB; kb += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kb + u < KB) {
+                    if (kb + u + 3 < KB) gload(kb + u + 3, ra[(u + 3) & 3], rw[(u + 3) & 3]);
+                    stage_in(kb + u, ra[u], rw[u]);
+                }
             }
         }
     } else if (lane == 0) {
@@ -297,25 +299,35 @@ static int launch_gemm_tn_tc(poi_engine* e, const float* A, int lda, const float
 // reduction over m = (t, b) is split over blockIdx.z; partials are reduced in split order by the
 // same k_reduce_update / k_reduce_only kernels as the FMA path.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_transpose_ld(const float* __restrict__ in, int ld_in, int64_t R, int Cc,
-                               float* __restrict__ out, int64_t ldo) {
-    __shared__ float tile[32][33];
-    const int64_t r0 = (int64_t)blockIdx.y * 32; const int c0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        int64_t r = r0 + i; int c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < R && c < Cc) ? in[(size_t)r * ld_in + c] : 0.f;
+// out[c*ldo + r] = in[r*ld_in + c]; 64x64 tiles, 128-bit global accesses on both sides; Cc, ld_in, ldo % 4 == 0
+__global__ void __launch_bounds__(256)
+k_transpose_ld(const float* __restrict__ in, int ld_in, int64_t R, int Cc, float* __restrict__ out, int64_t ldo) {
+    __shared__ float tile[64][65];
+    const int64_t r0 = (int64_t)blockIdx.y * 64; const int c0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // 16 float4 columns x 16 rows per pass
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t r = r0 + ty + 16 * i; int c = c0 + tx * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < R && c < Cc) v = *reinterpret_cast<const float4*>(in + (size_t)r * ld_in + c);
+        tile[ty + 16 * i][tx * 4 + 0] = v.x; tile[ty + 16 * i][tx * 4 + 1] = v.y;
+        tile[ty + 16 * i][tx * 4 + 2] = v.z; tile[ty + 16 * i][tx * 4 + 3] = v.w;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        int c = c0 + i; int64_t r = r0 + threadIdx.x;
-        if (c < Cc && r < ldo) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = c0 + ty + 16 * i; int64_t r = r0 + tx * 4;
+        if (c < Cc && r < ldo)
+            *reinterpret_cast<float4*>(out + (size_t)c * ldo + r) =
+                make_float4(tile[tx * 4 + 0][ty + 16 * i], tile[tx * 4 + 1][ty + 16 * i],
+                            tile[tx * 4 + 2][ty + 16 * i], tile[tx * 4 + 3][ty + 16 * i]);
     }
 }
 
 static int launch_transpose_ld(poi_engine* e, const float* in, int ld_in, int64_t R, int Cc, float* out, int64_t ldo) {
-    dim3 grid((unsigned)poi_cdiv(Cc, 32), (unsigned)poi_cdiv(ldo, 32));
+    dim3 grid((unsigned)poi_cdiv(Cc, 64), (unsigned)poi_cdiv(ldo, 64));
     POI_CAT(e, CAT_WGRAD, 0, 2.0 * (double)R * Cc * 4);
-    POI_LAUNCH(e, k_transpose_ld, grid, dim3(32, 8), 0, in, ld_in, R, Cc, out, ldo);
+    POI_LAUNCH(e, k_transpose_ld, grid, 256, 0, in, ld_in, R, Cc, out, ldo);
     return 0;
 }
 

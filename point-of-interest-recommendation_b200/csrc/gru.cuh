@@ -16,6 +16,7 @@
 #include "rows.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gru_fused.cuh"
 #include <string.h>
 
 // ---------------------------------------------------------------------------------------------
@@ -432,6 +433,11 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
     phase_mark(e, 2);
     // hoisted input projection: AX = X . ui^T + bi over every (t, b)
     POI_TRY(gemm_tn(e, X, din, p->ui, din, TB, 3 * H, din, EpiBiasStore{AX, 3 * H, p->bi, 3 * H}));
+    if (e->gemm_mode != 0 && e->fuse_recurrence && fused::fwd_supported(H)) {
+        // the whole recurrence in one persistent tcgen05 kernel (gru_fused.cuh)
+        POI_TRY(fused::launch_gru_fwd_fused(e, AX, p->wh, Hs, Z, R, C, RH, B, T, H, e->gemm_mode == 1));
+        return 0;
+    }
     for (int j = 0; j < T; ++j) {
         const float* hp = Hs + (size_t)j * B * H;
         const float* AXj = AX + (size_t)j * B * 3 * H;
