@@ -230,26 +230,42 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
         }
     }
 
-    // ---- epilogue (warps 0..7): TMEM -> registers -> fused functor ----
+    // ---- epilogue (warps 0..7): TMEM -> registers -> per-warp smem transpose -> fused functor ----
+    // tcgen05.ld hands each thread one accumulator ROW (lane = row); calling the functor like that makes
+    // every global access touch 32 different lines.  Each warp therefore bounces its 32 rows x 32 columns
+    // through a private 4 KB swizzled staging tile (the pipeline stages are free by now) and calls the
+    // functor with 8 lanes per row: 4 rows x 128 contiguous bytes per instruction.
     if (warp < 8) {
         if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
-        const int row = m0 + (warp & 3) * 32 + lane;
+        const uint32_t stg = sbase + warp * 4096;
+        const int rbase = m0 + (warp & 3) * 32;
         const int cbeg = (warp >> 2) * (BN / 2);
+        const int rr0 = lane >> 3, qq = lane & 7;
 #pragma unroll 1
-        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 16) {
+        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
             float v[16];
-            if (KB > 0) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-            else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.f;
-            }
-            if (row < M) {
+            for (int h = 0; h < 2; ++h) {
+                if (KB > 0) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c0 + 16 * h), v);
+                else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int n = n0 + c0 + 4 * j;
-                    if (n < N) { float q[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]}; epi(row, n, q); }
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    sts4(stg + lane * 128 + (((4 * h + q) ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = rr0 + 4 * i;
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                             : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
+                const int m = rbase + rr, n = n0 + c0 + 4 * qq;
+                if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4); }
+            }
+            __syncwarp();
         }
     }
     tc_fence_before();
