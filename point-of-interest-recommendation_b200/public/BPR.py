@@ -46,6 +46,10 @@ class MfBasic(object):
         se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
         return (self.trained_users.t[se] @ self.trained_items.t[:-1].T).cpu().numpy()
 
+    def compute_sub_topk(self, start_end, top_k):
+        se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
+        return self.engine.score_topk(self.trained_users.t[se].contiguous(), self.trained_items.t[:-1], top_k).cpu().numpy()
+
     def compute_sub_auc_preference(self, start_end):
         se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
         items = self.trained_items.t

@@ -70,6 +70,14 @@ class GruBasic(object):
         sub = self.trained_users.t[se] @ self.trained_items.t[:-1].T
         return sub.cpu().numpy()
 
+    def compute_sub_topk(self, start_end, top_k):
+        """Indices of the top_k scores per user, best first, without materialising the score rows on the
+        host: users . items^T fused with a streaming top-K on the device.  Same
+        ranking as compute_sub_all_scores + Valuate's argpartition/argsort up to fp32 near-ties."""
+        se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
+        users = self.trained_users.t[se].contiguous()
+        return self.engine.score_topk(users, self.trained_items.t[:-1], top_k).cpu().numpy()
+
     def compute_sub_auc_preference(self, start_end):
         se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
         items = self.trained_items.t

@@ -75,6 +75,14 @@ class OboSpatialGru(GruBasic):
             sub = sub + self._scal.t[0] * self.prob.t[se]
         return sub.cpu().numpy()
 
+    def compute_sub_topk(self, start_end, top_k):
+        """Fused device scoring + top-K with the `wd * prob` term (GRU_Spatial.py:117-125)."""
+        se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
+        users = self.trained_users.t[se].contiguous()
+        prob = self.prob.t[se].contiguous() if self.prob is not None else None
+        wd = float(self._scal.t[0].item())
+        return self.engine.score_topk(users, self.trained_items.t[:-1], top_k, prob, wd).cpu().numpy()
+
     def _params(self, trained=False):
         return Engine.gru_params(self.trained_items.t if trained else self.lt.t, self.ui.t, self.wh.t, self.bi.t,
                                  self.trained_dists.t if trained else self.di.t, self.vs.t, self.bs.t, self._scal.t)

@@ -114,3 +114,26 @@ def test_checkpoint_roundtrip(engine, tmp_path):
     drv.load_checkpoint(m2, f)
     for k in ("loss_weight", "wd", "lt", "di", "ui", "wh", "bi", "vs", "bs"):
         assert np.array_equal(np.asarray(getattr(m1, k).get_value(), dtype=np.float32), np.asarray(getattr(m2, k).get_value(), dtype=np.float32)), k
+
+
+def test_gpu_topk_gives_same_recall(engine, tmp_path):
+    """p['gpu_topk'] = 1 routes Valuate's ranking through the fused score + top-K kernel; the metrics
+    must equal the host argpartition path."""
+    from poi_b200 import prog_bpr_gru_spatial as drv
+    from poi_b200.public.Global_Best import GlobalBest
+    from poi_b200.public.Valuate import fun_predict_auc_recall_map_ndcg
+    path = _dataset(tmp_path, n_user=40, n_item=300)
+    p = drv.default_params(); p.update(dataset="Synth.txt", epochs=1, latent_size=8, gru=2, dd=2000, at_nums=[5, 10, 20])
+    random.seed(9)
+    pas = drv.Params(p=p, path=path)
+    model, _ = pas.build_model_one_by_one(2)
+    for u in range(pas.user_num):
+        model.train(u)
+    _, ses = pas.compute_start_end('test'); _, ses_auc = pas.compute_start_end('test_auc')
+    drv.compute_user_representations(p, model, ses, pas.ulptai, pas.dist_num)
+    res = {}
+    for flag in (0, 1):
+        p['gpu_topk'] = flag
+        res[flag] = fun_predict_auc_recall_map_ndcg(p, model, GlobalBest(p['at_nums']), 0, ses_auc, ses, pas.tes_buys_masks, pas.tes_masks)
+    for k in ("recall", "map", "ndcg"):
+        assert np.allclose(res[0][k], res[1][k], atol=1e-12), k
