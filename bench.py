@@ -197,6 +197,7 @@ def run_ours(args):
                                   [ALPHA, LAM], I, D, d, d, st, device=local_rank)
     eng = model.engine
     eng.set_gemm_mode(args.gemm_mode)
+    eng.set_fused_recurrence(bool(args.fused))
     U_loc = len(mine)
     B = min(args.batch, U_loc)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -324,7 +325,7 @@ def run_ours(args):
         "config": {"workload": "c2: Distance2Pre |POI|=%d |U|=%d seq=%d d=%d D=%d" % (I, U, seq, d, D),
                    "users_per_step_per_gpu": B, "check_ins_per_step": done_all / K,
                    "semantics": "mini-batch extension (SURVEY 3.6); B=1 is the reference's one-by-one mode",
-                   "gemm_mode": args.gemm_mode, "l2": "flushed between timed steps (256 MB write)",
+                   "gemm_mode": args.gemm_mode, "fused_recurrence": bool(args.fused) and args.gemm_mode != 0, "l2": "flushed between timed steps (256 MB write)",
                    "parallelism": "1 GPU" if world == 1 else
                    "dp%d: users sharded, item table row-sharded (row %% %d) with NCCL all-to-all of rows / row-gradients, "
                    "dense gradients all-reduced" % (world, world)},
@@ -350,6 +351,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=512, help="users per CPU-oracle step")
     ap.add_argument("--gemm-mode", type=int, default=1,
                     help="0 fp32 FMA, 1 tcgen05 3xTF32 (fp32-faithful, default), 2 tcgen05 1xTF32")
+    ap.add_argument("--fused", type=int, default=1, help="1 = persistent fused recurrence kernel (tensor-core modes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

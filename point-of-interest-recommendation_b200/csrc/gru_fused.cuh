@@ -1,18 +1,22 @@
-// gru_fused.cuh -- the GRU recurrence as ONE persistent tcgen05 kernel per direction.
+// gru_fused.cuh -- the GRU forward recurrence as ONE persistent tcgen05 kernel.
 //
 // The reference's `theano.scan` runs the cell once per time step (GRU.py:345-360,
-// GRU_Spatial.py:170-197); the first version of this engine did the same with two GEMM launches
-// per step.  Users are independent inside a step and across steps only through their own h, so a
-// CTA can own 128 users for the WHOLE sequence: h_t never leaves the SM between steps.
+// GRU_Spatial.py:170-197); the per-step path of this engine does the same with two GEMM launches
+// per step.  Users are independent inside a step and coupled across steps only through their own
+// h, so a CTA can own 128 users for the WHOLE sequence: h_t never leaves the SM between steps.
 //
-//   warps 0-3  epilogue: thread = one user row.  TMEM accumulator -> gate math -> Z/R/C/H to global
-//              (saved for BPTT) and the next A operand (r*h, then h_t) straight into shared memory
-//              in the UMMA layout (128B-swizzled K-major, hi/lo split for 3xTF32)
-//   warps 4-7  producers: stream the Wh tiles (L2-resident, identical every step) through a ring
+//   warps 0-3  epilogue, thread = one user row (= TMEM lane).  Accumulator -> gate math -> next A
+//              operand (r*h, then h_t) written straight into shared memory in the UMMA layout
+//              (128B-swizzled K-major, hi/lo split for 3xTF32).  z and (1-z)*h_prev are stashed in the
+//              TMEM columns they came from, so epilogue 2 reloads nothing.  Z/R/C/H go to global
+//              memory (saved for BPTT) through a per-warp staging tile so that stores are coalesced.
+//   warps 4-5  Wh producers: stream the Wh tiles (L2-resident, identical every step) through a ring
+//   warps 6-7  AX producers: cp.async the hoisted input projection rows of the coming chunks into a
+//              ring (coalesced, no registers), completion signalled on mbarriers
 //   warp  8    one thread issues tcgen05.mma:  D1z|D1r = h . Wh[0:2]^T,  D2 = (r*h) . Wh[2]^T
 //
-// Per step the chain is GEMM1 -> epilogue1 -> GEMM2 -> epilogue2; nothing else is on it: the input
-// projection AX (hoisted GEMM) and Wh arrive by prefetch.  H must be a multiple of 32, <= 128.
+// Per step the chain is GEMM1 -> epilogue1 -> GEMM2 -> epilogue2; everything else is prefetch.
+// H must be a multiple of 32, <= 128.
 #pragma once
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -23,6 +27,28 @@ using namespace tc;
 constexpr int FM = 128;               // users per CTA = UMMA M
 constexpr int F_THREADS = 288;
 constexpr int A_KB_BYTES = FM * 128;  // one 32-float k-block of the A tile
+constexpr int AX_TILE = FM * 64;      // 128 rows x 16 floats
+constexpr int AX_STAGES = 3;
+constexpr int OUT_STG = 32 * 64;      // per-warp output staging: 32 rows x 16 floats
+
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 x;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(a));
+    return x;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 64-byte rows (16 floats): XOR the 16-byte chunk index with bits 1..2 of the row -> lane=row accesses
+// and 4-lanes-per-row accesses are both bank-conflict free
+__device__ __forceinline__ uint32_t sw64(int row, int c) { return row * 64 + ((c ^ ((row >> 1) & 3)) << 4); }
 
 template <bool SPLIT3>
 __device__ __forceinline__ void a_store16(uint32_t a_hi, uint32_t a_lo, int row, int col, const float (&v)[16]) {
@@ -35,19 +61,34 @@ __device__ __forceinline__ void a_store16(uint32_t a_hi, uint32_t a_lo, int row,
         else sts4(a_hi + off, x);
     }
 }
-__device__ __forceinline__ void ld16(const float* p, bool ok, float (&v)[16]) {
+// exact fp32 values of the A tile (hi + lo is exact by construction)
+template <bool SPLIT3>
+__device__ __forceinline__ void a_load16(uint32_t a_hi, uint32_t a_lo, int row, int col, float (&v)[16]) {
+    const int kb = col >> 5, cc0 = (col & 31) >> 2;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        float4 x = ok ? *reinterpret_cast<const float4*>(p + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t off = kb * A_KB_BYTES + row * 128 + (((cc0 + q) ^ (row & 7)) << 4);
+        float4 x = lds4(a_hi + off);
+        if (SPLIT3) { float4 l = lds4(a_lo + off); x.x += l.x; x.y += l.y; x.z += l.z; x.w += l.w; }
         v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
 }
-__device__ __forceinline__ void st16(float* p, const float (&v)[16]) {
+// one warp: 32 rows x 16 floats from registers (lane = row) to global with 4 lanes per row
+__device__ __forceinline__ void warp_store_chunk(uint32_t stg, int lane, const float (&v)[16], float* gbase, int ld,
+                                                 int rows_valid) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) sts4(stg + sw64(lane, q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    __syncwarp();
+    const int qq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        float4 x = lds4(stg + sw64(rr, qq));
+        if (rr < rows_valid) *reinterpret_cast<float4*>(gbase + (size_t)rr * ld + 4 * qq) = x;
+    }
+    __syncwarp();
 }
 
-// issue the MMAs of one k-block: A tile (hi/lo) x W stage (hi/lo) -> D
 template <bool SPLIT3>
 __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo,
                                            uint32_t idesc, bool first) {
@@ -66,24 +107,28 @@ __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint3
 
 template <bool SPLIT3>
 __global__ void __launch_bounds__(F_THREADS, 1)
-k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, float* Hs, float* Z, float* R,
-                float* C, float* RH, int B, int T, int H) {
-    constexpr int STAGES = SPLIT3 ? 3 : 4;
+k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, float* __restrict__ Hs, float* __restrict__ Z,
+                float* __restrict__ R, float* __restrict__ C, int B, int T, int H) {
+    constexpr int WST = 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[STAGES], w_empty[STAGES], a_ready, d1_full, d2_full;
+    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[AX_STAGES], ax_empty[AX_STAGES], a_ready, d1_full, d2_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KB = H >> 5;
+    const int KB = H >> 5, NCH = H >> 4;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_hi = sbase, a_lo = sbase + KB * A_KB_BYTES;
-    const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
     const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
+    const uint32_t ax_base = w_base + WST * w_stage;
+    const uint32_t out_base = ax_base + AX_STAGES * AX_TILE;
     const int m0 = blockIdx.x * FM;
     uint32_t ncols = 32; while (ncols < (uint32_t)(3 * H)) ncols <<= 1;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&w_full[s], 128); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 64); mbar_init(&w_empty[s], 1); }
+#pragma unroll
+        for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&ax_full[s], 64); mbar_init(&ax_empty[s], 128); }
         mbar_init(&a_ready, 128); mbar_init(&d1_full, 1); mbar_init(&d2_full, 1);
         fence_barrier_init();
     }
@@ -96,10 +141,11 @@ k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, floa
 
     if (warp < 4) {
         // ================================ epilogue ================================
-        const int row = tid;                       // TMEM lane == row of the tile
-        const int64_t m = (int64_t)m0 + row;
-        const bool ok = m < B;
+        const int row = tid;                                   // TMEM lane == row of the tile
+        const bool ok = m0 + row < B;
         const uint32_t tl = (uint32_t)(warp * 32) << 16;
+        const uint32_t stg = out_base + warp * OUT_STG;
+        const int rows_valid = min(32, B - (m0 + warp * 32));  // rows of this warp's quadrant that exist (may be <= 0)
         {   // h_{-1} = 0 -> A tile
             float zero[16];
 #pragma unroll
@@ -108,91 +154,97 @@ k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, floa
             fence_async_smem();
             mbar_arrive(&a_ready);
         }
+        int64_t axi = 0;                                       // AX ring position (tiles consumed so far)
+        auto ax_take = [&](float (&v)[16]) {
+            const int s = (int)(axi % AX_STAGES);
+            mbar_wait(&ax_full[s], (uint32_t)(axi / AX_STAGES) & 1);
+            const uint32_t t = ax_base + s * AX_TILE;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 x = lds4(t + sw64(row, q));
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            }
+            mbar_arrive(&ax_empty[s]);
+            ++axi;
+        };
         for (int j = 0; j < T; ++j) {
-            const size_t rb = (size_t)j * B + (ok ? m : 0);
-            const float* ax = AX + rb * 3 * H;
-            const float* hp = Hs + rb * H;
-            float* hn = Hs + (rb + B) * H;
-            float *zj = Z + rb * H, *rj = R + rb * H, *cj = C + rb * H, *rhj = RH + rb * H;
-            // ---- epilogue 1: z, r, r*h ----
-            float axz[16], axr[16], hv[16];
-            ld16(ax, ok, axz); ld16(ax + H, ok, axr); ld16(hp, ok, hv);          // in flight while GEMM1 runs
+            const size_t wrow = (size_t)j * B + m0 + warp * 32;            // first global row of this warp at step j
+            // ---- epilogue 1: z, r, r*h ; stash z and (1-z)*h ----
             mbar_wait(&d1_full, j & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float nz[16], nr[16], nh[16];
-                const bool more = c0 + 16 < H;
-                if (more) { ld16(ax + c0 + 16, ok, nz); ld16(ax + H + c0 + 16, ok, nr); ld16(hp + c0 + 16, ok, nh); }
-                float dz[16], dr[16], zz[16], rr[16], rh[16];
+            for (int k = 0; k < NCH; ++k) {
+                const int c0 = 16 * k;
+                float a[16], b[16], hv[16], dz[16], dr[16];
+                ax_take(a); ax_take(b);
                 tmem_ld16(tmem + tl + (uint32_t)c0, dz);
                 tmem_ld16(tmem + tl + (uint32_t)(H + c0), dr);
+                a_load16<SPLIT3>(a_hi, a_lo, row, c0, hv);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    zz[i] = sigmoidf_(dz[i] + axz[i]);
-                    rr[i] = sigmoidf_(dr[i] + axr[i]);
-                    rh[i] = ok ? rr[i] * hv[i] : 0.f;
+                    const float zz = sigmoidf_(dz[i] + a[i]);
+                    const float rr = sigmoidf_(dr[i] + b[i]);
+                    const float h_ = ok ? hv[i] : 0.f;
+                    dz[i] = zz; dr[i] = rr;
+                    a[i] = rr * h_;                 // r*h -> next A operand
+                    b[i] = (1.f - zz) * h_;         // (1-z)*h_prev, used by epilogue 2
                 }
-                if (ok) { st16(zj + c0, zz); st16(rj + c0, rr); st16(rhj + c0, rh); }
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, rh);
-                if (more) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { axz[i] = nz[i]; axr[i] = nr[i]; hv[i] = nh[i]; }
-                }
+                tmem_st16(tmem + tl + (uint32_t)c0, dz);              // stash z
+                tmem_st16(tmem + tl + (uint32_t)(H + c0), b);         // stash (1-z)*h_prev
+                a_store16<SPLIT3>(a_hi, a_lo, row, c0, a);
+                warp_store_chunk(stg, lane, dz, Z + wrow * H + c0, H, rows_valid);
+                warp_store_chunk(stg, lane, dr, R + wrow * H + c0, H, rows_valid);
             }
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(&a_ready);                 // r*h tile ready, D1 drained
+            mbar_arrive(&a_ready);                 // r*h tile ready
             // ---- epilogue 2: c, h_t ----
-            float axc[16], zv[16];
-            ld16(ax + 2 * H, ok, axc); ld16(zj, ok, zv); ld16(hp, ok, hv);
             mbar_wait(&d2_full, j & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float nc[16], nz[16], nh[16];
-                const bool more = c0 + 16 < H;
-                if (more) { ld16(ax + 2 * H + c0 + 16, ok, nc); ld16(zj + c0 + 16, ok, nz); ld16(hp + c0 + 16, ok, nh); }
-                float dc[16], cc[16], hh[16];
+            for (int k = 0; k < NCH; ++k) {
+                const int c0 = 16 * k;
+                float a[16], dc[16], zz[16], u[16];
+                ax_take(a);
                 tmem_ld16(tmem + tl + (uint32_t)(2 * H + c0), dc);
+                tmem_ld16(tmem + tl + (uint32_t)c0, zz);
+                tmem_ld16(tmem + tl + (uint32_t)(H + c0), u);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    cc[i] = tanhf(dc[i] + axc[i]);
-                    hh[i] = ok ? (1.f - zv[i]) * hv[i] + zv[i] * cc[i] : 0.f;
+                    const float cc = tanhf(dc[i] + a[i]);
+                    dc[i] = cc;
+                    u[i] = ok ? u[i] + zz[i] * cc : 0.f;   // h_t = (1-z) h_prev + z c
                 }
-                if (ok) { st16(cj + c0, cc); st16(hn + c0, hh); }
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, hh);
-                if (more) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { axc[i] = nc[i]; zv[i] = nz[i]; hv[i] = nh[i]; }
-                }
+                a_store16<SPLIT3>(a_hi, a_lo, row, c0, u);
+                warp_store_chunk(stg, lane, dc, C + wrow * H + c0, H, rows_valid);
+                warp_store_chunk(stg, lane, u, Hs + (wrow + B) * H + c0, H, rows_valid);
             }
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(&a_ready);                 // h_t tile ready, D2 drained
+            mbar_arrive(&a_ready);                 // h_t tile ready
         }
-    } else if (warp < 8) {
-        // ================================ Wh producers ================================
+    } else if (warp < 6) {
+        // ================================ Wh producers (64 threads) ================================
         const int ptid = tid - 128;
-        const int LW = H >> 4;                     // 16-byte chunks per thread per tile (H*8/128)
+        const int LW = H >> 3;                     // 16-byte chunks per thread per tile (H*8/64)
         const int64_t n_tiles = (int64_t)T * 3 * KB;
-        float4 r0[8], r1[8];
-        auto gload = [&](int64_t ws, float4 (&rg)[8]) {
+        float4 r0[16], r1[16];
+        auto gload = [&](int64_t ws, float4 (&rg)[16]) {
             const int t12 = (int)(ws % (3 * KB)), gate = t12 / KB, kb = t12 % KB;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 if (i < LW) {
-                    int f = ptid + i * 128, rw = f >> 3, c = f & 7;
+                    int f = ptid + i * 64, rw = f >> 3, c = f & 7;
                     rg[i] = __ldg(reinterpret_cast<const float4*>(wh + ((size_t)gate * H + rw) * H + kb * 32 + c * 4));
                 }
             }
         };
-        auto stage_in = [&](int64_t ws, const float4 (&rg)[8]) {
-            const int s = (int)(ws % STAGES);
-            if (ws >= STAGES) mbar_wait(&w_empty[s], (uint32_t)((ws / STAGES) - 1) & 1);
+        auto stage_in = [&](int64_t ws, const float4 (&rg)[16]) {
+            const int s = (int)(ws % WST);
+            if (ws >= WST) mbar_wait(&w_empty[s], (uint32_t)((ws / WST) - 1) & 1);
             const uint32_t sW = w_base + s * w_stage, sWl = sW + w_tile;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 if (i < LW) {
-                    int f = ptid + i * 128, rw = f >> 3, c = f & 7;
+                    int f = ptid + i * 64, rw = f >> 3, c = f & 7;
                     uint32_t off = rw * 128 + ((c ^ (rw & 7)) << 4);
                     if (SPLIT3) { float4 hi, lo; split4(rg[i], hi, lo); sts4(sW + off, hi); sts4(sWl + off, lo); }
                     else sts4(sW + off, rg[i]);
@@ -210,16 +262,38 @@ k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, floa
                 stage_in(ws + 1, r1);
             }
         }
+    } else if (warp < 8) {
+        // ================================ AX producers (64 threads, cp.async) ================================
+        const int ptid = tid - 192;
+        const int per_step = 3 * NCH;
+        const int64_t n_tiles = (int64_t)T * per_step;
+        for (int64_t ai = 0; ai < n_tiles; ++ai) {
+            const int s = (int)(ai % AX_STAGES);
+            if (ai >= AX_STAGES) mbar_wait(&ax_empty[s], (uint32_t)((ai / AX_STAGES) - 1) & 1);
+            const int j = (int)(ai / per_step), ti = (int)(ai % per_step);
+            const int gate = ti < 2 * NCH ? (ti & 1) : 2;
+            const int k = ti < 2 * NCH ? (ti >> 1) : ti - 2 * NCH;
+            const float* src = AX + ((size_t)j * B + m0) * 3 * H + gate * H + 16 * k;
+            const uint32_t dst = ax_base + s * AX_TILE;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int f = ptid + i * 64, rw = f >> 2, c = f & 3;
+                if (m0 + rw < B)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + sw64(rw, c)), "l"(src + (size_t)rw * 3 * H + 4 * c) : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ax_full[s])) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (lane == 0) {
         // ================================ MMA issuer ================================
         int64_t ws = 0; uint32_t pa = 0;
         for (int j = 0; j < T; ++j) {
-            mbar_wait(&a_ready, pa & 1); ++pa;     // h_{j-1} tile staged (and D2 of the previous step drained)
+            mbar_wait(&a_ready, pa & 1); ++pa;     // h_{j-1} tile staged (and the stashes of step j-1 consumed)
             tc_fence_after();
             for (int half = 0; half < 2; ++half) {
                 for (int kb = 0; kb < KB; ++kb, ++ws) {
-                    const int s = (int)(ws % STAGES);
-                    mbar_wait(&w_full[s], (uint32_t)(ws / STAGES) & 1);
+                    const int s = (int)(ws % WST);
+                    mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
                     tc_fence_after();
                     const uint32_t sW = w_base + s * w_stage;
                     mma_kblock<SPLIT3>(tmem + half * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
@@ -230,8 +304,8 @@ k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, floa
             mbar_wait(&a_ready, pa & 1); ++pa;     // r*h tile staged
             tc_fence_after();
             for (int kb = 0; kb < KB; ++kb, ++ws) {
-                const int s = (int)(ws % STAGES);
-                mbar_wait(&w_full[s], (uint32_t)(ws / STAGES) & 1);
+                const int s = (int)(ws % WST);
+                mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
                 tc_fence_after();
                 const uint32_t sW = w_base + s * w_stage;
                 mma_kblock<SPLIT3>(tmem + 2 * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
@@ -247,23 +321,35 @@ k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, floa
 
 static inline bool fwd_supported(int H) { return H % 32 == 0 && H >= 32 && H <= 128; }
 
+// RH = R * H_prev (the r-gated state the candidate GEMM consumed): the fused kernel keeps it on chip, the
+// weight-gradient stage wants it in memory
+__global__ void k_mul_rh(const float* __restrict__ R, const float* __restrict__ Hprev, float* __restrict__ RH, int64_t n4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 r = reinterpret_cast<const float4*>(R)[i], h = reinterpret_cast<const float4*>(Hprev)[i];
+    reinterpret_cast<float4*>(RH)[i] = make_float4(r.x * h.x, r.y * h.y, r.z * h.z, r.w * h.w);
+}
+
 template <bool SPLIT3>
 static int launch_fwd_inst(poi_engine* e, const float* AX, const float* wh, float* Hs, float* Z, float* R, float* C,
-                           float* RH, int B, int T, int H) {
-    constexpr int STAGES = SPLIT3 ? 3 : 4;
+                           int B, int T, int H) {
     const int KB = H / 32;
-    size_t smem = (size_t)KB * A_KB_BYTES * (SPLIT3 ? 2 : 1) + (size_t)STAGES * H * 128 * (SPLIT3 ? 2 : 1) + 1024;
+    size_t smem = (size_t)KB * A_KB_BYTES * (SPLIT3 ? 2 : 1) + (size_t)2 * H * 128 * (SPLIT3 ? 2 : 1) +
+                  (size_t)AX_STAGES * AX_TILE + 4 * OUT_STG + 1024;
     POI_CK(e, cudaFuncSetAttribute(k_gru_fwd_fused<SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // flops the tensor pipe is asked for: per step 2*B*H*3H (x3 products in 3xTF32 are not counted twice)
     POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
-    POI_LAUNCH(e, (k_gru_fwd_fused<SPLIT3>), (unsigned)poi_cdiv(B, FM), F_THREADS, smem, AX, wh, Hs, Z, R, C, RH, B, T, H);
+    POI_LAUNCH(e, (k_gru_fwd_fused<SPLIT3>), (unsigned)poi_cdiv(B, FM), F_THREADS, smem, AX, wh, Hs, Z, R, C, B, T, H);
     return 0;
 }
 
 static int launch_gru_fwd_fused(poi_engine* e, const float* AX, const float* wh, float* Hs, float* Z, float* R,
                                 float* C, float* RH, int B, int T, int H, bool split3) {
-    if (split3) return launch_fwd_inst<true>(e, AX, wh, Hs, Z, R, C, RH, B, T, H);
-    return launch_fwd_inst<false>(e, AX, wh, Hs, Z, R, C, RH, B, T, H);
+    if (split3) POI_TRY(launch_fwd_inst<true>(e, AX, wh, Hs, Z, R, C, B, T, H));
+    else POI_TRY(launch_fwd_inst<false>(e, AX, wh, Hs, Z, R, C, B, T, H));
+    const int64_t n4 = (int64_t)T * B * H / 4;
+    POI_CAT(e, CAT_ELTWISE, 0, 3.0 * (double)n4 * 16);
+    POI_LAUNCH(e, k_mul_rh, (unsigned)poi_cdiv(n4, 256), 256, 0, R, Hs, RH, n4);
+    return 0;
 }
 
 }  // namespace fused

@@ -180,3 +180,29 @@ def test_spatial_minibatch_tensor_core_modes(engine, mode, rtol):
     got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
     for k in got:
         assert_close(got[k], ref[k], rtol, k)
+
+
+@pytest.mark.parametrize("mode,rtol", [(1, 1e-4), (2, 2e-2)])
+@pytest.mark.parametrize("n_user,d", [(192, 128), (70, 64), (5, 32)])
+def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d):
+    """The persistent fused forward-recurrence kernel (gru_fused.cuh) against the oracle, ragged batch
+    sizes (partial 128-user tiles) and H in {32, 64, 128}."""
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(500 + n_user + d)
+    n_item, lmax, n_dist = 2000, 13, 60
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    tes_d = [[n_dist]] * n_user
+    model = SpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    engine.set_gemm_mode(mode); engine.set_fused_recurrence(True)
+    try:
+        for _ in range(2):
+            se = np.arange(n_user, dtype=np.int32)
+            los, sur, upq, ls = model.train(se)
+            (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
+            assert_close([los, sur, upq], [rl, rs_, ru], rtol, "losses")
+    finally:
+        engine.set_gemm_mode(0); engine.set_fused_recurrence(False)
+    got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
+    for k in got:
+        assert_close(got[k], ref[k], rtol, k)
