@@ -155,41 +155,42 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
     if (warp < 8) {
         // ------------------------------ producers ------------------------------
         float4 ra[4][C::LA], rw[4][C::LW];       // 4 register sets: loads run 3 k-blocks ahead of the staging
-        auto gload = [&](int kb, float4 (&ra)[C::LA], float4 (&rw)[C::LW]) {
+        // per-thread constants: chunk f = tid + i*256 -> row = (tid>>3) + 32 i, 16-byte chunk c = tid & 7, so the
+        // swizzle term (row & 7) and the chunk are fixed per thread; only +i*32 rows / +k0 move
+        const int srow = tid >> 3, sc = tid & 7;
+        const uint32_t soff = srow * 128 + ((sc ^ (srow & 7)) << 4);
+        const float* pA = A + (size_t)(m0 + srow) * lda + sc * 4;
+        const float* pW = W + (size_t)(n0 + srow) * ldw + sc * 4;
+        const size_t strA = (size_t)32 * lda, strW = (size_t)32 * ldw;
+        uint32_t okA = 0, okW = 0;
+#pragma unroll
+        for (int i = 0; i < C::LA; ++i) okA |= (m0 + srow + 32 * i < M ? 1u : 0u) << i;
+#pragma unroll
+        for (int i = 0; i < C::LW; ++i) okW |= (n0 + srow + 32 * i < N ? 1u : 0u) << i;
+        auto gload = [&](int kb, float4 (&ra_)[C::LA], float4 (&rw_)[C::LW]) {
             const int k0 = kbeg + kb * BK;
+            const bool kin = k0 + sc * 4 < kend;
 #pragma unroll
-            for (int i = 0; i < C::LA; ++i) {
-                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m0 + row < M && k0 + c * 4 < kend) v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + k0 + c * 4);
-                ra[i] = v;
-            }
+            for (int i = 0; i < C::LA; ++i)
+                ra_[i] = (kin && ((okA >> i) & 1u)) ? *reinterpret_cast<const float4*>(pA + i * strA + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < C::LW; ++i) {
-                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n0 + row < N && k0 + c * 4 < kend) v = *reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * ldw + k0 + c * 4);
-                rw[i] = v;
-            }
+            for (int i = 0; i < C::LW; ++i)
+                rw_[i] = (kin && ((okW >> i) & 1u)) ? *reinterpret_cast<const float4*>(pW + i * strW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        auto stage_in = [&](int kb, const float4 (&ra)[C::LA], const float4 (&rw)[C::LW]) {
+        auto stage_in = [&](int kb, const float4 (&ra_)[C::LA], const float4 (&rw_)[C::LW]) {
             const int s = kb % C::STAGES;
             if (kb >= C::STAGES) mbar_wait(&mbar_empty[s], ((kb / C::STAGES) - 1) & 1);   // MMAs reading this stage are done
-            const uint32_t sA = sbase + s * C::STAGE_BYTES, sW = sA + C::A_BYTES;
+            const uint32_t sA = sbase + s * C::STAGE_BYTES + soff, sW = sA + C::A_BYTES;
             const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
 #pragma unroll
             for (int i = 0; i < C::LA; ++i) {
-                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
-                uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);        // Swizzle<3,4,3>
-                if (SPLIT3) { float4 hi, lo; split4(ra[i], hi, lo); sts4(sA + off, hi); sts4(sAl + off, lo); }
-                else sts4(sA + off, ra[i]);
+                if (SPLIT3) { float4 hi, lo; split4(ra_[i], hi, lo); sts4(sA + i * 4096, hi); sts4(sAl + i * 4096, lo); }
+                else sts4(sA + i * 4096, ra_[i]);
             }
 #pragma unroll
             for (int i = 0; i < C::LW; ++i) {
-                int f = tid + i * PRODUCERS, row = f >> 3, c = f & 7;
-                uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-                if (SPLIT3) { float4 hi, lo; split4(rw[i], hi, lo); sts4(sW + off, hi); sts4(sWl + off, lo); }
-                else sts4(sW + off, rw[i]);
+                if (SPLIT3) { float4 hi, lo; split4(rw_[i], hi, lo); sts4(sW + i * 4096, hi); sts4(sWl + i * 4096, lo); }
+                else sts4(sW + i * 4096, rw_[i]);
             }
             fence_async_smem();           // generic-proxy writes -> visible to the tensor-core (async) proxy
             mbar_arrive(&mbar_full[s]);
