@@ -106,7 +106,7 @@ struct EpiBiasStore {               // C = acc + bias          (input projection
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
         float* c = C + (size_t)m * ldc + n;
         if (n + 3 < N) {
-            float4 b = bias ? ld4(bias + n) : f4zero();
+            float4 b = bias ? ldg4(bias + n) : f4zero();
             st4(c, make_float4(v[0] + b.x, v[1] + b.y, v[2] + b.z, v[3] + b.w));
         } else {
             for (int i = 0; i < 4 && n + i < N; ++i) c[i] = v[i] + (bias ? bias[n + i] : 0.f);
@@ -117,13 +117,13 @@ struct EpiBiasStore {               // C = acc + bias          (input projection
 struct EpiZR {   // z_r = sigmoid(ui[:2].x + wh[:2].h + bi[:2])   (GRU_Spatial.py:173-175); also r*h
     const float* AXj; const float* hp; float* Z; float* R; float* RH; int H;
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
-        float4 ax = ld4(AXj + (size_t)m * 3 * H + n);
+        float4 ax = ldg4(AXj + (size_t)m * 3 * H + n);
         float4 s = make_float4(sigmoidf_(v[0] + ax.x), sigmoidf_(v[1] + ax.y), sigmoidf_(v[2] + ax.z), sigmoidf_(v[3] + ax.w));
         if (n < H) {
             st4(Z + (size_t)m * H + n, s);
         } else {
             size_t o = (size_t)m * H + (n - H);
-            float4 h = ld4(hp + o);
+            float4 h = ldg4(hp + o);
             st4(R + o, s);
             st4(RH + o, make_float4(s.x * h.x, s.y * h.y, s.z * h.z, s.w * h.w));
         }
@@ -133,9 +133,9 @@ struct EpiZR {   // z_r = sigmoid(ui[:2].x + wh[:2].h + bi[:2])   (GRU_Spatial.p
 struct EpiC {    // c = tanh(ui[2].x + wh[2].(r*h) + bi[2]); h_t = (1-z)*h + z*c   (GRU_Spatial.py:176-178)
     const float* AXj; const float* hp; const float* Z; float* C; float* Hn; int H;
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
-        float4 ax = ld4(AXj + (size_t)m * 3 * H + 2 * H + n);
+        float4 ax = ldg4(AXj + (size_t)m * 3 * H + 2 * H + n);
         size_t o = (size_t)m * H + n;
-        float4 z = ld4(Z + o), h = ld4(hp + o);
+        float4 z = ldg4(Z + o), h = ldg4(hp + o);
         float4 c = make_float4(tanhf(v[0] + ax.x), tanhf(v[1] + ax.y), tanhf(v[2] + ax.z), tanhf(v[3] + ax.w));
         st4(C + o, c);
         st4(Hn + o, make_float4((1.f - z.x) * h.x + z.x * c.x, (1.f - z.y) * h.y + z.y * c.y,
@@ -147,8 +147,8 @@ struct EpiDHl {  // d cost/d h_j from the loss: Vs^T.do_j + e_j (xp_{j+1} - xq_{
     float* DHl; const float* ev; const float* XDiff; int H;
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
         size_t o = (size_t)m * H + n;
-        float e_ = ev[m];
-        float4 x = ld4(XDiff + o);
+        float e_ = __ldg(ev + m);
+        float4 x = ldg4(XDiff + o);
         st4(DHl + o, make_float4(fmaf(e_, x.x, v[0]), fmaf(e_, x.y, v[1]), fmaf(e_, x.z, v[2]), fmaf(e_, x.w, v[3])));
     }
 };
@@ -157,7 +157,7 @@ struct EpiM {    // m = Wh[2]^T.da_c ; dr = m*h_prev ; da_r = dr*r(1-r) ; dh_kee
     const float* hp; const float* R; float* DAj; float* DHK; int H;
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
         size_t o = (size_t)m * H + n;
-        float4 h = ld4(hp + o), r = ld4(R + o), k = ld4(DHK + o);
+        float4 h = ldg4(hp + o), r = ldg4(R + o), k = ld4(DHK + o);
         st4(DAj + (size_t)m * 3 * H + H + n,
             make_float4(v[0] * h.x * r.x * (1.f - r.x), v[1] * h.y * r.y * (1.f - r.y),
                         v[2] * h.z * r.z * (1.f - r.z), v[3] * h.w * r.w * (1.f - r.w)));
@@ -175,7 +175,7 @@ struct EpiDH {   // dh_{j-1} = dh_keep + [da_z,da_r].Wh[:2] ; then the gate math
     float* DHK; const float* DHlp; const float* Zp; const float* Cp; const float* HPp; float* DAp; int H;
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
         size_t o = (size_t)m * H + n;
-        float4 k = ld4(DHK + o), l = ld4(DHlp + o), z = ld4(Zp + o), c = ld4(Cp + o), h = ld4(HPp + o);
+        float4 k = ld4(DHK + o), l = ldg4(DHlp + o), z = ldg4(Zp + o), c = ldg4(Cp + o), h = ldg4(HPp + o);
         float4 daz, dac, kp;
         bwd_gate_math(v[0] + k.x + l.x, z.x, c.x, h.x, daz.x, dac.x, kp.x);
         bwd_gate_math(v[1] + k.y + l.y, z.y, c.y, h.y, daz.y, dac.y, kp.y);
