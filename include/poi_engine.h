@@ -169,6 +169,11 @@ int poi_gru_predict(poi_engine* e, const poi_gru_params* params, const poi_seq_i
  *      lt_local_dev [n_local_rows x d] with recv_local_ids (= global id / world), duplicate ids from
  *      different ranks summed in arrival order.  out_host as poi_gru_train (global sums). */
 int poi_gru_mg_dense_size(const poi_gru_params* params, int64_t* n_floats);
+/* Optional first phase: slice + sort the batch's row ids once and hand the sorted unique ids to the
+ * caller (uniq_out_dev: room for 2*B*lmax int32).  A poi_gru_train_mg call that follows directly (same
+ * B, same index) reuses the sorted segments instead of sorting again. */
+int poi_gru_mg_prepare(poi_engine* e, const poi_gru_params* params, const poi_seq_index* index,
+                       const int32_t* uidx_host, int32_t B, int32_t* uniq_out_dev, int64_t* n_unique_host);
 int poi_gru_train_mg(poi_engine* e, const poi_gru_params* params, const poi_seq_index* index,
                      const int32_t* uidx_host, int32_t B, int32_t max_len_host, int32_t global_batch,
                      const float* rows_dev, int64_t n_unique, float* dense_grads_dev,

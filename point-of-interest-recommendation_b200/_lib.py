@@ -63,6 +63,7 @@ _PROTOS = {
     "poi_gru_predict": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32,
                                 c_void_p, c_void_p]),
     "poi_gru_mg_dense_size": (c_int, [POINTER(PoiGruParams), POINTER(c_int64)]),
+    "poi_gru_mg_prepare": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_void_p, POINTER(c_int64)]),
     "poi_gru_train_mg": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32, c_int32,
                                  c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "poi_gru_apply_mg": (c_int, [_E, POINTER(PoiGruParams), c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int64,

@@ -153,9 +153,58 @@ int poi_gru_mg_dense_size(const poi_gru_params* p, int64_t* n_floats) {
     return 0;
 }
 
+struct MgPrep { GruIdx ix; SegList seg_lt, seg_di; };
+
+__global__ void k_copy_u32_to_i32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ n, int32_t* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *n) dst[i] = (int32_t)src[i];
+}
+
+int poi_gru_mg_prepare(poi_engine* e, const poi_gru_params* p, const poi_seq_index* index, const int32_t* uidx_host,
+                       int32_t B, int32_t* uniq_out_dev, int64_t* n_unique_host) {
+    e->prep_valid = false;
+    POI_TRY(begin_call(e));
+    const bool head = p->di != nullptr;
+    if (!index || !index->p || !index->q || !index->lens || (head && (!index->dp || !index->dq))) POI_FAIL(e, "index matrices missing");
+    if (B <= 0) POI_FAIL(e, "empty batch");
+    if (!e->prep_state) e->prep_state = new MgPrep();
+    MgPrep* st = static_cast<MgPrep*>(e->prep_state);
+    POI_TRY(stage_reserve(e, (size_t)B * 4 + 256));
+    size_t so = 0;
+    int32_t* uidx_dev = nullptr;
+    POI_TRY(gru_upload_i32(e, uidx_host, (size_t)B, &uidx_dev, &so));
+    POI_TRY(gru_alloc_idx(e, B, index->lmax, head, &st->ix));
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv((int64_t)B * index->lmax, 256), 256, 0, index->p, index->q,
+               head ? index->dp : nullptr, head ? index->dq : nullptr, index->lens, index->lmax, uidx_dev, B,
+               st->ix.PQt, st->ix.DPt, st->ix.DQt, st->ix.lensB);
+    const int64_t LB = (int64_t)index->lmax * B;
+    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(st->ix.PQt), 2 * LB, (uint32_t)p->n_rows_lt, true, &st->seg_lt));
+    if (head) POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(st->ix.DPt), LB, (uint32_t)p->n_rows_di, false, &st->seg_di));
+    POI_LAUNCH(e, k_copy_u32_to_i32, (unsigned)poi_cdiv(2 * LB, 256), 256, 0, st->seg_lt.uniq, st->seg_lt.n_unique, uniq_out_dev);
+    uint32_t nu = 0;
+    POI_CK(e, cudaMemcpyAsync(&nu, st->seg_lt.n_unique, 4, cudaMemcpyDeviceToHost, e->stream));
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    *n_unique_host = nu;
+    e->prep_valid = true; e->prep_B = B; e->prep_lmax = index->lmax;
+    return 0;
+}
+
 int poi_gru_train_mg(poi_engine* e, const poi_gru_params* p, const poi_seq_index* index, const int32_t* uidx_host,
                      int32_t B, int32_t max_len, int32_t global_batch, const float* rows_dev, int64_t n_unique,
                      float* dense_grads, float* row_grads, float* row_cnt, double* loss_sums) {
+    if (e->prep_valid && e->prep_B == B && index && e->prep_lmax == index->lmax) {
+        // continue in the arena epoch of poi_gru_mg_prepare: indices are sliced and sorted already
+        e->prep_valid = false;
+        POI_CK(e, cudaSetDevice(e->device));
+        if (!rows_dev || !dense_grads || !row_grads || !row_cnt || !loss_sums) POI_FAIL(e, "null exchange buffer");
+        MgPrep* st = static_cast<MgPrep*>(e->prep_state);
+        MgCtx mg; mg.rows = rows_dev; mg.global_batch = global_batch; mg.dense_grads = dense_grads;
+        mg.row_grads = row_grads; mg.row_cnt = row_cnt; mg.loss_sums = loss_sums;
+        PreSeg pre{&st->seg_lt, &st->seg_di};
+        phase_mark(e, 0);
+        return gru_train_core(e, p, st->ix, B, index->lmax, max_len, 0, 0.f, 0.f, nullptr, &mg, &pre);
+    }
     POI_TRY(begin_call(e));
     if (!p || !p->ui || !p->wh || !p->bi) POI_FAIL(e, "gru params: null pointer");
     if (p->d <= 0 || p->d % 4 || p->H != p->d) POI_FAIL(e, "n_in must equal n_hidden and be a multiple of 4");

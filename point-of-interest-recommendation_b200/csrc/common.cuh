@@ -41,6 +41,10 @@ struct poi_engine {
     size_t nrec = 0;
     double cat_ms[POI_NCAT] = {}, cat_flops[POI_NCAT] = {}, cat_bytes[POI_NCAT] = {};
     int64_t cat_launches[POI_NCAT] = {};
+    // multi-GPU: index prep + segments of poi_gru_mg_prepare kept alive (same arena epoch) for poi_gru_train_mg
+    bool prep_valid = false;
+    int prep_B = 0, prep_lmax = 0;
+    void* prep_state = nullptr;      // MgPrep*, owned
     // phase timing
     bool timing = false;
     cudaEvent_t ev[9] = {};

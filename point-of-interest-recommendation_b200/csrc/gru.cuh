@@ -381,6 +381,7 @@ struct MgCtx {
     double* loss_sums;       // device double[3]: sur, bpr, gwd
 };
 struct MgLayout { int64_t ui, wh, bi, vs, bs, di, dicnt, total; };
+struct GruIdx;
 static MgLayout mg_layout(int H, int din, int nD, int d) {
     MgLayout L; int64_t o = 0;
     auto take = [&](int64_t n) { int64_t at = o; o += (n + 3) / 4 * 4; return at; };
@@ -449,9 +450,12 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
     return 0;
 }
 
+// segments built by an earlier call in the same arena epoch (multi-GPU: poi_gru_mg_prepare)
+struct PreSeg { const SegList* lt; const SegList* di; };
+
 static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& ix, int B, int lmax,
                           int max_len, int64_t n_nonempty, float alpha, float lambda, double* out_host,
-                          const MgCtx* mg = nullptr) {
+                          const MgCtx* mg = nullptr, const PreSeg* pre = nullptr) {
     const bool head = p->di != nullptr;
     const int d = p->d, H = p->H, din = head ? 2 * d : d;
     const int nD = head ? p->n_rows_di : 0, nDp = (nD + 3) / 4 * 4;
@@ -462,8 +466,11 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
 
     // ---- integer work: sorted-unique segments of the gathered row ids (pad rows included) ----
     SegList seg_lt, seg_di;
-    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.PQt), 2 * LB, (uint32_t)p->n_rows_lt, mg != nullptr, &seg_lt));
-    if (head) POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.DPt), LB, (uint32_t)nD, false, &seg_di));
+    if (pre) { seg_lt = *pre->lt; if (head) seg_di = *pre->di; }
+    else {
+        POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.PQt), 2 * LB, (uint32_t)p->n_rows_lt, mg != nullptr, &seg_lt));
+        if (head) POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.DPt), LB, (uint32_t)nD, false, &seg_di));
+    }
     phase_mark(e, 1);
 
     // ---- forward ----

@@ -87,7 +87,8 @@ static int begin_call(poi_engine* e) {
     POI_CK(e, cudaSetDevice(e->device));
     if (e->nrec > 4096) { POI_CK(e, cudaStreamSynchronize(e->stream)); prof_harvest(e); }
     POI_CAT(e, CAT_OTHER, 0, 0);
-    POI_TRY(arena_reset(e));
+    // between poi_gru_mg_prepare and poi_gru_train_mg the arena holds the prepared segments: append, don't reset
+    if (!e->prep_valid) POI_TRY(arena_reset(e));
     return 0;
 }
 

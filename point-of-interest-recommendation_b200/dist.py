@@ -50,8 +50,8 @@ class RowExchange:
             self.recv_counts = rc
         else:
             self.recv_counts = self.send_counts.clone()
-        self.send_split = self.send_counts.cpu().tolist()
-        self.recv_split = self.recv_counts.cpu().tolist()
+        both = torch.stack((self.send_counts, self.recv_counts)).cpu()                     # one host sync
+        self.send_split, self.recv_split = both[0].tolist(), both[1].tolist()
         self.n_recv = int(sum(self.recv_split))
         self.recv_ids = self._a2a(self.send_ids, self.send_split, self.recv_split)       # global ids I own
         self.recv_local = (self.recv_ids // world).to(torch.int32).contiguous()
@@ -171,9 +171,7 @@ class ShardedSpatialGru:
         if self.world > 1:
             dist.all_reduce(meta, group=self.group)
         global_batch, n_nonempty = int(meta[0].item()), int(meta[1].item())
-        ut = torch.from_numpy(uidx.astype(np.int64)).to(dev)
-        keys = torch.cat((Pt[ut].T.reshape(-1), Qt[ut].T.reshape(-1))).contiguous()
-        uniq, _ = eng.unique(keys, self.n_rows)
+        uniq = eng.gru_mg_prepare(self._params(), index, uidx, Pt.shape[1])     # slice + sort once, reused below
         ex = RowExchange(uniq, self.world, self.group)
         rows = ex.fetch(lambda loc: eng.gather_rows(self.lt_local.t, loc))
         n_u = uniq.numel()

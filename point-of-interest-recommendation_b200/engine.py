@@ -217,6 +217,14 @@ class Engine:
         lib.poi_gru_mg_dense_size(byref(params), byref(n))
         return n.value
 
+    def gru_mg_prepare(self, params, index, uidx, lmax):
+        """Sorted unique row ids of the batch (int32 CUDA tensor); the next gru_train_mg reuses the sort."""
+        uidx = _host_i32(uidx, "uidx").reshape(-1)
+        buf = torch.empty(2 * uidx.size * lmax, dtype=torch.int32, device=self.torch_device)
+        n = c_int64()
+        self._ck(lib.poi_gru_mg_prepare(self._h, byref(params), byref(index), uidx.ctypes.data, uidx.size, buf.data_ptr(), byref(n)))
+        return buf[: n.value]
+
     def gru_train_mg(self, params, index, uidx, max_len, global_batch, rows, dense_grads, row_grads, row_cnt, loss_sums):
         uidx = _host_i32(uidx, "uidx").reshape(-1)
         self._ck(lib.poi_gru_train_mg(self._h, byref(params), byref(index), uidx.ctypes.data, uidx.size, int(max_len),
