@@ -25,10 +25,10 @@ namespace fused {
 using namespace tc;
 
 constexpr int FM = 128;               // users per CTA = UMMA M
-constexpr int F_THREADS = 288;
+constexpr int F_THREADS = 384;      // 8 epilogue warps, 2 AX producer warps, MMA warp, Wh bulk-copy warp
 constexpr int A_KB_BYTES = FM * 128;  // one 32-float k-block of the A tile
 constexpr int AX_TILE = FM * 64;      // 128 rows x 16 floats
-constexpr int AX_STAGES = 3;
+constexpr int AX_STAGES = 2;         // per column half
 constexpr int OUT_STG = 32 * 64;      // per-warp output staging: 32 rows x 16 floats
 
 __device__ __forceinline__ float4 lds4(uint32_t a) {
@@ -105,31 +105,55 @@ __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint3
     for (int k = 0; k < 4; ++k) { umma_tf32(d_tmem, dA + 2 * k, dW + 2 * k, idesc, acc); acc = 1u; }
 }
 
+// Wh staged ONCE per call in the exact shared-memory image the UMMA wants (tile = one gate x one 32-float
+// k-block: H rows x 128 B, 128B-swizzled, hi then lo for 3xTF32), so that inside the recurrence a tile is one
+// bulk async copy (TMA, cp.async.bulk) issued by a single thread instead of 64 threads converting it
+template <bool SPLIT3>
+__global__ void k_stage_wh(const float* __restrict__ wh, int H, uint8_t* __restrict__ image) {
+    const int KB = H >> 5;
+    const int64_t n = (int64_t)3 * KB * H * 8;
+    const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int t12 = (int)(idx / (H * 8)), rem = (int)(idx % (H * 8)), row = rem >> 3, c = rem & 7;
+        const int gate = t12 / KB, kb = t12 % KB;
+        float4 v = *reinterpret_cast<const float4*>(wh + ((size_t)gate * H + row) * H + kb * 32 + c * 4);
+        uint8_t* dst = image + (size_t)t12 * w_stage + row * 128 + ((c ^ (row & 7)) << 4);
+        if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + w_tile) = lo; }
+        else *reinterpret_cast<float4*>(dst) = v;
+    }
+}
+
+// tensor-core modes only: the gate non-linearities with the fast exp / divide (error ~1e-6, far inside the
+// 1e-4 parity bar; the fp32 FMA mode keeps expf/tanhf)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
 template <bool SPLIT3>
 __global__ void __launch_bounds__(F_THREADS, 1)
-k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, float* __restrict__ Hs, float* __restrict__ Z,
+k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, float* __restrict__ Hs, float* __restrict__ Z,
                 float* __restrict__ R, float* __restrict__ C, int B, int T, int H) {
     constexpr int WST = 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[AX_STAGES], ax_empty[AX_STAGES], a_ready, d1_full, d2_full;
+    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[2][AX_STAGES], ax_empty[2][AX_STAGES], a_ready, d1_full, d2_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KB = H >> 5, NCH = H >> 4;
+    const int KB = H >> 5, NCH = H >> 4, HCH = NCH >> 1;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_hi = sbase, a_lo = sbase + KB * A_KB_BYTES;
     const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
-    const uint32_t ax_base = w_base + WST * w_stage;
-    const uint32_t out_base = ax_base + AX_STAGES * AX_TILE;
+    const uint32_t ax_base = w_base + WST * w_stage;           // [half][stage] tiles of AX_TILE bytes
     const int m0 = blockIdx.x * FM;
     uint32_t ncols = 32; while (ncols < (uint32_t)(3 * H)) ncols <<= 1;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 64); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
 #pragma unroll
-        for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&ax_full[s], 64); mbar_init(&ax_empty[s], 128); }
-        mbar_init(&a_ready, 128); mbar_init(&d1_full, 1); mbar_init(&d2_full, 1);
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&ax_full[h][s], 32); mbar_init(&ax_empty[h][s], 128); }
+        mbar_init(&a_ready, 256); mbar_init(&d1_full, 1); mbar_init(&d2_full, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
@@ -139,50 +163,56 @@ k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, floa
     const uint32_t tmem = tmem_base_s;
     const uint32_t idesc = make_idesc_tf32(FM, H);
 
-    if (warp < 4) {
-        // ================================ epilogue ================================
-        const int row = tid;                                   // TMEM lane == row of the tile
+    if (warp < 8) {
+        // ================================ epilogue (8 warps) ================================
+        // warp w: TMEM lane quadrant q = w & 3 (rows 32q..32q+31), column half hf = w >> 2
+        const int q = warp & 3, hf = warp >> 2;
+        const int row = q * 32 + lane;                         // TMEM lane == row of the tile
         const bool ok = m0 + row < B;
-        const uint32_t tl = (uint32_t)(warp * 32) << 16;
-        const uint32_t stg = out_base + warp * OUT_STG;
-        const int rows_valid = min(32, B - (m0 + warp * 32));  // rows of this warp's quadrant that exist (may be <= 0)
-        {   // h_{-1} = 0 -> A tile
+        const uint32_t tl = (uint32_t)(q * 32) << 16;
+        const int rows_valid = min(32, B - (m0 + q * 32));
+        const int k_beg = hf * HCH, k_end = k_beg + HCH;
+        if (hf == 0 || true) {   // h_{-1} = 0 -> this warp's half of the A tile
             float zero[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) zero[i] = 0.f;
-            for (int c0 = 0; c0 < H; c0 += 16) a_store16<SPLIT3>(a_hi, a_lo, row, c0, zero);
+            for (int k = k_beg; k < k_end; ++k) a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, zero);
             fence_async_smem();
             mbar_arrive(&a_ready);
         }
-        int64_t axi = 0;                                       // AX ring position (tiles consumed so far)
-        auto ax_take = [&](float (&v)[16]) {
+        int64_t axi = 0;                                       // position in this half's AX ring
+        // wait for the next AX tile, read this thread's row, return this warp's 2 KB slice of the tile (free to
+        // be reused as output staging once the whole warp has read) and the barrier to release it on
+        auto ax_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
             const int s = (int)(axi % AX_STAGES);
-            mbar_wait(&ax_full[s], (uint32_t)(axi / AX_STAGES) & 1);
-            const uint32_t t = ax_base + s * AX_TILE;
+            mbar_wait(&ax_full[hf][s], (uint32_t)(axi / AX_STAGES) & 1);
+            slice = ax_base + (hf * AX_STAGES + s) * AX_TILE + q * OUT_STG;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 x = lds4(t + sw64(row, q));
-                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            for (int c = 0; c < 4; ++c) {
+                float4 x = lds4(slice + sw64(lane, c));
+                v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
             }
-            mbar_arrive(&ax_empty[s]);
+            __syncwarp();
+            rel = &ax_empty[hf][s];
             ++axi;
         };
         for (int j = 0; j < T; ++j) {
-            const size_t wrow = (size_t)j * B + m0 + warp * 32;            // first global row of this warp at step j
+            const size_t wrow = (size_t)j * B + m0 + q * 32;   // first global row of this warp's quadrant at step j
             // ---- epilogue 1: z, r, r*h ; stash z and (1-z)*h ----
             mbar_wait(&d1_full, j & 1);
             tc_fence_after();
-            for (int k = 0; k < NCH; ++k) {
+            for (int k = k_beg; k < k_end; ++k) {
                 const int c0 = 16 * k;
                 float a[16], b[16], hv[16], dz[16], dr[16];
-                ax_take(a); ax_take(b);
+                uint32_t sl_z, sl_r; uint64_t *rel_z, *rel_r;
+                ax_take(a, sl_z, rel_z); ax_take(b, sl_r, rel_r);
                 tmem_ld16(tmem + tl + (uint32_t)c0, dz);
                 tmem_ld16(tmem + tl + (uint32_t)(H + c0), dr);
                 a_load16<SPLIT3>(a_hi, a_lo, row, c0, hv);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float zz = sigmoidf_(dz[i] + a[i]);
-                    const float rr = sigmoidf_(dr[i] + b[i]);
+                    const float zz = sigmoid_fast(dz[i] + a[i]);
+                    const float rr = sigmoid_fast(dr[i] + b[i]);
                     const float h_ = ok ? hv[i] : 0.f;
                     dz[i] = zz; dr[i] = rr;
                     a[i] = rr * h_;                 // r*h -> next A operand
@@ -191,127 +221,102 @@ k_gru_fwd_fused(const float* __restrict__ AX, const float* __restrict__ wh, floa
                 tmem_st16(tmem + tl + (uint32_t)c0, dz);              // stash z
                 tmem_st16(tmem + tl + (uint32_t)(H + c0), b);         // stash (1-z)*h_prev
                 a_store16<SPLIT3>(a_hi, a_lo, row, c0, a);
-                warp_store_chunk(stg, lane, dz, Z + wrow * H + c0, H, rows_valid);
-                warp_store_chunk(stg, lane, dr, R + wrow * H + c0, H, rows_valid);
+                warp_store_chunk(sl_z, lane, dz, Z + wrow * H + c0, H, rows_valid);
+                warp_store_chunk(sl_r, lane, dr, R + wrow * H + c0, H, rows_valid);
+                mbar_arrive(rel_z); mbar_arrive(rel_r);
             }
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(&a_ready);                 // r*h tile ready
+            mbar_arrive(&a_ready);                 // this warp's part of the r*h tile is in place
             // ---- epilogue 2: c, h_t ----
             mbar_wait(&d2_full, j & 1);
             tc_fence_after();
-            for (int k = 0; k < NCH; ++k) {
+            for (int k = k_beg; k < k_end; ++k) {
                 const int c0 = 16 * k;
                 float a[16], dc[16], zz[16], u[16];
-                ax_take(a);
+                uint32_t sl; uint64_t* rel;
+                ax_take(a, sl, rel);
                 tmem_ld16(tmem + tl + (uint32_t)(2 * H + c0), dc);
                 tmem_ld16(tmem + tl + (uint32_t)c0, zz);
                 tmem_ld16(tmem + tl + (uint32_t)(H + c0), u);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float cc = tanhf(dc[i] + a[i]);
+                    const float cc = tanh_fast(dc[i] + a[i]);
                     dc[i] = cc;
                     u[i] = ok ? u[i] + zz[i] * cc : 0.f;   // h_t = (1-z) h_prev + z c
                 }
                 a_store16<SPLIT3>(a_hi, a_lo, row, c0, u);
-                warp_store_chunk(stg, lane, dc, C + wrow * H + c0, H, rows_valid);
-                warp_store_chunk(stg, lane, u, Hs + (wrow + B) * H + c0, H, rows_valid);
+                warp_store_chunk(sl, lane, dc, C + wrow * H + c0, H, rows_valid);
+                warp_store_chunk(sl, lane, u, Hs + (wrow + B) * H + c0, H, rows_valid);
+                mbar_arrive(rel);
             }
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(&a_ready);                 // h_t tile ready
+            mbar_arrive(&a_ready);                 // this warp's part of the h_t tile is in place
         }
-    } else if (warp < 6) {
-        // ================================ Wh producers (64 threads) ================================
-        const int ptid = tid - 128;
-        const int LW = H >> 3;                     // 16-byte chunks per thread per tile (H*8/64)
-        const int64_t n_tiles = (int64_t)T * 3 * KB;
-        float4 r0[16], r1[16];
-        auto gload = [&](int64_t ws, float4 (&rg)[16]) {
-            const int t12 = (int)(ws % (3 * KB)), gate = t12 / KB, kb = t12 % KB;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (i < LW) {
-                    int f = ptid + i * 64, rw = f >> 3, c = f & 7;
-                    rg[i] = __ldg(reinterpret_cast<const float4*>(wh + ((size_t)gate * H + rw) * H + kb * 32 + c * 4));
-                }
-            }
-        };
-        auto stage_in = [&](int64_t ws, const float4 (&rg)[16]) {
-            const int s = (int)(ws % WST);
-            if (ws >= WST) mbar_wait(&w_empty[s], (uint32_t)((ws / WST) - 1) & 1);
-            const uint32_t sW = w_base + s * w_stage, sWl = sW + w_tile;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (i < LW) {
-                    int f = ptid + i * 64, rw = f >> 3, c = f & 7;
-                    uint32_t off = rw * 128 + ((c ^ (rw & 7)) << 4);
-                    if (SPLIT3) { float4 hi, lo; split4(rg[i], hi, lo); sts4(sW + off, hi); sts4(sWl + off, lo); }
-                    else sts4(sW + off, rg[i]);
-                }
-            }
-            fence_async_smem();
-            mbar_arrive(&w_full[s]);
-        };
-        if (n_tiles > 0) gload(0, r0);
-        for (int64_t ws = 0; ws < n_tiles; ws += 2) {
-            if (ws + 1 < n_tiles) gload(ws + 1, r1);
-            stage_in(ws, r0);
-            if (ws + 1 < n_tiles) {
-                if (ws + 2 < n_tiles) gload(ws + 2, r0);
-                stage_in(ws + 1, r1);
-            }
-        }
-    } else if (warp < 8) {
-        // ================================ AX producers (64 threads, cp.async) ================================
-        const int ptid = tid - 192;
-        const int per_step = 3 * NCH;
+    } else if (warp < 10) {
+        // ================================ AX producers (one warp per column half, cp.async) ================================
+        const int hf = warp - 8;
+        const int per_step = 3 * HCH;
         const int64_t n_tiles = (int64_t)T * per_step;
         for (int64_t ai = 0; ai < n_tiles; ++ai) {
             const int s = (int)(ai % AX_STAGES);
-            if (ai >= AX_STAGES) mbar_wait(&ax_empty[s], (uint32_t)((ai / AX_STAGES) - 1) & 1);
+            if (ai >= AX_STAGES) mbar_wait(&ax_empty[hf][s], (uint32_t)((ai / AX_STAGES) - 1) & 1);
             const int j = (int)(ai / per_step), ti = (int)(ai % per_step);
-            const int gate = ti < 2 * NCH ? (ti & 1) : 2;
-            const int k = ti < 2 * NCH ? (ti >> 1) : ti - 2 * NCH;
+            const int gate = ti < 2 * HCH ? (ti & 1) : 2;
+            const int k = hf * HCH + (ti < 2 * HCH ? (ti >> 1) : ti - 2 * HCH);
             const float* src = AX + ((size_t)j * B + m0) * 3 * H + gate * H + 16 * k;
-            const uint32_t dst = ax_base + s * AX_TILE;
+            const uint32_t dst = ax_base + (hf * AX_STAGES + s) * AX_TILE;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int f = ptid + i * 64, rw = f >> 2, c = f & 3;
+            for (int i = 0; i < 16; ++i) {
+                int f = lane + i * 32, rw = f >> 2, c = f & 3;
                 if (m0 + rw < B)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + sw64(rw, c)), "l"(src + (size_t)rw * 3 * H + 4 * c) : "memory");
             }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ax_full[s])) : "memory");
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ax_full[hf][s])) : "memory");
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (lane == 0) {
-        // ================================ MMA issuer ================================
-        int64_t ws = 0; uint32_t pa = 0;
-        for (int j = 0; j < T; ++j) {
-            mbar_wait(&a_ready, pa & 1); ++pa;     // h_{j-1} tile staged (and the stashes of step j-1 consumed)
-            tc_fence_after();
-            for (int half = 0; half < 2; ++half) {
+    } else if (warp == 10) {
+        if (lane == 0) {
+            // ================================ MMA issuer ================================
+            int64_t ws = 0; uint32_t pa = 0;
+            for (int j = 0; j < T; ++j) {
+                mbar_wait(&a_ready, pa & 1); ++pa;     // h_{j-1} tile staged (and the stashes of step j-1 consumed)
+                tc_fence_after();
+                for (int half = 0; half < 2; ++half) {
+                    for (int kb = 0; kb < KB; ++kb, ++ws) {
+                        const int s = (int)(ws % WST);
+                        mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                        tc_fence_after();
+                        const uint32_t sW = w_base + s * w_stage;
+                        mma_kblock<SPLIT3>(tmem + half * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
+                        umma_commit(&w_empty[s]);
+                    }
+                }
+                umma_commit(&d1_full);
+                mbar_wait(&a_ready, pa & 1); ++pa;     // r*h tile staged
+                tc_fence_after();
                 for (int kb = 0; kb < KB; ++kb, ++ws) {
                     const int s = (int)(ws % WST);
                     mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
                     tc_fence_after();
                     const uint32_t sW = w_base + s * w_stage;
-                    mma_kblock<SPLIT3>(tmem + half * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
+                    mma_kblock<SPLIT3>(tmem + 2 * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
                     umma_commit(&w_empty[s]);
                 }
+                umma_commit(&d2_full);
             }
-            umma_commit(&d1_full);
-            mbar_wait(&a_ready, pa & 1); ++pa;     // r*h tile staged
-            tc_fence_after();
-            for (int kb = 0; kb < KB; ++kb, ++ws) {
-                const int s = (int)(ws % WST);
-                mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
-                tc_fence_after();
-                const uint32_t sW = w_base + s * w_stage;
-                mma_kblock<SPLIT3>(tmem + 2 * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
-                umma_commit(&w_empty[s]);
-            }
-            umma_commit(&d2_full);
+        }
+    } else if (lane == 0) {
+        // ================================ Wh tiles: one bulk async copy (TMA) per tile ================================
+        const int64_t n_tiles = (int64_t)T * 3 * KB;
+        for (int64_t ws = 0; ws < n_tiles; ++ws) {
+            const int s = (int)(ws % WST);
+            if (ws >= WST) mbar_wait(&w_empty[s], (uint32_t)((ws / WST) - 1) & 1);
+            const uint32_t bar = smem_u32(&w_full[s]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_stage) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(w_base + s * w_stage), "l"(wimg + (size_t)(ws % (3 * KB)) * w_stage), "r"(w_stage), "r"(bar) : "memory");
         }
     }
     tc_fence_before();
@@ -334,11 +339,15 @@ template <bool SPLIT3>
 static int launch_fwd_inst(poi_engine* e, const float* AX, const float* wh, float* Hs, float* Z, float* R, float* C,
                            int B, int T, int H) {
     const int KB = H / 32;
-    size_t smem = (size_t)KB * A_KB_BYTES * (SPLIT3 ? 2 : 1) + (size_t)2 * H * 128 * (SPLIT3 ? 2 : 1) +
-                  (size_t)AX_STAGES * AX_TILE + 4 * OUT_STG + 1024;
+    const size_t w_stage = (size_t)H * 128 * (SPLIT3 ? 2 : 1);
+    uint8_t* wimg = nullptr;
+    POI_TRY(arena_get(e, (size_t)3 * KB * w_stage, &wimg));
+    POI_CAT(e, CAT_ELTWISE, 0, 0);
+    POI_LAUNCH(e, (k_stage_wh<SPLIT3>), 48, 256, 0, wh, H, wimg);
+    size_t smem = (size_t)KB * A_KB_BYTES * (SPLIT3 ? 2 : 1) + 2 * w_stage + (size_t)2 * AX_STAGES * AX_TILE + 1024;
     POI_CK(e, cudaFuncSetAttribute(k_gru_fwd_fused<SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
-    POI_LAUNCH(e, (k_gru_fwd_fused<SPLIT3>), (unsigned)poi_cdiv(B, FM), F_THREADS, smem, AX, wh, Hs, Z, R, C, B, T, H);
+    POI_LAUNCH(e, (k_gru_fwd_fused<SPLIT3>), (unsigned)poi_cdiv(B, FM), F_THREADS, smem, AX, wimg, Hs, Z, R, C, B, T, H);
     return 0;
 }
 
