@@ -25,7 +25,7 @@ struct poi_engine {
     std::string err;
     int64_t launches = 0;
     int gemm_mode = 0;
-    bool fuse_recurrence = false;    // tensor-core modes: persistent fused recurrence kernel (gru_fused.cuh); off until its epilogue I/O goes through TMA
+    bool fuse_recurrence = true;     // tensor-core modes: forward recurrence as one persistent fused kernel (gru_fused.cuh)
     // bump arena (device scratch owned by the engine); reset at the start of every call
     std::vector<PoiChunk> chunks;
     size_t cur_chunk = 0, cur_off = 0, high_water = 0, call_bytes = 0;

@@ -168,7 +168,7 @@ def test_spatial_minibatch_tensor_core_modes(engine, mode, rtol):
     tes_d = [[n_dist]] * n_user
     model = SpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
     ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
-    engine.set_gemm_mode(mode)
+    engine.set_gemm_mode(mode); engine.set_fused_recurrence(False)       # the per-step GEMM path
     try:
         for start in range(0, n_user, 96):
             se = np.arange(start, start + 96, dtype=np.int32)
@@ -176,7 +176,7 @@ def test_spatial_minibatch_tensor_core_modes(engine, mode, rtol):
             (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
             assert_close([los, sur, upq], [rl, rs_, ru], rtol, "losses batch %d" % start)
     finally:
-        engine.set_gemm_mode(0)
+        engine.set_gemm_mode(0); engine.set_fused_recurrence(True)
     got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
     for k in got:
         assert_close(got[k], ref[k], rtol, k)
@@ -202,7 +202,7 @@ def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d):
             (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
             assert_close([los, sur, upq], [rl, rs_, ru], rtol, "losses")
     finally:
-        engine.set_gemm_mode(0); engine.set_fused_recurrence(False)
+        engine.set_gemm_mode(0); engine.set_fused_recurrence(True)
     got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
     for k in got:
         assert_close(got[k], ref[k], rtol, k)
