@@ -24,7 +24,7 @@ struct poi_engine {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
-    int gemm_mode = 0;
+    int gemm_mode = 1;               // default: tcgen05 3xTF32 (fp32-faithful); 0 = fp32 FMA, 2 = 1xTF32
     bool fuse_recurrence = true;     // tensor-core modes: forward recurrence as one persistent fused kernel (gru_fused.cuh)
     // bump arena (device scratch owned by the engine); reset at the start of every call
     std::vector<PoiChunk> chunks;

@@ -168,6 +168,7 @@ def test_spatial_minibatch_tensor_core_modes(engine, mode, rtol):
     tes_d = [[n_dist]] * n_user
     model = SpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
     ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    prev = engine.get_gemm_mode()
     engine.set_gemm_mode(mode); engine.set_fused_recurrence(False)       # the per-step GEMM path
     try:
         for start in range(0, n_user, 96):
@@ -176,7 +177,7 @@ def test_spatial_minibatch_tensor_core_modes(engine, mode, rtol):
             (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
             assert_close([los, sur, upq], [rl, rs_, ru], rtol, "losses batch %d" % start)
     finally:
-        engine.set_gemm_mode(0); engine.set_fused_recurrence(True)
+        engine.set_gemm_mode(prev); engine.set_fused_recurrence(True)
     got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
     for k in got:
         assert_close(got[k], ref[k], rtol, k)
@@ -194,6 +195,7 @@ def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d):
     tes_d = [[n_dist]] * n_user
     model = SpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
     ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    prev = engine.get_gemm_mode()
     engine.set_gemm_mode(mode); engine.set_fused_recurrence(True)
     try:
         for _ in range(2):
@@ -202,7 +204,31 @@ def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d):
             (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
             assert_close([los, sur, upq], [rl, rs_, ru], rtol, "losses")
     finally:
-        engine.set_gemm_mode(0); engine.set_fused_recurrence(True)
+        engine.set_gemm_mode(prev); engine.set_fused_recurrence(True)
     got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
     for k in got:
         assert_close(got[k], ref[k], rtol, k)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_obo_spatial_both_gemm_modes(engine, mode):
+    """One-by-one Distance2Pre (the reference's semantics) under the fp32 FMA path and the default
+    tcgen05 3xTF32 path: both must hold the 1e-4 bar over a trajectory."""
+    from poi_b200.public.GRU_Spatial import OboSpatialGru
+    rs = np.random.RandomState(900)
+    n_user, n_item, d, lmax, n_dist = 6, 500, 64, 40, 200
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    model = OboSpatialGru([P, M, Q], test, [DP, [[n_dist]] * n_user, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    prev = engine.get_gemm_mode()
+    engine.set_gemm_mode(mode)
+    try:
+        for u in [0, 1, 2, 3, 4, 5, 0, 1]:
+            los, sur, upq, ls = model.train(u)
+            (rl, rs_, ru, rw), ref = OM.obo_spatial_gru_train(ref, P[u], Q[u], DP[u], DQ[u], M[u], ALPHA, LAM)
+            assert_close([los, sur, upq], [rl, rs_, ru], RTOL, "losses user %d" % u)
+    finally:
+        engine.set_gemm_mode(prev)
+    got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
+    for k in got:
+        assert_close(got[k], ref[k], RTOL, k)
