@@ -326,6 +326,18 @@ def run_ours(args):
         roof["traffic_note"] = "ncu capture of the largest launch of this kernel (%s)" % traffic[roof["kernel"]]["kernel"]
     breakdown = {k: round(v["ms"] / nprof, 4) for k, v in prof.items() if v["ms"] > 0}
 
+    # one-by-one mode (B = 1): the reference's own update semantics, one `model.train(uidx)` call per user
+    obo = None
+    if world == 1 and not args.no_obo:
+        n_obo = 64
+        t0 = time.perf_counter()
+        for u in range(n_obo):
+            model.train(np.array([u], dtype=np.int32))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        obo = {"value": checkins_of(lens_loc[:n_obo]) / dt, "unit": UNIT, "ms_per_user_call": dt / n_obo * 1e3,
+               "note": "B=1 calls through the Python class (wall clock incl. host overhead), reference semantics"}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cb = min(args.cpu_batch, U)
@@ -350,7 +362,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e_max / K},
         "gpu_launches": launches_all,
         "roofline": roof, "hbm_kernels": hbm_kernels, "kernel_ms_per_step": breakdown,
-        "cpu_baseline": cpu, "clocks": clocks, "final_loss": float(losses[-1]),
+        "cpu_baseline": cpu, "obo_mode": obo, "clocks": clocks, "final_loss": float(losses[-1]),
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -370,6 +382,7 @@ def main():
                     help="0 fp32 FMA, 1 tcgen05 3xTF32 (fp32-faithful, default), 2 tcgen05 1xTF32")
     ap.add_argument("--fused", type=int, default=1, help="1 = persistent fused recurrence kernel (tensor-core modes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-obo", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,103 @@
+"""Larger shapes (BASELINE.json configs C3-C5 scale in the dimensions that matter to the kernels:
+wide rows d = 256 / 512, big tables, long sequences), each against the oracle on a small number of
+users, plus size-independent properties at a size the oracle cannot reach (determinism, batch
+additivity of the dense gradient step)."""
+import numpy as np
+import pytest
+
+from oracle import explicit as E
+from oracle import fixtures as Fx
+from oracle import models as OM
+from tests.util import assert_close, state_from_model
+
+pytestmark = pytest.mark.gpu
+A, L = 0.01, 0.001
+
+
+def test_distance2pre_d512_long_sequences(engine):
+    """C5-like row width (d = H = 512 -> per-step tensor-core GEMMs, N up to 1536) and lmax = 96."""
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(5)
+    n_user, n_item, d, lmax, n_dist = 48, 20000, 512, 96, 200
+    P, Q, M = Fx.ragged_sequences(rs, n_user, n_item, lmax, min_len=40)
+    DP, DQ = Fx.interval_matrices(rs, P, Q, M, n_dist)
+    st = Fx.gru_state(rs, n_item, d, d, n_dist)
+    for k in ("ui", "wh", "vs"):          # keep the recurrence in a sane regime at this width
+        st[k] = (st[k] * (4.0 / np.sqrt(d))).astype(np.float32)
+    tes = [[n_item]] * n_user
+    m = SpatialGru([P, M, Q], [tes, [[0]] * n_user, tes], [DP, [[n_dist]] * n_user, DQ], [A, L], n_user, n_item,
+                   [n_dist, 0.2], d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    se = np.arange(n_user, dtype=np.int32)
+    out = m.train(se)
+    (rl, rsur, rupq, rw), ref = E.gru_family_train_batch(ref, P, Q, M, A, L, DP, DQ)
+    assert_close(out[:3], [rl, rsur, rupq], 1e-4, "losses")
+    got = state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
+    for k in got:
+        assert_close(got[k], ref[k], 1e-4, k)
+
+
+def test_prme_c3_shape(engine):
+    """PRME at |POI| = 100k, d = 256 (C3): a short ordered call list against the oracle."""
+    from poi_b200.public.PRME import OboPrme
+    rs = np.random.RandomState(6)
+    n_user, n_item, d = 50, 100000, 256
+    st = Fx.prme_state(rs, n_user, n_item, d)
+    tes = [[n_item]] * n_user
+    m = OboPrme([tes, [[0]] * n_user, [[0.0]] * n_user, [[1]] * n_user, tes], [tes, [[0]] * n_user, [[0.0]] * n_user, [[1]] * n_user, tes],
+                [A, L], 360, 0.2, np.zeros((n_item + 1, 2)), n_user, n_item, d, init=st)
+    n = 40
+    u = rs.randint(0, n_user, n); p = rs.randint(0, n_item, n); q = rs.randint(0, n_item, n); pr = rs.randint(0, n_item, n)
+    p[5] = pr[5]                       # repeat visit
+    dist = rs.uniform(0, 30, n); gap = rs.randint(1, 720, n)
+    got = m.train_sequence(u, p, q, pr, dist, gap)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    rl = []
+    for i in range(n):
+        l, ref = OM.obo_prme_train(ref, int(u[i]), [int(p[i]), int(q[i]), int(pr[i])], float(dist[i]), int(gap[i]), A, L, 360, 0.2)
+        rl.append(l)
+    assert_close(got, rl, 1e-4, "losses")
+    touched = np.unique(np.concatenate((p, q, pr)))
+    assert_close(m.dp.get_value()[touched], ref["dp"][touched], 1e-4, "dp rows")
+    assert_close(m.ds.get_value()[touched], ref["ds"][touched], 1e-4, "ds rows")
+
+
+def test_geoie_c4_shape(engine):
+    """GeoIE at |POI| = 1M, d = 256 (C4 row width and table size), one user."""
+    from poi_b200.public.GeoIE import GeoIE
+    rs = np.random.RandomState(7)
+    n_user, n_item, H, lmax = 2, 1000000, 256, 33
+    P, Q, M = Fx.ragged_sequences(rs, n_user, n_item, lmax, min_len=33)
+    st = Fx.geoie_state(rs, n_user, n_item, H)
+    tes = [[n_item]] * n_user
+    m = GeoIE([P, Q, np.ones_like(P), M], [tes, tes], [A, L], n_user, n_item, H, H, None, init=st)
+    dpos, dneg, msk = Fx.geoie_inputs(rs, lmax)
+    loss = m.train(0, dpos, dneg, msk)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    rl, ref = OM.geoie_train(ref, 0, P[0], Q[0], dpos, dneg, msk, A, L)
+    assert_close(loss, rl, 1e-4, "loss")
+    rows = np.unique(np.concatenate((P[0], Q[0])))
+    for k in ("g", "h", "z"):
+        assert_close(getattr(m, k).get_value()[rows], ref[k][rows], 1e-4, k)
+
+
+def test_c2_full_batch_properties(engine):
+    """BASELINE C2 at full size (10k users x 32, |POI| = 40k, d = 128): same bits on a re-run; rows outside
+    unique(p u q) are untouched; the pad row is untouched (no padding in this workload)."""
+    import poi_b200  # noqa: F401
+    from poi_b200 import synth
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    ds = synth.make_dataset(10000, 40000, 32)
+    st = synth.init_state(40000, 128, 128, ds["dist_num"])
+    tes = ds["tes"]; D = ds["dist_num"]
+    outs, tabs = [], []
+    for _ in range(2):
+        m = SpatialGru([ds["P"], ds["M"], ds["Q"]], [tes, np.ones_like(tes), tes], [ds["DP"], np.full_like(tes, D), ds["DQ"]],
+                       [A, L], 10000, 40000, [D, 0.2], 128, 128, init=st)
+        outs.append(m.train(np.arange(10000, dtype=np.int32))[:3])
+        tabs.append(m.lt.get_value())
+    assert outs[0] == outs[1] and np.array_equal(tabs[0], tabs[1])
+    touched = np.zeros(40001, dtype=bool); touched[ds["P"].ravel()] = True; touched[ds["Q"].ravel()] = True
+    assert np.array_equal(tabs[0][~touched], st["lt"][~touched])
+    assert not touched[40000]
+    assert np.all(np.isfinite(tabs[0]))
