@@ -518,20 +518,25 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
             POI_CAT(e, CAT_ELTWISE, 0, 0);
             POI_LAUNCH(e, k_dhl_nohead, (unsigned)poi_cdiv(TB * (H / 4), 256), 256, 0, ev, XDiff, DHl, TB, H / 4);
         }
-        {
-            size_t o = (size_t)(T - 1) * B * H;
-            POI_CAT(e, CAT_ELTWISE, 0, 0);
-            POI_LAUNCH(e, k_bwd_prep, (unsigned)poi_cdiv((int64_t)B * H / 4, 256), 256, 0, DHl + o, Z + o, C + o,
-                       Hs + o, DA + (size_t)(T - 1) * B * 3 * H, DHK, B, H);
-        }
-        for (int j = T - 1; j >= 0; --j) {
-            size_t o = (size_t)j * B * H;
-            float* DAj = DA + (size_t)j * B * 3 * H;
-            POI_TRY(gemm_tn(e, DAj + 2 * H, 3 * H, W2cT, H, B, H, H, EpiM{Hs + o, R + o, DAj, DHK, H}));
-            if (j > 0) {
-                size_t op = (size_t)(j - 1) * B * H;
-                POI_TRY(gemm_tn(e, DAj, 3 * H, W2zrT, 2 * H, B, H, 2 * H,
-                                EpiDH{DHK, DHl + op, Z + op, C + op, Hs + op, DA + (size_t)(j - 1) * B * 3 * H, H}));
+        if (e->gemm_mode != 0 && e->fuse_recurrence && fused::fwd_supported(H) && H <= 128) {
+            // BPTT through the cell as one persistent tcgen05 kernel (gru_fused.cuh); dh never leaves the SM
+            POI_TRY(fused::launch_gru_bwd_fused(e, DHl, Z, R, C, Hs, p->wh, DA, B, T, H, e->gemm_mode == 1));
+        } else {
+            {
+                size_t o = (size_t)(T - 1) * B * H;
+                POI_CAT(e, CAT_ELTWISE, 0, 0);
+                POI_LAUNCH(e, k_bwd_prep, (unsigned)poi_cdiv((int64_t)B * H / 4, 256), 256, 0, DHl + o, Z + o, C + o,
+                           Hs + o, DA + (size_t)(T - 1) * B * 3 * H, DHK, B, H);
+            }
+            for (int j = T - 1; j >= 0; --j) {
+                size_t o = (size_t)j * B * H;
+                float* DAj = DA + (size_t)j * B * 3 * H;
+                POI_TRY(gemm_tn(e, DAj + 2 * H, 3 * H, W2cT, H, B, H, H, EpiM{Hs + o, R + o, DAj, DHK, H}));
+                if (j > 0) {
+                    size_t op = (size_t)(j - 1) * B * H;
+                    POI_TRY(gemm_tn(e, DAj, 3 * H, W2zrT, 2 * H, B, H, 2 * H,
+                                    EpiDH{DHK, DHl + op, Z + op, C + op, Hs + op, DA + (size_t)(j - 1) * B * 3 * H, H}));
+                }
             }
         }
         POI_TRY(gemm_tn(e, DA, 3 * H, U2T, 3 * H, TB, din, 3 * H, EpiBiasStore{DX, din, nullptr, din}));

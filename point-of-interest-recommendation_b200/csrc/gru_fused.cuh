@@ -324,6 +324,276 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward recurrence (BPTT through the cell) as one persistent kernel, same roles.
+// Per step j = T-1 .. 0, for the 128 users of the CTA (dh carried in TMEM, never in global memory):
+//   P : dht = dh + DHl_j ; da_c = dht z (1-c^2) ; da_z = dht (c-h') z(1-z) ; keep = dht (1-z)
+//       A <- da_c                                         GEMM_M  : m   = da_c . Wh[2]
+//   M1: A <- da_z                                         GEMM_DH1: dhn = da_z . Wh[0]
+//   M2: da_r = m h' r(1-r) ; keep += m r      (overlaps GEMM_DH1)
+//   M3: A <- da_r                                         GEMM_DH2: dhn += da_r . Wh[1]
+//   D : dh = keep + dhn  -> P of step j-1
+// TMEM columns: [0,H) D_m (then the da_r stash), [H,2H) D_dh, [2H,3H) keep, [3H,4H) da_z.
+// Inputs (DHl, Z, C, H_prev, R) stream through cp.async rings in 16-column tiles, DA_z/DA_r/DA_c are
+// stored through the consumed ring slices (coalesced), the transposed Wh tiles are bulk-copied (TMA) from
+// an image staged once per call.
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT3>
+__global__ void k_stage_wh_bwd(const float* __restrict__ wh, int H, uint8_t* __restrict__ image) {
+    const int KB = H >> 5;
+    const int64_t n = (int64_t)3 * KB * H * 8;
+    const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int t12 = (int)(idx / (H * 8)), rem = (int)(idx % (H * 8)), row = rem >> 3, c = rem & 7;
+        const int g = t12 / KB, kb = t12 % KB;
+        const int gsel = g == 0 ? 2 : g - 1;             // tile order: Wh[2] (c), Wh[0] (z), Wh[1] (r)
+        // B operand row n, k-major: element (n, k) = Wh[gsel][k][n]
+        const float* src = wh + ((size_t)gsel * H + kb * 32 + c * 4) * H + row;
+        float4 v = make_float4(src[0], src[H], src[2 * (size_t)H], src[3 * (size_t)H]);
+        uint8_t* dst = image + (size_t)t12 * w_stage + row * 128 + ((c ^ (row & 7)) << 4);
+        if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + w_tile) = lo; }
+        else *reinterpret_cast<float4*>(dst) = v;
+    }
+}
+
+template <bool SPLIT3>
+__global__ void __launch_bounds__(F_THREADS, 1)
+k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, const float* __restrict__ R,
+                const float* __restrict__ C, const float* __restrict__ Hs, const uint8_t* __restrict__ wimg,
+                float* __restrict__ DA, int B, int T, int H) {
+    constexpr int WST = 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t w_full[WST], w_empty[WST], in_full[2][AX_STAGES], in_empty[2][AX_STAGES], a_ready, dm_full, dh1_done, ddh_full;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KB = H >> 5, NCH = H >> 4, HCH = NCH >> 1;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_hi = sbase, a_lo = sbase + KB * A_KB_BYTES;
+    const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
+    const uint32_t in_base = w_base + WST * w_stage;
+    const int m0 = blockIdx.x * FM;
+    uint32_t ncols = 32; while (ncols < (uint32_t)(4 * H)) ncols <<= 1;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&in_full[h][s], 32); mbar_init(&in_empty[h][s], 128); }
+        mbar_init(&a_ready, 256); mbar_init(&dm_full, 1); mbar_init(&dh1_done, 1); mbar_init(&ddh_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = make_idesc_tf32(FM, H);
+    const uint32_t T_M = 0, T_DH = (uint32_t)H, T_KEEP = (uint32_t)(2 * H), T_DAZ = (uint32_t)(3 * H);
+
+    if (warp < 8) {
+        // ================================ epilogue (8 warps) ================================
+        const int q = warp & 3, hf = warp >> 2;
+        const int row = q * 32 + lane;
+        const bool ok = m0 + row < B;
+        const uint32_t tl = (uint32_t)(q * 32) << 16;
+        const int rows_valid = min(32, B - (m0 + q * 32));
+        const int k_beg = hf * HCH, k_end = k_beg + HCH;
+        int64_t ini = 0;
+        auto in_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
+            const int s = (int)(ini % AX_STAGES);
+            mbar_wait(&in_full[hf][s], (uint32_t)(ini / AX_STAGES) & 1);
+            slice = in_base + (hf * AX_STAGES + s) * AX_TILE + q * OUT_STG;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 x = lds4(slice + sw64(lane, c));
+                v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+            }
+            __syncwarp();
+            rel = &in_empty[hf][s];
+            ++ini;
+        };
+        for (int j = T - 1; j >= 0; --j) {
+            const int it = T - 1 - j;                           // iteration number (barrier phases)
+            const size_t wrow = (size_t)j * B + m0 + q * 32;
+            float* DAw = DA + wrow * 3 * H;
+            // ---- D + P: dh = keep + dhn (0 for the last step) ; gate derivatives ; A <- da_c ----
+            if (it > 0) { mbar_wait(&ddh_full, (it - 1) & 1); tc_fence_after(); }
+            for (int k = k_beg; k < k_end; ++k) {
+                const int c0 = 16 * k;
+                float dl[16], zz[16], cc[16], hp[16], dh[16], kp[16];
+                uint32_t s0, s1, s2, s3; uint64_t *r0, *r1, *r2, *r3;
+                // the ring has 2 stages: release the first two tiles as soon as they are in registers, keep the
+                // slices of the last two as store staging
+                in_take(dl, s0, r0); mbar_arrive(r0);
+                in_take(zz, s1, r1); mbar_arrive(r1);
+                in_take(cc, s2, r2); in_take(hp, s3, r3);
+                if (it > 0) {
+                    tmem_ld16(tmem + tl + T_DH + (uint32_t)c0, dh);
+                    tmem_ld16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { dh[i] = 0.f; kp[i] = 0.f; }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float dht = ok ? dh[i] + kp[i] + dl[i] : 0.f;
+                    const float z_ = zz[i], c_ = cc[i];
+                    const float dac = dht * z_ * (1.f - c_ * c_);
+                    const float daz = dht * (c_ - hp[i]) * z_ * (1.f - z_);
+                    kp[i] = ok ? dht * (1.f - z_) : 0.f;        // keep
+                    dl[i] = ok ? dac : 0.f;                     // da_c
+                    dh[i] = ok ? daz : 0.f;                     // da_z
+                }
+                tmem_st16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
+                tmem_st16(tmem + tl + T_DAZ + (uint32_t)c0, dh);
+                a_store16<SPLIT3>(a_hi, a_lo, row, c0, dl);
+                warp_store_chunk(s2, lane, dh, DAw + c0, 3 * H, rows_valid);            // DA_z
+                warp_store_chunk(s3, lane, dl, DAw + 2 * H + c0, 3 * H, rows_valid);    // DA_c
+                mbar_arrive(r2); mbar_arrive(r3);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(&a_ready);                              // A = da_c
+            // ---- M1: A <- da_z (after GEMM_M has read da_c) ----
+            mbar_wait(&dm_full, it & 1);
+            tc_fence_after();
+            if (j > 0) {
+                for (int k = k_beg; k < k_end; ++k) {
+                    float dz[16];
+                    tmem_ld16(tmem + tl + T_DAZ + (uint32_t)(16 * k), dz);
+                    a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, dz);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready);                          // A = da_z
+            }
+            // ---- M2: da_r, keep += m r  (runs while GEMM_DH1 executes) ----
+            for (int k = k_beg; k < k_end; ++k) {
+                const int c0 = 16 * k;
+                float rr[16], hp[16], mm[16], kp[16];
+                uint32_t s0, s1; uint64_t *r0, *r1;
+                in_take(rr, s0, r0); in_take(hp, s1, r1);
+                tmem_ld16(tmem + tl + T_M + (uint32_t)c0, mm);
+                tmem_ld16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float m_ = ok ? mm[i] : 0.f, r_ = rr[i];
+                    kp[i] = kp[i] + m_ * r_;
+                    mm[i] = ok ? m_ * hp[i] * r_ * (1.f - r_) : 0.f;       // da_r
+                }
+                tmem_st16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
+                tmem_st16(tmem + tl + T_M + (uint32_t)c0, mm);              // stash da_r over m
+                warp_store_chunk(s0, lane, mm, DAw + H + c0, 3 * H, rows_valid);        // DA_r
+                mbar_arrive(r0); mbar_arrive(r1);
+            }
+            // ---- M3: A <- da_r (after GEMM_DH1 has read da_z) ----
+            if (j > 0) {
+                mbar_wait(&dh1_done, it & 1);
+                tc_fence_after();
+                for (int k = k_beg; k < k_end; ++k) {
+                    float dr[16];
+                    tmem_ld16(tmem + tl + T_M + (uint32_t)(16 * k), dr);
+                    a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, dr);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready);                          // A = da_r
+            }
+        }
+    } else if (warp < 10) {
+        // ================================ input producers (one warp per column half, cp.async) ================================
+        const int hf = warp - 8;
+        const int per_step = 6 * HCH;
+        const int64_t n_tiles = (int64_t)T * per_step;
+        for (int64_t ai = 0; ai < n_tiles; ++ai) {
+            const int s = (int)(ai % AX_STAGES);
+            if (ai >= AX_STAGES) mbar_wait(&in_empty[hf][s], (uint32_t)((ai / AX_STAGES) - 1) & 1);
+            const int j = T - 1 - (int)(ai / per_step), ti = (int)(ai % per_step);
+            int kind, kk;                                       // 0 DHl, 1 Z, 2 C, 3 H_prev, 4 R
+            if (ti < 4 * HCH) { kind = ti & 3; kk = ti >> 2; }
+            else { const int t2 = ti - 4 * HCH; kind = (t2 & 1) ? 3 : 4; kk = t2 >> 1; }
+            const float* base = kind == 0 ? DHl : kind == 1 ? Z : kind == 2 ? C : kind == 3 ? Hs : R;
+            const float* src = base + ((size_t)j * B + m0) * H + 16 * (hf * HCH + kk);
+            const uint32_t dst = in_base + (hf * AX_STAGES + s) * AX_TILE;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                int f = lane + i * 32, rw = f >> 2, c = f & 3;
+                if (m0 + rw < B)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + sw64(rw, c)), "l"(src + (size_t)rw * H + 4 * c) : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&in_full[hf][s])) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp == 10) {
+        if (lane == 0) {
+            // ================================ MMA issuer ================================
+            int64_t ws = 0; uint32_t pa = 0;
+            auto gemm = [&](uint32_t dcol, bool fresh) {
+                for (int kb = 0; kb < KB; ++kb, ++ws) {
+                    const int s = (int)(ws % WST);
+                    mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                    tc_fence_after();
+                    const uint32_t sW = w_base + s * w_stage;
+                    mma_kblock<SPLIT3>(tmem + dcol, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, fresh && kb == 0);
+                    umma_commit(&w_empty[s]);
+                }
+            };
+            for (int j = T - 1; j >= 0; --j) {
+                mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_c
+                gemm(T_M, true);
+                umma_commit(&dm_full);
+                if (j > 0) {
+                    mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_z
+                    gemm(T_DH, true);
+                    umma_commit(&dh1_done);
+                    mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_r
+                    gemm(T_DH, false);
+                    umma_commit(&ddh_full);
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ================================ transposed Wh tiles: one bulk async copy (TMA) each ================================
+        const int64_t n_tiles = (int64_t)(T - 1) * 3 * KB + KB;         // the last step (j = 0) needs only Wh[2]
+        for (int64_t ws = 0; ws < n_tiles; ++ws) {
+            const int s = (int)(ws % WST);
+            if (ws >= WST) mbar_wait(&w_empty[s], (uint32_t)((ws / WST) - 1) & 1);
+            const uint32_t bar = smem_u32(&w_full[s]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_stage) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(w_base + s * w_stage), "l"(wimg + (size_t)(ws % (3 * KB)) * w_stage), "r"(w_stage), "r"(bar) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+template <bool SPLIT3>
+static int launch_bwd_inst(poi_engine* e, const float* DHl, const float* Z, const float* R, const float* C, const float* Hs,
+                           const float* wh, float* DA, int B, int T, int H) {
+    const int KB = H / 32;
+    const size_t w_stage = (size_t)H * 128 * (SPLIT3 ? 2 : 1);
+    uint8_t* wimg = nullptr;
+    POI_TRY(arena_get(e, (size_t)3 * KB * w_stage, &wimg));
+    POI_CAT(e, CAT_ELTWISE, 0, 0);
+    POI_LAUNCH(e, (k_stage_wh_bwd<SPLIT3>), 48, 256, 0, wh, H, wimg);
+    size_t smem = (size_t)KB * A_KB_BYTES * (SPLIT3 ? 2 : 1) + 2 * w_stage + (size_t)2 * AX_STAGES * AX_TILE + 1024;
+    POI_CK(e, cudaFuncSetAttribute(k_gru_bwd_fused<SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
+    POI_LAUNCH(e, (k_gru_bwd_fused<SPLIT3>), (unsigned)poi_cdiv(B, FM), F_THREADS, smem, DHl, Z, R, C, Hs, wimg, DA, B, T, H);
+    return 0;
+}
+
+static int launch_gru_bwd_fused(poi_engine* e, const float* DHl, const float* Z, const float* R, const float* C,
+                                const float* Hs, const float* wh, float* DA, int B, int T, int H, bool split3) {
+    if (split3) return launch_bwd_inst<true>(e, DHl, Z, R, C, Hs, wh, DA, B, T, H);
+    return launch_bwd_inst<false>(e, DHl, Z, R, C, Hs, wh, DA, B, T, H);
+}
+
 static inline bool fwd_supported(int H) { return H % 32 == 0 && H >= 32 && H <= 128; }
 
 // RH = R * H_prev (the r-gated state the candidate GEMM consumed): the fused kernel keeps it on chip, the
