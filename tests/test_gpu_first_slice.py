@@ -78,3 +78,22 @@ def test_sumsq(engine, n):
     got = engine.sumsq(torch.from_numpy(x).cuda())
     ref = float(np.sum(x.astype(np.float64) ** 2))
     assert abs(got - ref) <= 1e-6 * max(ref, 1e-12) + 1e-12
+
+
+def test_empty_inputs(engine):
+    """n = 0: unique of nothing is nothing, scatter of nothing leaves the table alone."""
+    t = torch.ones((4, 8), device="cuda")
+    e_idx = torch.zeros((0,), dtype=torch.int32, device="cuda")
+    uq, cnt = engine.unique(e_idx, 4)
+    assert uq.numel() == 0 and cnt.numel() == 0
+    engine.scatter_sgd(t, e_idx, None, 0.1, 0.1)
+    assert torch.equal(t, torch.ones((4, 8), device="cuda"))
+
+
+def test_scatter_without_gradient_is_pure_decay(engine):
+    """grad = NULL: rows decay by alpha * lambda * count (the pad-row case of GRU.py:365)."""
+    t = torch.full((6, 8), 2.0, device="cuda")
+    idx = torch.tensor([5, 5, 5, 1], dtype=torch.int32, device="cuda")
+    engine.scatter_sgd(t, idx, None, 0.5, 0.1)
+    exp = np.full((6, 8), 2.0, dtype=np.float32); exp[5] = 2.0 - 0.5 * (0.1 * 3 * 2.0); exp[1] = 2.0 - 0.5 * (0.1 * 1 * 2.0)
+    assert np.allclose(t.cpu().numpy(), exp, rtol=1e-6)

@@ -232,3 +232,30 @@ def test_obo_spatial_both_gemm_modes(engine, mode):
     got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
     for k in got:
         assert_close(got[k], ref[k], RTOL, k)
+
+
+def test_edge_cases_length_one_and_two(engine):
+    """L = 1 users: no scan step at all (T = 0) -> the call only applies the L2 decay of the gathered rows and
+    weights; L = 2: a single step.  Both against the oracle, in the default GEMM mode."""
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(31)
+    n_user, n_item, d, lmax, n_dist = 4, 60, 32, 6, 20
+    P = np.full((n_user, lmax), n_item, dtype=np.int32); Q = P.copy(); M = np.zeros_like(P)
+    DP = np.full_like(P, n_dist); DQ = DP.copy()
+    lens = [1, 1, 2, 2]
+    for u, L in enumerate(lens):
+        P[u, :L] = rs.randint(0, n_item, L); Q[u, :L] = rs.randint(0, n_item, L); M[u, :L] = 1
+        if L > 1:
+            DP[u, 1:L] = rs.randint(0, n_dist + 1, L - 1); DQ[u, 1:L] = rs.randint(0, n_dist + 1, L - 1)
+    st = Fx.nonzero_bias(rs, Fx.gru_state(rs, n_item, d, d, n_dist))
+    tes = [[n_item]] * n_user
+    m = SpatialGru([P, M, Q], [tes, [[0]] * n_user, tes], [DP, [[n_dist]] * n_user, DQ], [ALPHA, LAM], n_user, n_item,
+                   [n_dist, 0.2], d, d, init=st)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for se in (np.array([0, 1], dtype=np.int32), np.array([2, 3], dtype=np.int32), np.array([0, 3], dtype=np.int32)):
+        out = m.train(se)
+        (rl, rsur, rupq, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
+        assert abs(out[0] - rl) <= 1e-4 * max(abs(rl), 1e-3)
+    got = state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
+    for k in got:
+        assert_close(got[k], ref[k], RTOL, k)
