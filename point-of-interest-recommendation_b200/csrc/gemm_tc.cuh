@@ -274,6 +274,180 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
     if (warp == 0) tmem_dealloc(tmem, BN);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for the large GEMMs: grid = #SMs, every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+// with TWO TMEM accumulators, so the epilogue of tile i (4 dedicated warps) overlaps the main loop of
+// tile i+1 (8 producer warps + the MMA thread never stop).  Tile order keeps the n-blocks of one m-block
+// adjacent (the A tile is re-read from L2, not HBM).
+// ---------------------------------------------------------------------------------------------
+constexpr int P_THREADS = PRODUCERS + 32 + 128;     // 8 producer warps, MMA warp, 4 epilogue warps
+
+template <int BN, bool SPLIT3, class Epi>
+__global__ void __launch_bounds__(P_THREADS, 1)
+k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                     int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, int splits, Epi epi) {
+    using C = Cfg<BN, SPLIT3>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t mbar_full[C::STAGES], mbar_empty[C::STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stg_base = sbase + C::STAGES * C::STAGE_BYTES;      // 4 x 4 KB epilogue staging
+    const int total = tiles_m * tiles_n * splits;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&mbar_full[s], PRODUCERS); mbar_init(&mbar_empty[s], 1); }
+        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+        mbar_init(&acc_empty[0], 128); mbar_init(&acc_empty[1], 128);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    auto decode = [&](int t, int& m0, int& n0, int& kbeg, int& kend) {
+        const int z = t / (tiles_m * tiles_n), r = t % (tiles_m * tiles_n);
+        m0 = (r / tiles_n) * BM; n0 = (r % tiles_n) * BN;
+        kbeg = z * k_per_split; kend = min(K, kbeg + k_per_split);
+    };
+
+    if (warp < 8) {
+        // ------------------------------ producers ------------------------------
+        float4 ra[3][C::LA], rw[3][C::LW];
+        const int srow = tid >> 3, sc = tid & 7;
+        const uint32_t soff = srow * 128 + ((sc ^ (srow & 7)) << 4);
+        const size_t strA = (size_t)32 * lda, strW = (size_t)32 * ldw;
+        int64_t gkb = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            int m0, n0, kbeg, kend; decode(t, m0, n0, kbeg, kend);
+            const int KB = (kend - kbeg + BK - 1) / BK;
+            const float* pA = A + (size_t)(m0 + srow) * lda + sc * 4;
+            const float* pW = W + (size_t)(n0 + srow) * ldw + sc * 4;
+            uint32_t okA = 0, okW = 0;
+#pragma unroll
+            for (int i = 0; i < C::LA; ++i) okA |= (m0 + srow + 32 * i < M ? 1u : 0u) << i;
+#pragma unroll
+            for (int i = 0; i < C::LW; ++i) okW |= (n0 + srow + 32 * i < N ? 1u : 0u) << i;
+            auto gload = [&](int kb, float4 (&ra_)[C::LA], float4 (&rw_)[C::LW]) {
+                const int k0 = kbeg + kb * BK;
+                const bool kin = k0 + sc * 4 < kend;
+#pragma unroll
+                for (int i = 0; i < C::LA; ++i)
+                    ra_[i] = (kin && ((okA >> i) & 1u)) ? *reinterpret_cast<const float4*>(pA + i * strA + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < C::LW; ++i)
+                    rw_[i] = (kin && ((okW >> i) & 1u)) ? *reinterpret_cast<const float4*>(pW + i * strW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            auto stage_in = [&](const float4 (&ra_)[C::LA], const float4 (&rw_)[C::LW]) {
+                const int s = (int)(gkb % C::STAGES);
+                if (gkb >= C::STAGES) mbar_wait(&mbar_empty[s], (uint32_t)((gkb / C::STAGES) - 1) & 1);
+                const uint32_t sA = sbase + s * C::STAGE_BYTES + soff, sW = sA + C::A_BYTES;
+                const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
+#pragma unroll
+                for (int i = 0; i < C::LA; ++i) {
+                    if (SPLIT3) { float4 hi, lo; split4(ra_[i], hi, lo); sts4(sA + i * 4096, hi); sts4(sAl + i * 4096, lo); }
+                    else sts4(sA + i * 4096, ra_[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < C::LW; ++i) {
+                    if (SPLIT3) { float4 hi, lo; split4(rw_[i], hi, lo); sts4(sW + i * 4096, hi); sts4(sWl + i * 4096, lo); }
+                    else sts4(sW + i * 4096, rw_[i]);
+                }
+                fence_async_smem();
+                mbar_arrive(&mbar_full[s]);
+                ++gkb;
+            };
+#pragma unroll
+            for (int u = 0; u < 2; ++u) if (u < KB) gload(u, ra[u], rw[u]);
+            for (int kb = 0; kb < KB; kb += 3) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    if (kb + u < KB) {
+                        if (kb + u + 2 < KB) gload(kb + u + 2, ra[(u + 2) % 3], rw[(u + 2) % 3]);
+                        stage_in(ra[u], rw[u]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            // ------------------------------ MMA issuer ------------------------------
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            int64_t gkb = 0; int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+                int m0, n0, kbeg, kend; decode(t, m0, n0, kbeg, kend);
+                const int KB = (kend - kbeg + BK - 1) / BK;
+                const int buf = it & 1;
+                if (it >= 2) { mbar_wait(&acc_empty[buf], (uint32_t)((it >> 1) - 1) & 1); tc_fence_after(); }
+                const uint32_t d_tmem = tmem + buf * BN;
+                for (int kb = 0; kb < KB; ++kb, ++gkb) {
+                    const int s = (int)(gkb % C::STAGES);
+                    mbar_wait(&mbar_full[s], (uint32_t)(gkb / C::STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sA = sbase + s * C::STAGE_BYTES, sW = sA + C::A_BYTES;
+                    const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
+                    const uint64_t dA = make_sdesc(sA), dW = make_sdesc(sW);
+                    uint32_t acc = kb > 0 ? 1u : 0u;
+                    if (SPLIT3) {
+                        const uint64_t dAl = make_sdesc(sAl), dWl = make_sdesc(sWl);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) { umma_tf32(d_tmem, dAl + 2 * k, dW + 2 * k, idesc, acc); acc = 1u; }
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) umma_tf32(d_tmem, dA + 2 * k, dWl + 2 * k, idesc, 1u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) { umma_tf32(d_tmem, dA + 2 * k, dW + 2 * k, idesc, acc); acc = 1u; }
+                    umma_commit(&mbar_empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ------------------------------ epilogue (warps 9..12; TMEM lane quadrant = warp % 4) ------------------------------
+        const int q = warp & 3;
+        const uint32_t stg = stg_base + q * 4096;
+        const int rr0 = lane >> 3, qq = lane & 7;
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            int m0, n0, kbeg, kend; decode(t, m0, n0, kbeg, kend);
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1);
+            tc_fence_after();
+            const int rbase = m0 + q * 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[16];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0 + 16 * h), v);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd)
+                        sts4(stg + lane * 128 + (((4 * h + qd) ^ (lane & 7)) << 4), make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = rr0 + 4 * i;
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                 : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
+                    const int m = rbase + rr, n = n0 + c0 + 4 * qq;
+                    if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4); }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);          // accumulator drained: the MMA thread may overwrite it
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 2 * BN);
+}
+
 }  // namespace tc
 
 static inline bool tc_gemm_supported(int64_t M, int N, int K, int lda, int ldw) {
@@ -296,12 +470,36 @@ static int launch_tc_inst(poi_engine* e, const float* A, int lda, const float* W
     return 0;
 }
 
+template <int BN, bool SPLIT3, class Epi>
+static int launch_tc_persist(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K,
+                             const Epi& epi, int splits, int k_per_split) {
+    using C = tc::Cfg<BN, SPLIT3>;
+    const int smem = C::STAGES * C::STAGE_BYTES + 4 * 4096 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_tn_tc_persist<BN, SPLIT3, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    if (splits <= 1) { splits = 1; k_per_split = K; }
+    const int tiles_m = (int)poi_cdiv(M, tc::BM), tiles_n = (int)poi_cdiv(N, BN);
+    const int64_t total = (int64_t)tiles_m * tiles_n * splits;
+    unsigned grid = (unsigned)std::min<int64_t>(total, e->num_sms);
+    POI_LAUNCH(e, (tc::k_gemm_tn_tc_persist<BN, SPLIT3, Epi>), grid, tc::P_THREADS, smem, A, lda, W, ldw, (int)M, N, K,
+               k_per_split, tiles_m, tiles_n, splits, epi);
+    return 0;
+}
+
 template <class Epi>
 static int launch_gemm_tn_tc(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K,
                              const Epi& epi, bool split3) {
-    // 3xTF32 performs 3 MMAs per staged tile, 1xTF32 one: count what the tensor pipe executes
+    // achieved = algorithmic flops (3xTF32 issues three MMAs per product; counted once)
     POI_CAT(e, CAT_GEMM, 2.0 * (double)M * N * K, 0);
-    const bool wide = poi_cdiv(M, tc::BM) * poi_cdiv(N, 128) >= e->num_sms;
+    const int64_t tiles128 = poi_cdiv(M, tc::BM) * poi_cdiv(N, 128);
+    if (e->persistent_gemm && tiles128 >= 2 * e->num_sms) {       // many tiles: persistent CTAs with overlapped epilogue
+        if (split3) return launch_tc_persist<128, true>(e, A, lda, W, ldw, M, N, K, epi, 1, 0);
+        return launch_tc_persist<128, false>(e, A, lda, W, ldw, M, N, K, epi, 1, 0);
+    }
+    const bool wide = tiles128 >= e->num_sms;
     if (split3) {
         if (wide) return launch_tc_inst<128, true>(e, A, lda, W, ldw, M, N, K, epi);
         return launch_tc_inst<64, true>(e, A, lda, W, ldw, M, N, K, epi);
