@@ -90,6 +90,12 @@ int poi_scatter_sgd(poi_engine* e, float* table_dev, int64_t n_rows, int dim,
 int poi_gemm_tn(poi_engine* e, const float* A_dev, int lda, const float* W_dev, int ldw,
                 int64_t M, int N, int K, const float* bias_dev, float* C_dev, int ldc, int mode);
 
+/* C[i, j] = sum_m A[m*lda + i] * B[m*ldb + j]  (i < N1, j < N2; N1, N2 multiples of 4) -- the weight-gradient
+ * contraction over all (t, b) rows (T.grad w.r.t. ui / wh / vs, GRU.py:370, GRU_Spatial.py:210).  mode 0 = fp32
+ * FMA split-K kernel, 1/2 = tcgen05 with MN-major operands (no transposed copies).  Test hook. */
+int poi_gemm_atb(poi_engine* e, const float* A_dev, int lda, const float* B_dev, int ldb,
+                 int64_t M, int N1, int N2, float* C_dev, int mode);
+
 /* sum of squares of n floats, fp64 accumulation -- building block of `model.l2.eval()`
  * (GRU.py:305-309, GRU_Spatial.py:83-88, BPR.py:195-198, PRME.py:166-169, GeoIE.py:92-98). */
 int poi_sumsq(poi_engine* e, const float* x_dev, int64_t n, double* out_host);

@@ -55,6 +55,7 @@ _PROTOS = {
     "poi_unique": (c_int, [_E, c_void_p, c_int64, c_int32, c_void_p, c_void_p, POINTER(c_int64)]),
     "poi_scatter_sgd": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_float]),
     "poi_gemm_tn": (c_int, [_E, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int]),
+    "poi_gemm_atb": (c_int, [_E, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int]),
     "poi_sumsq": (c_int, [_E, c_void_p, c_int64, POINTER(c_double)]),
     "poi_gru_train": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32,
                               c_float, c_float, POINTER(c_double)]),

@@ -285,6 +285,28 @@ int poi_gemm_tn(poi_engine* e, const float* A, int lda, const float* W, int ldw,
     return 0;
 }
 
+__global__ void k_reduce_plain(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = 0.f;
+    for (int s = 0; s < splits; ++s) g += part[(size_t)s * n + i];
+    out[i] = g;
+}
+
+int poi_gemm_atb(poi_engine* e, const float* A, int lda, const float* B, int ldb, int64_t M, int N1, int N2,
+                 float* C, int mode) {
+    POI_TRY(begin_call(e));
+    if ((N1 % 4) || (N2 % 4) || (lda % 4) || (ldb % 4)) POI_FAIL(e, "N1, N2, lda, ldb must be multiples of 4");
+    AtbPlan plan;
+    if (mode == 0) POI_TRY(launch_gemm_atb(e, A, lda, B, ldb, M, N1, N2, &plan));
+    else POI_TRY(launch_gemm_atb_tc_mn(e, A, lda, B, ldb, M, N1, N2, mode == 1, &plan));
+    const int64_t n = (int64_t)N1 * N2;
+    POI_LAUNCH(e, k_reduce_plain, (unsigned)poi_cdiv(n, 256), 256, 0, plan.part, plan.splits, n, C);
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    return 0;
+}
+
 int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* items, int64_t n_item, int32_t H,
                    const float* prob, float wd, int32_t top_k, int32_t* topk_dev) {
     POI_TRY(begin_call(e));

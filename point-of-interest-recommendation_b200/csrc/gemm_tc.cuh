@@ -448,6 +448,162 @@ k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restri
     if (warp == 0) tmem_dealloc(tmem, 2 * BN);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight-gradient GEMM without transposes:  C[i,j] = sum_m A[m,i] * Bm[m,j]  (reduction over the rows).
+// Both operands are MN-major for the UMMA: a stage holds 32 rows m (the K dimension) x 128 columns, stored as
+// [MN block of 32 columns][group of 8 rows][8 rows x 128 B, 128B-swizzled] -- the canonical MN-major SW128
+// layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with SBO = 1 KB (next 8 rows) and LBO = 4 KB (next
+// 32 columns).  Global rows are read as they lie (512 contiguous bytes per warp), no transposed copies.
+// blockIdx.z = split over m; partials reduced in split order by k_reduce_update / k_reduce_only.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)(4096 >> 4) << 16;      // LBO: next MN block (32 columns)
+    d |= (uint64_t)(1024 >> 4) << 32;      // SBO: next group of 8 k-rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+    return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);     // a_major = b_major = MN
+}
+
+template <bool SPLIT3>
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_atb_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+              int64_t Mrows, int N1, int N2, int64_t m_per_split, float* __restrict__ part) {
+    constexpr int BN = 128;
+    constexpr int STAGES = SPLIT3 ? 3 : 4;
+    constexpr int T_BYTES = BK * 128 * 4;                       // one operand tile: 32 rows x 128 columns
+    constexpr int STAGE_BYTES = 2 * T_BYTES * (SPLIT3 ? 2 : 1);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t mbar_full[STAGES], mbar_empty[STAGES], mbar_done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int64_t mbeg = (int64_t)blockIdx.z * m_per_split;
+    const int64_t mend = mbeg + m_per_split < Mrows ? mbeg + m_per_split : Mrows;
+    const int KB = mend > mbeg ? (int)((mend - mbeg + BK - 1) / BK) : 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&mbar_full[s], PRODUCERS); mbar_init(&mbar_empty[s], 1); }
+        mbar_init(&mbar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp < 8) {
+        float4 ra[3][4], rb[3][4];
+        // chunk f = tid + 256 i : k-row kr = (tid >> 5) + 8 i, float4 column c = tid & 31 (fixed per thread)
+        const int kr0 = tid >> 5, cq = tid & 31;
+        const uint32_t soff = (cq >> 3) * 4096 + kr0 * 128 + (((cq & 7) ^ kr0) << 4);     // + i * 1024 (kr0 < 8, group = i)
+        const bool okA = i0 + 4 * cq < N1, okB = j0 + 4 * cq < N2;
+        const float* pA = A + (size_t)kr0 * lda + i0 + 4 * cq;
+        const float* pB = Bm + (size_t)kr0 * ldb + j0 + 4 * cq;
+        auto gload = [&](int kb, float4 (&ra_)[4], float4 (&rb_)[4]) {
+            const int64_t mk = mbeg + (int64_t)kb * BK;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t m = mk + kr0 + 8 * i;
+                ra_[i] = (okA && m < mend) ? *reinterpret_cast<const float4*>(pA + (size_t)(mk + 8 * i) * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rb_[i] = (okB && m < mend) ? *reinterpret_cast<const float4*>(pB + (size_t)(mk + 8 * i) * ldb) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto stage_in = [&](int kb, const float4 (&ra_)[4], const float4 (&rb_)[4]) {
+            const int s = kb % STAGES;
+            if (kb >= STAGES) mbar_wait(&mbar_empty[s], ((kb / STAGES) - 1) & 1);
+            const uint32_t sA = sbase + s * STAGE_BYTES + soff, sB = sA + T_BYTES;
+            const uint32_t sAl = sB + T_BYTES, sBl = sAl + T_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (SPLIT3) {
+                    float4 hi, lo;
+                    split4(ra_[i], hi, lo); sts4(sA + i * 1024, hi); sts4(sAl + i * 1024, lo);
+                    split4(rb_[i], hi, lo); sts4(sB + i * 1024, hi); sts4(sBl + i * 1024, lo);
+                } else { sts4(sA + i * 1024, ra_[i]); sts4(sB + i * 1024, rb_[i]); }
+            }
+            fence_async_smem();
+            mbar_arrive(&mbar_full[s]);
+        };
+#pragma unroll
+        for (int u = 0; u < 2; ++u) if (u < KB) gload(u, ra[u], rb[u]);
+        for (int kb = 0; kb < KB; kb += 3) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                if (kb + u < KB) {
+                    if (kb + u + 2 < KB) gload(kb + u + 2, ra[(u + 2) % 3], rb[(u + 2) % 3]);
+                    stage_in(kb + u, ra[u], rb[u]);
+                }
+            }
+        }
+    } else if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_tf32_mn(BM, BN);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&mbar_full[s], (kb / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t sA = sbase + s * STAGE_BYTES, sB = sA + T_BYTES, sAl = sB + T_BYTES, sBl = sAl + T_BYTES;
+            const uint64_t dA = make_sdesc_mn(sA), dB = make_sdesc_mn(sB);
+            uint32_t acc = kb > 0 ? 1u : 0u;
+            // one UMMA (K = 8) consumes one group of 8 k-rows: advance the start address by SBO = 1 KB (64 units)
+            if (SPLIT3) {
+                const uint64_t dAl = make_sdesc_mn(sAl), dBl = make_sdesc_mn(sBl);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { umma_tf32(tmem, dAl + 64 * k, dB + 64 * k, idesc, acc); acc = 1u; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem, dA + 64 * k, dBl + 64 * k, idesc, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { umma_tf32(tmem, dA + 64 * k, dB + 64 * k, idesc, acc); acc = 1u; }
+            umma_commit(&mbar_empty[s]);
+            if (kb == KB - 1) umma_commit(&mbar_done);
+        }
+    }
+    if (warp < 8) {
+        if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
+        const uint32_t stg = sbase + warp * 4096;
+        const int rbase = i0 + (warp & 3) * 32;
+        const int cbeg = (warp >> 2) * (BN / 2);
+        const int rr0 = lane >> 3, qq = lane & 7;
+        float* P = part + (size_t)blockIdx.z * N1 * N2;
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
+            float v[16];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (KB > 0) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c0 + 16 * h), v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    sts4(stg + lane * 128 + (((4 * h + q) ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = rr0 + 4 * i;
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                             : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
+                const int m = rbase + rr, n = j0 + c0 + 4 * qq;
+                if (m < N1 && n < N2) *reinterpret_cast<float4*>(P + (size_t)m * N2 + n) = x;
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, BN);
+}
+
 }  // namespace tc
 
 static inline bool tc_gemm_supported(int64_t M, int N, int K, int lda, int ldw) {
@@ -569,4 +725,30 @@ static int launch_gemm_atb_tc(poi_engine* e, const float* At, const float* Bt, i
     EpiPartial epi{plan->part, N1, N2};
     if (split3) return launch_tc_inst<128, true>(e, At, (int)Mp, Bt, (int)Mp, N1, N2, (int)Mp, epi, splits, (int)kps);
     return launch_tc_inst<128, false>(e, At, (int)Mp, Bt, (int)Mp, N1, N2, (int)Mp, epi, splits, (int)kps);
+}
+
+// A [M x lda] (columns i < N1 used), Bm [M x ldb] (columns j < N2 used), as they lie in memory; N1, N2 % 4 == 0
+static int launch_gemm_atb_tc_mn(poi_engine* e, const float* A, int lda, const float* Bm, int ldb, int64_t M, int N1, int N2,
+                                 bool split3, AtbPlan* plan) {
+    const int tiles = (int)(poi_cdiv(N1, tc::BM) * poi_cdiv(N2, 128));
+    const int64_t kblocks = poi_cdiv(M, tc::BK);
+    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(e->num_sms / std::max(tiles, 1), kblocks));
+    const int64_t mps = poi_cdiv(kblocks, splits) * tc::BK;
+    splits = (int)poi_cdiv(M, mps);
+    plan->splits = splits; plan->m_per_split = mps; plan->N1 = N1; plan->N2 = N2;
+    POI_TRY(arena_get(e, (size_t)splits * N1 * N2, &plan->part));
+    POI_CAT(e, CAT_WGRAD, 2.0 * (double)M * N1 * N2, 0);
+    dim3 grid((unsigned)poi_cdiv(N2, 128), (unsigned)poi_cdiv(N1, tc::BM), (unsigned)splits);
+    if (split3) {
+        constexpr int smem = 3 * (2 * tc::BK * 128 * 4 * 2) + 1024;
+        static bool set3 = false;
+        if (!set3) { POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_atb_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set3 = true; }
+        POI_LAUNCH(e, (tc::k_gemm_atb_tc<true>), grid, tc::THREADS, smem, A, lda, Bm, ldb, M, N1, N2, mps, plan->part);
+    } else {
+        constexpr int smem = 4 * (2 * tc::BK * 128 * 4) + 1024;
+        static bool set1 = false;
+        if (!set1) { POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_atb_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set1 = true; }
+        POI_LAUNCH(e, (tc::k_gemm_atb_tc<false>), grid, tc::THREADS, smem, A, lda, Bm, ldb, M, N1, N2, mps, plan->part);
+    }
+    return 0;
 }

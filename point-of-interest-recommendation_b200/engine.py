@@ -150,6 +150,13 @@ class Engine:
                                  C.data_ptr(), ldc, int(mode)))
         return C[:, :N]
 
+    def gemm_atb(self, A: torch.Tensor, B: torch.Tensor, mode: int = 0):
+        """C = A.T @ B; A [M, N1], B [M, N2] float32 CUDA row-major (N1, N2 multiples of 4)."""
+        C = torch.empty((A.shape[1], B.shape[1]), dtype=torch.float32, device=A.device)
+        self._ck(lib.poi_gemm_atb(self._h, _dev_f32(A, "A"), A.shape[1], _dev_f32(B, "B"), B.shape[1], A.shape[0],
+                                  A.shape[1], B.shape[1], C.data_ptr(), int(mode)))
+        return C
+
     def sumsq(self, x: torch.Tensor) -> float:
         out = c_double()
         self._ck(lib.poi_sumsq(self._h, _dev_f32(x, "x"), x.numel(), byref(out)))

@@ -27,3 +27,16 @@ def test_gemm_tn(engine, M, N, K, mode, tol):
     scale = np.sqrt(K) * 0.25 / 3.0 + 0.5          # typical magnitude of an entry
     err = np.max(np.abs(C - ref)) / scale
     assert err < tol, "mode %d max scaled error %.3e" % (mode, err)
+
+
+@pytest.mark.parametrize("M,N1,N2", [(64, 128, 128), (1000, 384, 256), (126976, 384, 256), (5001, 204, 128), (40, 128, 128), (33333, 256, 128)])
+@pytest.mark.parametrize("mode,tol", [(0, 1e-5), (1, 2e-5), (2, 5e-3)])
+def test_gemm_atb(engine, M, N1, N2, mode, tol):
+    """Weight-gradient contraction C = A^T B over the rows (MN-major tcgen05 operands in modes 1, 2)."""
+    rs = np.random.RandomState(M + N1)
+    A = rs.uniform(-0.5, 0.5, (M, N1)).astype(np.float32)
+    B = rs.uniform(-0.5, 0.5, (M, N2)).astype(np.float32)
+    C = engine.gemm_atb(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), mode).cpu().numpy()
+    ref = A.astype(np.float64).T @ B.astype(np.float64)
+    err = np.max(np.abs(C - ref)) / (np.sqrt(M) * 0.25 / 3.0 + 0.5)
+    assert err < tol, "mode %d scaled error %.3e" % (mode, err)
