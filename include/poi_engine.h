@@ -61,6 +61,10 @@ int         poi_get_gemm_mode(poi_engine* e, int* mode);
 /* tensor-core modes only: 1 (default) = the recurrence runs as one persistent fused kernel per
  * direction, 0 = two GEMM launches per time step (kept for A/B measurements) */
 int         poi_set_fused_recurrence(poi_engine* e, int on);
+/* tensor-core modes only: 1 (default) = the weight-gradient GEMMs read the activation matrices as they lie in
+ * memory (MN-major tcgen05 operands; bias gradients fused into the same pass), 0 = transposed copies + K-major
+ * operands + a separate column-sum pass (kept for A/B measurements) */
+int         poi_set_wgrad_mn(poi_engine* e, int on);
 
 /* ---- first-slice kernels, individually testable ------------ */
 

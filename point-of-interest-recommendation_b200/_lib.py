@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpoi_b200.so")
+# POI_B200_LIB: an instrumented build of the same library (tools/fused_trace.py); never a different backend
+LIB_PATH = os.environ.get("POI_B200_LIB") or os.path.join(_HERE, "libpoi_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -51,6 +52,7 @@ _PROTOS = {
     "poi_set_gemm_mode": (c_int, [_E, c_int]),
     "poi_get_gemm_mode": (c_int, [_E, POINTER(c_int)]),
     "poi_set_fused_recurrence": (c_int, [_E, c_int]),
+    "poi_set_wgrad_mn": (c_int, [_E, c_int]),
     "poi_gather_rows": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "poi_unique": (c_int, [_E, c_void_p, c_int64, c_int32, c_void_p, c_void_p, POINTER(c_int64)]),
     "poi_scatter_sgd": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_float]),

@@ -333,3 +333,11 @@ int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* it
 }
 
 }  // extern "C"
+
+#ifdef POI_FUSED_TRACE
+// debugging build only (tools/fused_trace.py): clock stamps of CTA 0 of the fused recurrence kernels
+extern "C" int poi_debug_fused_trace(int dir, long long* out, int n, int clear) {
+    if (clear) { static long long zero[512 * 16]; return (int)cudaMemcpyToSymbol(fused::g_trace, zero, sizeof(zero), (size_t)dir * sizeof(zero)); }
+    return (int)cudaMemcpyFromSymbol(out, fused::g_trace, (size_t)n * sizeof(long long), (size_t)dir * 512 * 16 * sizeof(long long));
+}
+#endif

@@ -26,6 +26,7 @@ struct poi_engine {
     int64_t launches = 0;
     int gemm_mode = 1;               // default: tcgen05 3xTF32 (fp32-faithful); 0 = fp32 FMA, 2 = 1xTF32
     bool persistent_gemm = true;     // large tensor-core GEMMs: persistent CTAs, epilogue overlapped with the next tile
+    bool wgrad_mn = true;            // tensor-core weight gradients read the activations as they lie (MN-major UMMA operands, no transposes)
     bool fuse_recurrence = true;     // tensor-core modes: forward recurrence as one persistent fused kernel (gru_fused.cuh)
     // bump arena (device scratch owned by the engine); reset at the start of every call
     std::vector<PoiChunk> chunks;

@@ -450,18 +450,20 @@ k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restri
 
 // ---------------------------------------------------------------------------------------------
 // Weight-gradient GEMM without transposes:  C[i,j] = sum_m A[m,i] * Bm[m,j]  (reduction over the rows).
-// Both operands are MN-major for the UMMA: a stage holds 32 rows m (the K dimension) x 128 columns, stored as
-// [MN block of 32 columns][group of 8 rows][8 rows x 128 B, 128B-swizzled] -- the canonical MN-major SW128
-// layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with SBO = 1 KB (next 8 rows) and LBO = 4 KB (next
-// 32 columns).  Global rows are read as they lie (512 contiguous bytes per warp), no transposed copies.
+// Both operands are MN-major for the UMMA.  For 32-bit (tf32) MN-major operands the only shared-memory layout the
+// tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1; cute::UMMA::Layout_MN_SW128_32B_Atom): atoms of
+// 4 k-rows x 128 B (32 columns) in which the 32-byte unit index is XORed with (k-row & 3).  A stage holds 32 rows m
+// (the K dimension) x 128 columns, stored as [MN block of 32 columns][group of 4 rows][4 rows x 128 B]:
+// SBO = 512 B (next 4 rows), LBO = 4 KB (next 32 columns); one UMMA (K = 8) consumes two row groups = 1 KB.
+// Global rows are read as they lie (512 contiguous bytes per warp), no transposed copies.
 // blockIdx.z = split over m; partials reduced in split order by k_reduce_update / k_reduce_only.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr) {
     uint64_t d = (uint64_t)((saddr >> 4) & 0x3fffu);
     d |= (uint64_t)(4096 >> 4) << 16;      // LBO: next MN block (32 columns)
-    d |= (uint64_t)(1024 >> 4) << 32;      // SBO: next group of 8 k-rows
+    d |= (uint64_t)(512 >> 4) << 32;       // SBO: next group of 4 k-rows
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+    d |= (uint64_t)1 << 61;                // SWIZZLE_128B_BASE32B
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
@@ -471,9 +473,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
 template <bool SPLIT3>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_atb_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
-              int64_t Mrows, int N1, int N2, int64_t m_per_split, float* __restrict__ part) {
+              int64_t Mrows, int N1, int N2, int64_t m_per_split, float* __restrict__ part,
+              float* __restrict__ colsum_part) {
+    // colsum_part != NULL: the CTAs of the first column tile (blockIdx.x == 0) also emit the column sums of A over
+    // their m range, colsum_part[blockIdx.z][i] (the bias gradients: no separate pass over A)
     constexpr int BN = 128;
     constexpr int STAGES = SPLIT3 ? 3 : 4;
+    __shared__ float4 cs_sh[8][32];
     constexpr int T_BYTES = BK * 128 * 4;                       // one operand tile: 32 rows x 128 columns
     constexpr int STAGE_BYTES = 2 * T_BYTES * (SPLIT3 ? 2 : 1);
     extern __shared__ uint8_t smem_raw[];
@@ -502,8 +508,12 @@ k_gemm_atb_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bm
         float4 ra[3][4], rb[3][4];
         // chunk f = tid + 256 i : k-row kr = (tid >> 5) + 8 i, float4 column c = tid & 31 (fixed per thread)
         const int kr0 = tid >> 5, cq = tid & 31;
-        const uint32_t soff = (cq >> 3) * 4096 + kr0 * 128 + (((cq & 7) ^ kr0) << 4);     // + i * 1024 (kr0 < 8, group = i)
+        // k-row kr = kr0 + 8 i: row group kr >> 2 = (kr0 >> 2) + 2 i, row in group kr0 & 3; 32-byte unit ((cq & 7) >> 1) ^ (kr0 & 3)
+        const uint32_t soff = (cq >> 3) * 4096 + (kr0 >> 2) * 512 + (kr0 & 3) * 128 +
+                              (((((cq & 7) >> 1) ^ (kr0 & 3)) << 5) | ((cq & 1) << 4));       // + i * 1024
         const bool okA = i0 + 4 * cq < N1, okB = j0 + 4 * cq < N2;
+        const bool do_cs = colsum_part != nullptr && blockIdx.x == 0;
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* pA = A + (size_t)kr0 * lda + i0 + 4 * cq;
         const float* pB = Bm + (size_t)kr0 * ldb + j0 + 4 * cq;
         auto gload = [&](int kb, float4 (&ra_)[4], float4 (&rb_)[4]) {
@@ -522,6 +532,7 @@ k_gemm_atb_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bm
             const uint32_t sAl = sB + T_BYTES, sBl = sAl + T_BYTES;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                cs.x += ra_[i].x; cs.y += ra_[i].y; cs.z += ra_[i].z; cs.w += ra_[i].w;      // rows kr0, kr0+8, ... in order
                 if (SPLIT3) {
                     float4 hi, lo;
                     split4(ra_[i], hi, lo); sts4(sA + i * 1024, hi); sts4(sAl + i * 1024, lo);
@@ -542,6 +553,16 @@ k_gemm_atb_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bm
                 }
             }
         }
+        if (do_cs) {        // fixed-order sum over the 8 row phases
+            cs_sh[kr0][cq] = cs;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (kr0 == 0 && okA) {
+                float4 t = cs_sh[0][cq];
+#pragma unroll
+                for (int r = 1; r < 8; ++r) { const float4 u = cs_sh[r][cq]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+                *reinterpret_cast<float4*>(colsum_part + (size_t)blockIdx.z * N1 + i0 + 4 * cq) = t;
+            }
+        }
     } else if (lane == 0) {
         constexpr uint32_t idesc = make_idesc_tf32_mn(BM, BN);
         for (int kb = 0; kb < KB; ++kb) {
@@ -551,7 +572,7 @@ k_gemm_atb_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bm
             const uint32_t sA = sbase + s * STAGE_BYTES, sB = sA + T_BYTES, sAl = sB + T_BYTES, sBl = sAl + T_BYTES;
             const uint64_t dA = make_sdesc_mn(sA), dB = make_sdesc_mn(sB);
             uint32_t acc = kb > 0 ? 1u : 0u;
-            // one UMMA (K = 8) consumes one group of 8 k-rows: advance the start address by SBO = 1 KB (64 units)
+            // one UMMA (K = 8) consumes two groups of 4 k-rows: advance the start address by 1 KB (64 units)
             if (SPLIT3) {
                 const uint64_t dAl = make_sdesc_mn(sAl), dBl = make_sdesc_mn(sBl);
 #pragma unroll
@@ -727,9 +748,10 @@ static int launch_gemm_atb_tc(poi_engine* e, const float* At, const float* Bt, i
     return launch_tc_inst<128, false>(e, At, (int)Mp, Bt, (int)Mp, N1, N2, (int)Mp, epi, splits, (int)kps);
 }
 
-// A [M x lda] (columns i < N1 used), Bm [M x ldb] (columns j < N2 used), as they lie in memory; N1, N2 % 4 == 0
+// A [M x lda] (columns i < N1 used), Bm [M x ldb] (columns j < N2 used), as they lie in memory; N1, N2 % 4 == 0,
+// lda, ldb % 4 == 0, 16-byte aligned bases.  colsum != NULL: also the column sums of A (plan with N1 = 1, N2 = N1).
 static int launch_gemm_atb_tc_mn(poi_engine* e, const float* A, int lda, const float* Bm, int ldb, int64_t M, int N1, int N2,
-                                 bool split3, AtbPlan* plan) {
+                                 bool split3, AtbPlan* plan, AtbPlan* colsum = nullptr) {
     const int tiles = (int)(poi_cdiv(N1, tc::BM) * poi_cdiv(N2, 128));
     const int64_t kblocks = poi_cdiv(M, tc::BK);
     int splits = (int)std::max<int64_t>(1, std::min<int64_t>(e->num_sms / std::max(tiles, 1), kblocks));
@@ -737,18 +759,24 @@ static int launch_gemm_atb_tc_mn(poi_engine* e, const float* A, int lda, const f
     splits = (int)poi_cdiv(M, mps);
     plan->splits = splits; plan->m_per_split = mps; plan->N1 = N1; plan->N2 = N2;
     POI_TRY(arena_get(e, (size_t)splits * N1 * N2, &plan->part));
+    float* cs_part = nullptr;
+    if (colsum) {
+        colsum->splits = splits; colsum->m_per_split = mps; colsum->N1 = 1; colsum->N2 = N1;
+        POI_TRY(arena_get(e, (size_t)splits * N1, &colsum->part));
+        cs_part = colsum->part;
+    }
     POI_CAT(e, CAT_WGRAD, 2.0 * (double)M * N1 * N2, 0);
     dim3 grid((unsigned)poi_cdiv(N2, 128), (unsigned)poi_cdiv(N1, tc::BM), (unsigned)splits);
     if (split3) {
         constexpr int smem = 3 * (2 * tc::BK * 128 * 4 * 2) + 1024;
         static bool set3 = false;
         if (!set3) { POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_atb_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set3 = true; }
-        POI_LAUNCH(e, (tc::k_gemm_atb_tc<true>), grid, tc::THREADS, smem, A, lda, Bm, ldb, M, N1, N2, mps, plan->part);
+        POI_LAUNCH(e, (tc::k_gemm_atb_tc<true>), grid, tc::THREADS, smem, A, lda, Bm, ldb, M, N1, N2, mps, plan->part, cs_part);
     } else {
         constexpr int smem = 4 * (2 * tc::BK * 128 * 4) + 1024;
         static bool set1 = false;
         if (!set1) { POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_atb_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set1 = true; }
-        POI_LAUNCH(e, (tc::k_gemm_atb_tc<false>), grid, tc::THREADS, smem, A, lda, Bm, ldb, M, N1, N2, mps, plan->part);
+        POI_LAUNCH(e, (tc::k_gemm_atb_tc<false>), grid, tc::THREADS, smem, A, lda, Bm, ldb, M, N1, N2, mps, plan->part, cs_part);
     }
     return 0;
 }

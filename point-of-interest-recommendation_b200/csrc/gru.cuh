@@ -546,7 +546,17 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
     // ---- weight gradients (split reductions) + dense SGD, all from pre-update values ----
     AtbPlan g_ui, g_whzr, g_whc, g_bi, g_vs, g_bs;
     const int64_t Mp = (TB + 3) / 4 * 4;
-    if (e->gemm_mode != 0 && TB >= 2048 && Mp < 0x7fffffffLL) {
+    bool have_colsums = false;
+    if (e->gemm_mode != 0 && e->wgrad_mn && TB >= 2048) {
+        // tensor-core path, MN-major operands: the activation matrices are read as they lie (time-major rows =
+        // the contraction dimension), bias gradients (column sums of DA and dO) come out of the same pass
+        const bool s3 = e->gemm_mode == 1;
+        POI_TRY(launch_gemm_atb_tc_mn(e, DA, 3 * H, X, din, TB, 3 * H, din, s3, &g_ui, &g_bi));
+        POI_TRY(launch_gemm_atb_tc_mn(e, DA, 3 * H, Hs, H, TB, 2 * H, H, s3, &g_whzr));
+        POI_TRY(launch_gemm_atb_tc_mn(e, DA + 2 * H, 3 * H, RH, H, TB, H, H, s3, &g_whc));
+        if (head) POI_TRY(launch_gemm_atb_tc_mn(e, S, nDp, Hc, H, TB, nDp, H, s3, &g_vs, &g_bs));
+        have_colsums = true;
+    } else if (e->gemm_mode != 0 && TB >= 2048 && Mp < 0x7fffffffLL) {
         // tensor-core path: one transpose per activation matrix, then split-K UMMA GEMMs
         const bool s3 = e->gemm_mode == 1;
         float *DAt, *Xt, *Hpt, *RHt;
@@ -572,8 +582,10 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
         POI_TRY(launch_gemm_atb(e, DA + 2 * H, 3 * H, RH, H, TB, H, H, &g_whc));
         if (head) POI_TRY(launch_gemm_atb(e, S, nDp, Hc, H, TB, nDp, H, &g_vs));
     }
-    POI_TRY(launch_colsum(e, DA, 3 * H, TB, 3 * H, &g_bi));
-    if (head) POI_TRY(launch_colsum(e, S, nDp, TB, nDp, &g_bs));
+    if (!have_colsums) {
+        POI_TRY(launch_colsum(e, DA, 3 * H, TB, 3 * H, &g_bi));
+        if (head) POI_TRY(launch_colsum(e, S, nDp, TB, nDp, &g_bs));
+    }
     float* dg = mg ? mg->dense_grads : nullptr;
     POI_TRY(launch_reduce_to(e, g_ui, p->ui, din, 3 * H, din, alpha, lambda, dg ? dg + ML.ui : nullptr));
     POI_TRY(launch_reduce_to(e, g_whzr, p->wh, H, 2 * H, H, alpha, lambda, dg ? dg + ML.wh : nullptr));
@@ -632,6 +644,14 @@ static int gru_alloc_idx(poi_engine* e, int B, int lmax, bool head, GruIdx* ix) 
 
 static int gru_upload_i32(poi_engine* e, const int32_t* host, size_t n, int32_t** dev, size_t* stage_off) {
     POI_TRY(arena_get(e, n, dev));
+    // page-locked caller memory goes to the device directly (the call synchronises before it returns, so the
+    // buffer outlives the copy); pageable memory is staged through the engine's pinned buffer
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+        POI_CK(e, cudaMemcpyAsync(*dev, host, n * 4, cudaMemcpyHostToDevice, e->stream));
+        return 0;
+    }
+    cudaGetLastError();
     char* st = e->h_stage + *stage_off;
     memcpy(st, host, n * 4);
     POI_CK(e, cudaMemcpyAsync(*dev, st, n * 4, cudaMemcpyHostToDevice, e->stream));

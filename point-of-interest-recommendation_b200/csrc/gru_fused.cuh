@@ -31,6 +31,19 @@ constexpr int AX_TILE = FM * 64;      // 128 rows x 16 floats
 constexpr int AX_STAGES = 2;         // per column half
 constexpr int OUT_STG = 32 * 64;      // per-warp output staging: 32 rows x 16 floats
 
+// -DPOI_FUSED_TRACE (tools/fused_trace.py builds a separate library): CTA 0 records SM clock stamps of the
+// recurrence's hand-offs, 16 slots per time step, read back with poi_debug_fused_trace
+#ifdef POI_FUSED_TRACE
+__device__ long long g_trace[2][512 * 16];
+#define FTR(dir, step, slot) do { if (blockIdx.x == 0) g_trace[dir][(step) * 16 + (slot)] = clock64(); } while (0)
+#define FTR_ADD(dir, step, slot, v) do { if (blockIdx.x == 0) g_trace[dir][(step) * 16 + (slot)] += (v); } while (0)
+#define FTR_NOW() clock64()
+#else
+#define FTR(dir, step, slot) do { } while (0)
+#define FTR_ADD(dir, step, slot, v) do { } while (0)
+#define FTR_NOW() 0ll
+#endif
+
 __device__ __forceinline__ float4 lds4(uint32_t a) {
     float4 x;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(a));
@@ -185,7 +198,9 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
         // be reused as output staging once the whole warp has read) and the barrier to release it on
         auto ax_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
             const int s = (int)(axi % AX_STAGES);
+            const long long tw0 = FTR_NOW();
             mbar_wait(&ax_full[hf][s], (uint32_t)(axi / AX_STAGES) & 1);
+            if (warp == 0 && lane == 0) FTR_ADD(0, (int)(axi / (3 * HCH)), 12, FTR_NOW() - tw0);
             slice = ax_base + (hf * AX_STAGES + s) * AX_TILE + q * OUT_STG;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -201,6 +216,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             // ---- epilogue 1: z, r, r*h ; stash z and (1-z)*h ----
             mbar_wait(&d1_full, j & 1);
             tc_fence_after();
+            if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 4 : 8);
             for (int k = k_beg; k < k_end; ++k) {
                 const int c0 = 16 * k;
                 float a[16], b[16], hv[16], dz[16], dr[16];
@@ -227,10 +243,12 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             }
             fence_async_smem();
             tc_fence_before();
+            if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 5 : 9);
             mbar_arrive(&a_ready);                 // this warp's part of the r*h tile is in place
             // ---- epilogue 2: c, h_t ----
             mbar_wait(&d2_full, j & 1);
             tc_fence_after();
+            if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 6 : 10);
             for (int k = k_beg; k < k_end; ++k) {
                 const int c0 = 16 * k;
                 float a[16], dc[16], zz[16], u[16];
@@ -252,6 +270,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             }
             fence_async_smem();
             tc_fence_before();
+            if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 7 : 11);
             mbar_arrive(&a_ready);                 // this warp's part of the h_t tile is in place
         }
     } else if (warp < 10) {
@@ -283,10 +302,13 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             for (int j = 0; j < T; ++j) {
                 mbar_wait(&a_ready, pa & 1); ++pa;     // h_{j-1} tile staged (and the stashes of step j-1 consumed)
                 tc_fence_after();
+                FTR(0, j, 0);
                 for (int half = 0; half < 2; ++half) {
                     for (int kb = 0; kb < KB; ++kb, ++ws) {
                         const int s = (int)(ws % WST);
+                        const long long tw0 = FTR_NOW();
                         mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                        FTR_ADD(0, j, 13, FTR_NOW() - tw0);
                         tc_fence_after();
                         const uint32_t sW = w_base + s * w_stage;
                         mma_kblock<SPLIT3>(tmem + half * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
@@ -294,17 +316,22 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                     }
                 }
                 umma_commit(&d1_full);
+                FTR(0, j, 1);
                 mbar_wait(&a_ready, pa & 1); ++pa;     // r*h tile staged
                 tc_fence_after();
+                FTR(0, j, 2);
                 for (int kb = 0; kb < KB; ++kb, ++ws) {
                     const int s = (int)(ws % WST);
+                    const long long tw0 = FTR_NOW();
                     mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                    FTR_ADD(0, j, 14, FTR_NOW() - tw0);
                     tc_fence_after();
                     const uint32_t sW = w_base + s * w_stage;
                     mma_kblock<SPLIT3>(tmem + 2 * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
                     umma_commit(&w_empty[s]);
                 }
                 umma_commit(&d2_full);
+                FTR(0, j, 3);
             }
         }
     } else if (lane == 0) {
@@ -404,7 +431,9 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
         int64_t ini = 0;
         auto in_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
             const int s = (int)(ini % AX_STAGES);
+            const long long tw0 = FTR_NOW();
             mbar_wait(&in_full[hf][s], (uint32_t)(ini / AX_STAGES) & 1);
+            if (warp == 0 && lane == 0) FTR_ADD(1, (int)(ini / (6 * HCH)), 13, FTR_NOW() - tw0);
             slice = in_base + (hf * AX_STAGES + s) * AX_TILE + q * OUT_STG;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -421,6 +450,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             float* DAw = DA + wrow * 3 * H;
             // ---- D + P: dh = keep + dhn (0 for the last step) ; gate derivatives ; A <- da_c ----
             if (it > 0) { mbar_wait(&ddh_full, (it - 1) & 1); tc_fence_after(); }
+            if (lane == 0 && warp == 0) FTR(1, it, 6);
             for (int k = k_beg; k < k_end; ++k) {
                 const int c0 = 16 * k;
                 float dl[16], zz[16], cc[16], hp[16], dh[16], kp[16];
@@ -456,10 +486,12 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             }
             fence_async_smem();
             tc_fence_before();
+            if (lane == 0 && warp == 0) FTR(1, it, 7);
             mbar_arrive(&a_ready);                              // A = da_c
             // ---- M1: A <- da_z (after GEMM_M has read da_c) ----
             mbar_wait(&dm_full, it & 1);
             tc_fence_after();
+            if (lane == 0 && warp == 0) FTR(1, it, 8);
             if (j > 0) {
                 for (int k = k_beg; k < k_end; ++k) {
                     float dz[16];
@@ -468,6 +500,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 }
                 fence_async_smem();
                 tc_fence_before();
+                if (lane == 0 && warp == 0) FTR(1, it, 9);
                 mbar_arrive(&a_ready);                          // A = da_z
             }
             // ---- M2: da_r, keep += m r  (runs while GEMM_DH1 executes) ----
@@ -489,10 +522,12 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 warp_store_chunk(s0, lane, mm, DAw + H + c0, 3 * H, rows_valid);        // DA_r
                 mbar_arrive(r0); mbar_arrive(r1);
             }
+            if (lane == 0 && warp == 0) FTR(1, it, 10);
             // ---- M3: A <- da_r (after GEMM_DH1 has read da_z) ----
             if (j > 0) {
                 mbar_wait(&dh1_done, it & 1);
                 tc_fence_after();
+                if (lane == 0 && warp == 0) FTR(1, it, 11);
                 for (int k = k_beg; k < k_end; ++k) {
                     float dr[16];
                     tmem_ld16(tmem + tl + T_M + (uint32_t)(16 * k), dr);
@@ -500,6 +535,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 }
                 fence_async_smem();
                 tc_fence_before();
+                if (lane == 0 && warp == 0) FTR(1, it, 12);
                 mbar_arrive(&a_ready);                          // A = da_r
             }
         }
@@ -534,7 +570,9 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             auto gemm = [&](uint32_t dcol, bool fresh) {
                 for (int kb = 0; kb < KB; ++kb, ++ws) {
                     const int s = (int)(ws % WST);
+                    const long long tw0 = FTR_NOW();
                     mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                    FTR_ADD(1, (int)(ws / (3 * KB)), 14, FTR_NOW() - tw0);
                     tc_fence_after();
                     const uint32_t sW = w_base + s * w_stage;
                     mma_kblock<SPLIT3>(tmem + dcol, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, fresh && kb == 0);
@@ -543,15 +581,21 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             };
             for (int j = T - 1; j >= 0; --j) {
                 mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_c
+                FTR(1, T - 1 - j, 0);
                 gemm(T_M, true);
                 umma_commit(&dm_full);
+                FTR(1, T - 1 - j, 1);
                 if (j > 0) {
                     mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_z
+                    FTR(1, T - 1 - j, 2);
                     gemm(T_DH, true);
                     umma_commit(&dh1_done);
+                    FTR(1, T - 1 - j, 3);
                     mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_r
+                    FTR(1, T - 1 - j, 4);
                     gemm(T_DH, false);
                     umma_commit(&ddh_full);
+                    FTR(1, T - 1 - j, 5);
                 }
             }
         }

@@ -68,6 +68,7 @@ int poi_set_gemm_mode(poi_engine* e, int mode) {
 }
 int poi_get_gemm_mode(poi_engine* e, int* mode) { *mode = e->gemm_mode; return 0; }
 int poi_set_fused_recurrence(poi_engine* e, int on) { e->fuse_recurrence = on != 0; return 0; }
+int poi_set_wgrad_mn(poi_engine* e, int on) { e->wgrad_mn = on != 0; return 0; }
 int poi_kprof_enable(poi_engine* e, int on) { e->kprof = on != 0; return 0; }
 int poi_kprof_reset(poi_engine* e) {
     for (int c = 0; c < POI_NCAT; ++c) { e->cat_ms[c] = e->cat_flops[c] = e->cat_bytes[c] = 0.0; e->cat_launches[c] = 0; }

@@ -114,6 +114,9 @@ class Engine:
     def set_fused_recurrence(self, on: bool):
         self._ck(lib.poi_set_fused_recurrence(self._h, 1 if on else 0))
 
+    def set_wgrad_mn(self, on: bool):
+        self._ck(lib.poi_set_wgrad_mn(self._h, 1 if on else 0))
+
     def get_gemm_mode(self) -> int:
         m = c_int()
         self._ck(lib.poi_get_gemm_mode(self._h, byref(m)))

@@ -101,3 +101,34 @@ def test_c2_full_batch_properties(engine):
     assert np.array_equal(tabs[0][~touched], st["lt"][~touched])
     assert not touched[40000]
     assert np.all(np.isfinite(tabs[0]))
+
+
+def test_wgrad_mn_major_matches_oracle_and_transposed_path(engine):
+    """T*B >= 2048 takes the tensor-core weight-gradient path.  MN-major operands (activations read as they lie,
+    bias gradients fused) against the oracle, and against the transposed-copy K-major path of the same engine."""
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(11)
+    n_user, n_item, d, lmax, n_dist = 160, 3000, 64, 24, 60
+    P, Q, M = Fx.ragged_sequences(rs, n_user, n_item, lmax, min_len=12)
+    DP, DQ = Fx.interval_matrices(rs, P, Q, M, n_dist)
+    st = Fx.gru_state(rs, n_item, d, d, n_dist)
+    tes = [[n_item]] * n_user
+    se = np.arange(n_user, dtype=np.int32)
+    got = {}
+    try:
+        for mn in (True, False):
+            engine.set_wgrad_mn(mn)
+            m = SpatialGru([P, M, Q], [tes, [[0]] * n_user, tes], [DP, [[n_dist]] * n_user, DQ], [A, L], n_user, n_item,
+                           [n_dist, 0.2], d, d, init=st)
+            out = m.train(se)
+            got[mn] = (out[:3], state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs"]))
+    finally:
+        engine.set_wgrad_mn(True)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    (rl, rsur, rupq, rw), ref = E.gru_family_train_batch(ref, P, Q, M, A, L, DP, DQ)
+    for mn in (True, False):
+        assert_close(got[mn][0], [rl, rsur, rupq], 1e-4, "losses mn=%s" % mn)
+        for k in got[mn][1]:
+            assert_close(got[mn][1][k], ref[k], 1e-4, "%s mn=%s" % (k, mn))
+    for k in ("ui", "wh", "bi", "vs", "bs"):
+        assert_close(got[True][1][k], got[False][1][k], 2e-5, "mn vs transposed: " + k)
