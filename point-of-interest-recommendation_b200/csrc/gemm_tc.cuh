@@ -732,12 +732,26 @@ struct EpiPartial {       // split-K partial tile: part[blockIdx.z][m][n]
     }
 };
 
+// Split count of the tensor-core weight-gradient contractions.  The tensor core adds into its fp32 accumulator
+// with truncation, not round-to-nearest, so the error of one accumulation chain grows linearly with its length
+// (measured: 5291-row chains, 126976 x 384 x 256 -> 1.8e-4 of a typical entry); partials are summed in fp32 with
+// round-to-nearest by k_reduce_update.  Chains are therefore capped at ATB_MAX_CHAIN rows (more, shorter splits
+// than one wave needs) as long as the partial buffer stays small.
+constexpr int64_t ATB_MAX_CHAIN = 2048;
+static inline int atb_tc_splits(int num_sms, int tiles, int64_t kblocks, int N1, int N2) {
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(num_sms / std::max(tiles, 1), kblocks));
+    const int64_t want = poi_cdiv(kblocks * tc::BK, ATB_MAX_CHAIN);
+    const int64_t cap = std::max<int64_t>(1, ((int64_t)48 << 20) / ((int64_t)N1 * N2 * 4));     // <= 48 MB of partials
+    splits = std::max(splits, std::min(want, cap));
+    return (int)std::min(splits, kblocks);
+}
+
 // At [N1 x Mp], Bt [N2 x Mp] already transposed (leading dimension Mp, zero padded); fills plan
 static int launch_gemm_atb_tc(poi_engine* e, const float* At, const float* Bt, int64_t Mp, int N1, int N2,
                               bool split3, AtbPlan* plan) {
     const int tiles = (int)(poi_cdiv(N1, tc::BM) * poi_cdiv(N2, 128));
     int64_t kblocks = poi_cdiv(Mp, tc::BK);
-    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(e->num_sms / std::max(tiles, 1), kblocks));
+    int splits = atb_tc_splits(e->num_sms, tiles, kblocks, N1, N2);
     int64_t kps = poi_cdiv(kblocks, splits) * tc::BK;
     splits = (int)poi_cdiv(Mp, kps);
     plan->splits = splits; plan->m_per_split = kps; plan->N1 = N1; plan->N2 = N2;
@@ -754,7 +768,7 @@ static int launch_gemm_atb_tc_mn(poi_engine* e, const float* A, int lda, const f
                                  bool split3, AtbPlan* plan, AtbPlan* colsum = nullptr) {
     const int tiles = (int)(poi_cdiv(N1, tc::BM) * poi_cdiv(N2, 128));
     const int64_t kblocks = poi_cdiv(M, tc::BK);
-    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(e->num_sms / std::max(tiles, 1), kblocks));
+    int splits = atb_tc_splits(e->num_sms, tiles, kblocks, N1, N2);
     const int64_t mps = poi_cdiv(kblocks, splits) * tc::BK;
     splits = (int)poi_cdiv(M, mps);
     plan->splits = splits; plan->m_per_split = mps; plan->N1 = N1; plan->N2 = N2;
