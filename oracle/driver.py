@@ -1,6 +1,6 @@
 """CPU restatement of one run of the reference's Distance2Pre / GRU epoch loop
 (prog_bpr_gru_spatial.py:219-304) on top of ``oracle.models`` -- used to check the ported driver's
-loss trajectory and Recall@K end to end.  TEST INFRASTRUCTURE ONLY; parity unpinned."""
+loss trajectory and Recall@K end to end.  TEST INFRASTRUCTURE ONLY; pinned to the reference's model code via tests/golden/ref_*.npz."""
 from __future__ import annotations
 
 import numpy as np

@@ -1,5 +1,5 @@
 """Second, independent statement of the GRU-family train step: hand-derived
-backward in numpy (no autograd).  TEST INFRASTRUCTURE ONLY; parity unpinned
+backward in numpy (no autograd).  TEST INFRASTRUCTURE ONLY; pinned to the reference's model code via tests/golden/ref_*.npz
 (see ``oracle/__init__.py``).
 
 Follows public/GRU.py:313-389,407-498 (plain GRU) and public/GRU_Spatial.py:127-229

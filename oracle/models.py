@@ -1,6 +1,6 @@
 """Torch-CPU restatement of the reference's Theano train / predict graphs.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``; parity unpinned).
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``; pinned to the reference's own model classes run on oracle/theano_shim.py, tests/golden/ref_*.npz).
 
 Every function is *functional*: it takes a ``state`` dict of numpy arrays (the
 values of the reference's ``theano.shared`` parameters), the integer index

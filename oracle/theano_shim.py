@@ -422,7 +422,8 @@ class Alloc(Var):
 
     def compute(self, env):
         v = ev(self.value, env)
-        return v.expand(*_shape_list(self.shp, env)).clone()
+        shp = _shape_list(self.shp, env)
+        return v.expand(*shp).clone() if shp else v.clone()
 
 
 def t_ones_like(x):

@@ -1,5 +1,11 @@
-"""The oracle against the committed golden vectors (tests/golden/*.npz, generated by
-tests/golden/make_golden.py): guards the oracle itself against drift."""
+"""The oracle against the committed golden vectors: guards the oracle against drift AND pins it to the reference.
+
+tests/golden/<case>.npz      written by the oracle (make_golden.py)
+tests/golden/ref_<case>.npz  written by THE REFERENCE'S OWN MODEL CLASSES (public/GRU.py, GRU_Spatial.py, BPR.py,
+                             PRME.py, GeoIE.py imported unmodified from /root/reference) running on the Theano-API
+                             stand-in oracle/theano_shim.py (make_ref_golden.py) -- same inputs, same initial state.
+The oracle must reproduce both to ~1e-11: a transcription error in the restatement (wrong h in the score, a
+missing L2 term, a wrong update set) shows up as a mismatch with the ref_ files."""
 import glob
 import os
 
@@ -26,10 +32,11 @@ def _check(st, final, tol=1e-12):
 
 
 def test_golden_files_present():
-    assert len(glob.glob(os.path.join(G, "*.npz"))) >= 8
+    assert len(glob.glob(os.path.join(G, "*.npz"))) >= 15
+    assert len(glob.glob(os.path.join(G, "ref_*.npz"))) >= 7
 
 
-@pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape"])
+@pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape", "ref_obo_gru_tiny", "ref_gru_batch2_c1shape"])
 def test_gru(name):
     z, st, final = _load(name)
     P, Q, M, B = z["P"], z["Q"], z["M"], int(z["batch"])
@@ -43,9 +50,12 @@ def test_gru(name):
             l, st = E.gru_family_train_batch(st, P[se], Q[se], M[se], A, L); losses.append(l)   # the OTHER statement
     assert np.allclose(losses, z["losses"], rtol=1e-11)
     _check(st, final)
+    if "l2" in z.files:         # model.l2.eval() of the reference class (GRU.py:305-309)
+        assert abs(OM.l2_value(st, ["lt", "ui", "wh", "bi"], L) - float(z["l2"])) < 1e-11 * float(z["l2"])
 
 
-@pytest.mark.parametrize("name", ["obo_spatial_tiny", "obo_spatial_d20_D200", "spatial_batch4"])
+@pytest.mark.parametrize("name", ["obo_spatial_tiny", "obo_spatial_d20_D200", "spatial_batch4",
+                                  "ref_obo_spatial_tiny", "ref_obo_spatial_d20_D200"])
 def test_spatial(name):
     z, st, final = _load(name)
     P, Q, M, DP, DQ, B = z["P"], z["Q"], z["M"], z["DP"], z["DQ"], int(z["batch"])
@@ -61,20 +71,27 @@ def test_spatial(name):
             outs.append([los, sur, upq, w[0], w[1]])
     assert np.allclose(outs, z["outs"], rtol=1e-10)
     _check(st, final, 1e-11)
+    st_p = dict(st); st_p["trained_items"] = st["lt"]; st_p["trained_dists"] = st["di"]
+    hts, sts = OM.gru_predict(st_p, P, M, DP)          # GRU_Spatial.py:231-288
+    assert np.allclose(hts, z["hts"], rtol=1e-10, atol=1e-13) and np.allclose(sts, z["sts"], rtol=1e-10, atol=1e-15)
+    if "l2" in z.files:         # GRU_Spatial.py:83-88
+        names = ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"]
+        assert abs(OM.l2_value(st, names, L) - float(z["l2"])) < 1e-11 * float(z["l2"])
 
 
-def test_bpr_prme_geoie():
-    z, st, final = _load("obo_bpr_tiny")
+@pytest.mark.parametrize("pre", ["", "ref_"])
+def test_bpr_prme_geoie(pre):
+    z, st, final = _load(pre + "obo_bpr_tiny")
     losses = []
     for (u, p, q) in z["calls"]:
         l, st = OM.obo_bpr_train(st, int(u), [int(p), int(q)], A, L); losses.append(l)
     assert np.allclose(losses, z["losses"], rtol=1e-12); _check(st, final)
-    z, st, final = _load("obo_prme_tiny")
+    z, st, final = _load(pre + "obo_prme_tiny")
     losses = []
     for (u, p, q, pr, ds_, g) in z["calls"]:
         l, st = OM.obo_prme_train(st, int(u), [int(p), int(q), int(pr)], float(ds_), int(g), A, L, 360, 0.2); losses.append(l)
     assert np.allclose(losses, z["losses"], rtol=1e-12); _check(st, final)
-    z, st, final = _load("geoie_tiny")
+    z, st, final = _load(pre + "geoie_tiny")
     losses = []
     for k, u in enumerate(z["order"]):
         l, st = OM.geoie_train(st, int(u), z["P"][u], z["Q"][u], z["dpos%d" % k], z["dneg%d" % k], z["msk%d" % k], A, L)

@@ -1,5 +1,7 @@
 """The CUDA path against the committed golden vectors (tests/golden/*.npz): per-call losses and the
-final parameter state after a short trajectory, 1e-4 relative (fp32 device arithmetic, float64 goldens)."""
+final parameter state after a short trajectory, 1e-4 relative (fp32 device arithmetic, float64 goldens).
+`ref_*` cases were written by the reference's own model classes (tests/golden/make_ref_golden.py), the others
+by the oracle."""
 import os
 
 import numpy as np
@@ -24,7 +26,7 @@ def _test_side(n_user, n_item):
     return [tes, [[0]] * n_user, tes]
 
 
-@pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape"])
+@pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape", "ref_obo_gru_tiny", "ref_gru_batch2_c1shape"])
 def test_gru_golden(engine, name):
     from poi_b200.public.GRU import Gru, OboGru
     z, init, final = _load(name)
@@ -39,9 +41,12 @@ def test_gru_golden(engine, name):
     assert_close(losses, z["losses"], RTOL, "losses")
     for k in ("lt", "ui", "wh", "bi"):
         assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
+    if "l2" in z.files:
+        assert_close(m.l2.eval(), float(z["l2"]), RTOL, "l2")
 
 
-@pytest.mark.parametrize("name", ["obo_spatial_tiny", "obo_spatial_d20_D200", "spatial_batch4"])
+@pytest.mark.parametrize("name", ["obo_spatial_tiny", "obo_spatial_d20_D200", "spatial_batch4",
+                                  "ref_obo_spatial_tiny", "ref_obo_spatial_d20_D200"])
 def test_spatial_golden(engine, name):
     from poi_b200.public.GRU_Spatial import OboSpatialGru, SpatialGru
     z, init, final = _load(name)
@@ -62,13 +67,16 @@ def test_spatial_golden(engine, name):
     m.update_trained_items(); m.update_trained_dists()
     hts, sts = m.predict(np.arange(n_user, dtype=np.int32))
     assert_close(hts, z["hts"], RTOL, "hts"); assert_close(sts, z["sts"], RTOL, "sts")
+    if "l2" in z.files:
+        assert_close(m.l2.eval(), float(z["l2"]), RTOL, "l2")
 
 
-def test_mf_geoie_golden(engine):
+@pytest.mark.parametrize("pre", ["", "ref_"])
+def test_mf_geoie_golden(engine, pre):
     from poi_b200.public.BPR import OboBpr
     from poi_b200.public.GeoIE import GeoIE
     from poi_b200.public.PRME import OboPrme
-    z, init, final = _load("obo_bpr_tiny")
+    z, init, final = _load(pre + "obo_bpr_tiny")
     n_user, n_item, d = init["ux"].shape[0], int(z["n_item"]), init["ux"].shape[1]
     t = _test_side(n_user, n_item)
     m = OboBpr([t[0], t[1], t[2]], t, [A, L], n_user, n_item, d, d, init=init)
@@ -76,7 +84,7 @@ def test_mf_geoie_golden(engine):
     assert_close(m.train_sequence(c[:, 0], c[:, 1], c[:, 2]), z["losses"], RTOL, "bpr losses")
     for k in ("ux", "lt"):
         assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
-    z, init, final = _load("obo_prme_tiny")
+    z, init, final = _load(pre + "obo_prme_tiny")
     n_user, n_item, d = init["du"].shape[0], int(z["n_item"]), init["du"].shape[1]
     t = _test_side(n_user, n_item)
     m = OboPrme([t[0], t[1], [[0.0]] * n_user, t[1], t[2]], [t[0], t[1], [[0.0]] * n_user, t[1], t[2]], [A, L], 360, 0.2,
@@ -85,7 +93,7 @@ def test_mf_geoie_golden(engine):
     assert_close(m.train_sequence(c[:, 0], c[:, 1], c[:, 2], c[:, 3], c[:, 4], c[:, 5]), z["losses"], RTOL, "prme losses")
     for k in ("du", "dp", "ds"):
         assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
-    z, init, final = _load("geoie_tiny")
+    z, init, final = _load(pre + "geoie_tiny")
     P, Q, M = z["P"], z["Q"], z["M"]
     n_user, n_item, H = P.shape[0], init["g"].shape[0] - 1, init["g"].shape[1]
     m = GeoIE([P, Q, np.ones_like(P), M], [[[n_item]] * n_user] * 2, [A, L], n_user, n_item, H, H, None, init=init)
