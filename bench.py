@@ -161,6 +161,48 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+def hbm_microbench(eng, dev, peaks, rows=1000001, d=256, n=1 << 20, reps=10):
+    """Stand-alone embedding gather and sparse-SGD scatter on a table larger than L2 (C4 shape: 1M x 256 fp32 =
+    1.02 GB), uniform random rows -- the "embedding gather HBM GB/s vs roofline" half of BASELINE.json's metric.
+    Timed per launch with CUDA events on the engine stream (the engine's own launch profiler).  Algorithmic bytes
+    (SURVEY.md 8d): gather = n*d*4 read + the same written + indices; scatter = each touched table row read and
+    written once + one gradient row per occurrence + indices."""
+    import torch
+    g = torch.Generator(device=dev); g.manual_seed(123)
+    table = torch.empty((rows, d), dtype=torch.float32, device=dev).uniform_(-0.5, 0.5, generator=g)
+    idx = torch.randint(0, rows - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    res = {}
+    for name in ("gather", "scatter_sgd"):
+        def run():
+            if name == "gather":
+                eng.gather_rows(table, idx, out)
+            else:
+                eng.scatter_sgd(table, idx, out, ALPHA * 1e-3, LAM)
+        for _ in range(3):
+            run()
+        eng.kprof_reset(); eng.kprof_enable(True)
+        for _ in range(reps):
+            run()
+        prof = eng.kprof_get(); eng.kprof_enable(False)
+        if name == "gather":
+            ms = prof["gather"]["ms"] / reps
+            by = 2.0 * n * d * 4 + 4.0 * n
+            parts = {"gather": ms}
+        else:
+            n_unique = int(torch.unique(idx).numel())
+            by = 2.0 * n_unique * d * 4 + 1.0 * n * d * 4 + 4.0 * n
+            parts = {k: v["ms"] / reps for k, v in prof.items() if v["ms"] > 0}
+            ms = sum(parts.values())
+        gbs = by / (ms * 1e-3) / 1e9
+        res[name] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                     "ms": ms, "algorithmic_bytes": by, "kernel_ms": {k: round(v, 4) for k, v in parts.items()},
+                     "workload": "table %d x %d fp32 (%.2f GB), %d uniform random rows" % (rows, d, rows * d * 4 / 1e9, n)}
+    del table, out, idx
+    torch.cuda.empty_cache()
+    return res
+
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
@@ -198,6 +240,7 @@ def run_ours(args):
     eng = model.engine
     eng.set_gemm_mode(args.gemm_mode)
     eng.set_fused_recurrence(bool(args.fused))
+    eng.set_fused_cluster(args.fused_cluster)
     U_loc = len(mine)
     B = min(args.batch, U_loc)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -342,6 +385,8 @@ def run_ours(args):
         obo = {"value": checkins_of(lens_loc[:n_obo]) / dt, "unit": UNIT, "ms_per_user_call": dt / n_obo * 1e3,
                "note": "B=1 calls through the Python class (wall clock incl. host overhead), reference semantics"}
 
+    micro = hbm_microbench(eng, dev, peaks) if (world == 1 and not args.no_micro) else None
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cb = min(args.cpu_batch, U)
@@ -359,14 +404,14 @@ def run_ours(args):
                    "users_per_step_per_gpu": B, "check_ins_per_step": done_all / K,
                    "semantics": "mini-batch extension (SURVEY 3.6); B=1 is the reference's one-by-one mode",
                    "gemm": {0: "fp32 FMA", 1: "tcgen05 3xTF32 (fp32-faithful), fp32 accumulate in TMEM", 2: "tcgen05 1xTF32"}[args.gemm_mode],
-                   "gemm_mode": args.gemm_mode, "fused_recurrence": bool(args.fused) and args.gemm_mode != 0, "l2": "flushed between timed steps (256 MB write)",
+                   "gemm_mode": args.gemm_mode, "fused_recurrence": bool(args.fused) and args.gemm_mode != 0, "fused_cluster": args.fused_cluster or "auto", "l2": "flushed between timed steps (256 MB write)",
                    "parallelism": "1 GPU" if world == 1 else
                    "dp%d: users sharded, item table row-sharded (row %% %d) with NCCL all-to-all of rows / row-gradients, "
                    "dense gradients all-reduced" % (world, world)},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 40,
                 "ms_per_step": ms_e2e_max / K},
         "gpu_launches": launches_all,
-        "roofline": roof, "hbm_kernels": hbm_kernels, "kernel_ms_per_step": breakdown,
+        "roofline": roof, "hbm_kernels": hbm_kernels, "hbm_microbench": micro, "kernel_ms_per_step": breakdown,
         "cpu_baseline": cpu, "obo_mode": obo, "clocks": clocks, "final_loss": float(losses[-1]),
     }
     print(json.dumps(line), flush=True)
@@ -386,8 +431,11 @@ def main():
     ap.add_argument("--gemm-mode", type=int, default=1,
                     help="0 fp32 FMA, 1 tcgen05 3xTF32 (fp32-faithful, default), 2 tcgen05 1xTF32")
     ap.add_argument("--fused", type=int, default=1, help="1 = persistent fused recurrence kernel (tensor-core modes)")
+    ap.add_argument("--fused-cluster", type=int, default=0,
+                    help="CTAs per 128 users in the fused recurrence kernels: 0 auto (default), 1, 2, 4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-obo", action="store_true")
+    ap.add_argument("--no-micro", action="store_true", help="skip the stand-alone gather / scatter HBM micro-benchmark")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -61,6 +61,9 @@ int         poi_get_gemm_mode(poi_engine* e, int* mode);
 /* tensor-core modes only: 1 (default) = the recurrence runs as one persistent fused kernel per
  * direction, 0 = two GEMM launches per time step (kept for A/B measurements) */
 int         poi_set_fused_recurrence(poi_engine* e, int on);
+/* CTAs per 128 users in the fused recurrence kernels (thread-block cluster splitting the gate columns, next
+ * operand exchanged through distributed shared memory): 0 = auto (default), 1, 2 or 4. */
+int         poi_set_fused_cluster(poi_engine* e, int cl);
 /* tensor-core modes only: 1 (default) = the weight-gradient GEMMs read the activation matrices as they lie in
  * memory (MN-major tcgen05 operands; bias gradients fused into the same pass), 0 = transposed copies + K-major
  * operands + a separate column-sum pass (kept for A/B measurements) */

@@ -17,6 +17,19 @@
 //
 // Per step the chain is GEMM1 -> epilogue1 -> GEMM2 -> epilogue2; everything else is prefetch.
 // H must be a multiple of 32, <= 128.
+//
+// Cluster split (CL = 1, 2 or 4 CTAs per 128 users): with B / 128 CTAs most SMs idle (B = 4096 -> 32 of 148) and
+// the per-step chain is bound by the epilogue passes of one SM.  A thread-block cluster of CL CTAs shares the
+// 128 users; CTA `cr` owns the gate columns [cr*H/CL, (cr+1)*H/CL): it multiplies against its rows of Wh only
+// (N = H/CL per gate) and runs the gate math for its columns.  Its slice of the next A operand (r*h, h_t) is a
+// whole number of 32-column k-blocks, i.e. one CONTIGUOUS 16 KB-per-k-block piece of the UMMA-layout A tile: the
+// epilogue warps write it into the CTA's own tile (st.shared, as in the single-CTA case) and the MMA thread then
+// pushes it into the same place of every peer's tile with one bulk async copy per peer and hi/lo half
+// (cp.async.bulk shared::cta -> shared::cluster, distributed shared memory), completing bytes on the PEER's
+// a_ready transaction barrier -- no per-thread remote stores (measured: 32-lane st.shared::cluster with a 128 B
+// lane stride costs ~370 cycles per instruction).  The accumulator-ready barriers are armed by tcgen05.commit
+// multicast to the whole cluster (count CL): a slice is overwritten, and sent, only when every CTA's MMA has
+// finished reading the previous operand.
 #pragma once
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -62,6 +75,70 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 // 64-byte rows (16 floats): XOR the 16-byte chunk index with bits 1..2 of the row -> lane=row accesses
 // and 4-lanes-per-row accesses are both bank-conflict free
 __device__ __forceinline__ uint32_t sw64(int row, int c) { return row * 64 + ((c ^ ((row >> 1) & 3)) << 4); }
+
+
+// ---- thread-block-cluster primitives (distributed shared memory) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// accumulator-ready signal to the same barrier of every CTA in the cluster
+template <int CL>
+__device__ __forceinline__ void umma_commit_cl(uint64_t* bar) {
+    if (CL == 1) umma_commit(bar);
+    else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                      ::"r"(smem_u32(bar)), "h"((uint16_t)((1u << CL) - 1)) : "memory");
+}
+// this CTA's k-blocks of the A tile (hi, and lo for 3xTF32) -> the same offsets in every peer CTA's shared memory;
+// bytes complete on the peer's a_ready[this rank] barrier.  One thread.
+template <bool SPLIT3, int CL>
+__device__ __forceinline__ void send_slice(uint32_t a_hi, uint32_t a_lo, uint32_t slice_off, uint32_t slice_bytes,
+                                           uint64_t* a_ready, int cr) {
+    const uint32_t bar = smem_u32(&a_ready[cr]);
+#pragma unroll
+    for (int i = 1; i < CL; ++i) {
+        const uint32_t r = (uint32_t)((cr + i) % CL);
+        const uint32_t rbar = mapa_u32(bar, r);
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(mapa_u32(a_hi + slice_off, r)), "r"(a_hi + slice_off), "r"(slice_bytes), "r"(rbar) : "memory");
+        if (SPLIT3)
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(mapa_u32(a_lo + slice_off, r)), "r"(a_lo + slice_off), "r"(slice_bytes), "r"(rbar) : "memory");
+    }
+}
+// MMA thread, once per operand hand-over: the local slice is staged (s_done); arm one transaction barrier per peer
+// and push the local slice to the peers.  The GEMM that follows starts on the LOCAL k-blocks at once and waits for
+// each peer's k-blocks (a_ready[owner]) only when it reaches them, so the transfer overlaps the MMAs.
+template <bool SPLIT3, int CL>
+__device__ __forceinline__ void begin_exchange(uint64_t* s_done, uint32_t& ps, uint64_t* a_ready,
+                                               uint32_t a_hi, uint32_t a_lo, uint32_t slice_off, uint32_t slice_bytes, int cr,
+                                               bool exchange) {
+    mbar_wait(s_done, ps & 1); ++ps;
+    if (CL > 1 && exchange) {
+        const uint32_t expect = slice_bytes * (SPLIT3 ? 2u : 1u);
+#pragma unroll
+        for (int o = 0; o < CL; ++o)
+            if (o != cr)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&a_ready[o])), "r"(expect) : "memory");
+        send_slice<SPLIT3, CL>(a_hi, a_lo, slice_off, slice_bytes, a_ready, cr);
+    }
+    tc_fence_after();
+}
 
 template <bool SPLIT3>
 __device__ __forceinline__ void a_store16(uint32_t a_hi, uint32_t a_lo, int row, int col, const float (&v)[16]) {
@@ -122,15 +199,21 @@ __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint3
 // k-block: H rows x 128 B, 128B-swizzled, hi then lo for 3xTF32), so that inside the recurrence a tile is one
 // bulk async copy (TMA, cp.async.bulk) issued by a single thread instead of 64 threads converting it
 template <bool SPLIT3>
-__global__ void k_stage_wh(const float* __restrict__ wh, int H, uint8_t* __restrict__ image) {
-    const int KB = H >> 5;
+__global__ void k_stage_wh(const float* __restrict__ wh, int H, int CL, uint8_t* __restrict__ image) {
+    // image = [cluster rank][tile t] of Hc = H / CL rows (the rows of Wh the rank owns) x 128 B, tiles in the order
+    // the rank's MMA thread consumes them: GEMM1 k-blocks in arrival order (owner rank, rank-1, ...), z and r tile
+    // of each; then GEMM2 (c gate) over the same k-block order
+    const int KB = H >> 5, Hc = H / CL, KBc = KB / CL;
     const int64_t n = (int64_t)3 * KB * H * 8;
-    const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int t12 = (int)(idx / (H * 8)), rem = (int)(idx % (H * 8)), row = rem >> 3, c = rem & 7;
-        const int gate = t12 / KB, kb = t12 % KB;
-        float4 v = *reinterpret_cast<const float4*>(wh + ((size_t)gate * H + row) * H + kb * 32 + c * 4);
-        uint8_t* dst = image + (size_t)t12 * w_stage + row * 128 + ((c ^ (row & 7)) << 4);
+        const int c = (int)(idx & 7), rl = (int)((idx >> 3) % Hc);
+        const int t = (int)((idx / (8 * Hc)) % (3 * KB)), rank = (int)(idx / ((int64_t)8 * Hc * 3 * KB));
+        int gate, pos;
+        if (t < 2 * KB) { pos = t >> 1; gate = t & 1; } else { pos = t - 2 * KB; gate = 2; }
+        const int owner = (rank - pos / KBc + CL) % CL, kb = owner * KBc + pos % KBc;
+        float4 v = *reinterpret_cast<const float4*>(wh + ((size_t)gate * H + rank * Hc + rl) * H + kb * 32 + c * 4);
+        uint8_t* dst = image + ((size_t)rank * 3 * KB + t) * w_stage + rl * 128 + ((c ^ (rl & 7)) << 4);
         if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + w_tile) = lo; }
         else *reinterpret_cast<float4*>(dst) = v;
     }
@@ -141,23 +224,27 @@ __global__ void k_stage_wh(const float* __restrict__ wh, int H, uint8_t* __restr
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
-template <bool SPLIT3>
+template <bool SPLIT3, int CL>
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, float* __restrict__ Hs, float* __restrict__ Z,
                 float* __restrict__ R, float* __restrict__ C, int B, int T, int H) {
-    constexpr int WST = 2;
+    constexpr int WST = CL == 1 ? 2 : (CL == 2 ? 3 : 4);
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[2][AX_STAGES], ax_empty[2][AX_STAGES], a_ready, d1_full, d2_full;
+    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[2][AX_STAGES], ax_empty[2][AX_STAGES], s_done, a_ready[CL], d1_full, d2_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KB = H >> 5, NCH = H >> 4, HCH = NCH >> 1;
+    const int cr = CL == 1 ? 0 : (int)cluster_ctarank();      // this CTA's slice of the gate columns
+    const int Hc = H / CL;                                      // columns of each gate owned by this CTA
+    const int KB = H >> 5, NCH = Hc >> 4, HCH = NCH >> 1;
+    const int col0 = cr * Hc;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_hi = sbase, a_lo = sbase + KB * A_KB_BYTES;
-    const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
     const uint32_t ax_base = w_base + WST * w_stage;           // [half][stage] tiles of AX_TILE bytes
-    const int m0 = blockIdx.x * FM;
-    uint32_t ncols = 32; while (ncols < (uint32_t)(3 * H)) ncols <<= 1;
+    const int m0 = (blockIdx.x / CL) * FM;
+    const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
+    uint32_t ncols = 32; while (ncols < (uint32_t)(3 * Hc)) ncols <<= 1;
 
     if (tid == 0) {
 #pragma unroll
@@ -166,32 +253,35 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&ax_full[h][s], 32); mbar_init(&ax_empty[h][s], 128); }
-        mbar_init(&a_ready, 256); mbar_init(&d1_full, 1); mbar_init(&d2_full, 1);
+        mbar_init(&s_done, 256); mbar_init(&d1_full, CL);
+#pragma unroll
+        for (int o = 0; o < CL; ++o) mbar_init(&a_ready[o], 1);
+        mbar_init(&d2_full, CL);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                             // every CTA's barriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = make_idesc_tf32(FM, H);
+    const uint32_t idesc = make_idesc_tf32(FM, Hc);
 
     if (warp < 8) {
         // ================================ epilogue (8 warps) ================================
-        // warp w: TMEM lane quadrant q = w & 3 (rows 32q..32q+31), column half hf = w >> 2
+        // warp w: TMEM lane quadrant q = w & 3 (rows 32q..32q+31), column half hf = w >> 2 of this CTA's columns
         const int q = warp & 3, hf = warp >> 2;
         const int row = q * 32 + lane;                         // TMEM lane == row of the tile
         const bool ok = m0 + row < B;
         const uint32_t tl = (uint32_t)(q * 32) << 16;
         const int rows_valid = min(32, B - (m0 + q * 32));
         const int k_beg = hf * HCH, k_end = k_beg + HCH;
-        if (hf == 0 || true) {   // h_{-1} = 0 -> this warp's half of the A tile
+        {   // h_{-1} = 0: the WHOLE local A tile (every CTA zeroes its own copy, nothing to exchange)
             float zero[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) zero[i] = 0.f;
-            for (int k = k_beg; k < k_end; ++k) a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, zero);
-            fence_async_smem();
-            mbar_arrive(&a_ready);
+            for (int k = hf * (H >> 5); k < (hf + 1) * (H >> 5); ++k) a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, zero);
+            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);
         }
         int64_t axi = 0;                                       // position in this half's AX ring
         // wait for the next AX tile, read this thread's row, return this warp's 2 KB slice of the tile (free to
@@ -214,16 +304,16 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
         for (int j = 0; j < T; ++j) {
             const size_t wrow = (size_t)j * B + m0 + q * 32;   // first global row of this warp's quadrant at step j
             // ---- epilogue 1: z, r, r*h ; stash z and (1-z)*h ----
-            mbar_wait(&d1_full, j & 1);
+            if (CL == 1) mbar_wait(&d1_full, j & 1); else mbar_wait_cl(&d1_full, j & 1);   // EVERY CTA's GEMM1 has read its A tile
             tc_fence_after();
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 4 : 8);
             for (int k = k_beg; k < k_end; ++k) {
-                const int c0 = 16 * k;
+                const int lc0 = 16 * k, c0 = col0 + lc0;       // local (TMEM) / global (A tile, memory) column
                 float a[16], b[16], hv[16], dz[16], dr[16];
                 uint32_t sl_z, sl_r; uint64_t *rel_z, *rel_r;
                 ax_take(a, sl_z, rel_z); ax_take(b, sl_r, rel_r);
-                tmem_ld16(tmem + tl + (uint32_t)c0, dz);
-                tmem_ld16(tmem + tl + (uint32_t)(H + c0), dr);
+                tmem_ld16(tmem + tl + (uint32_t)lc0, dz);
+                tmem_ld16(tmem + tl + (uint32_t)(Hc + lc0), dr);
                 a_load16<SPLIT3>(a_hi, a_lo, row, c0, hv);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -234,29 +324,27 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                     a[i] = rr * h_;                 // r*h -> next A operand
                     b[i] = (1.f - zz) * h_;         // (1-z)*h_prev, used by epilogue 2
                 }
-                tmem_st16(tmem + tl + (uint32_t)c0, dz);              // stash z
-                tmem_st16(tmem + tl + (uint32_t)(H + c0), b);         // stash (1-z)*h_prev
+                tmem_st16(tmem + tl + (uint32_t)lc0, dz);             // stash z
+                tmem_st16(tmem + tl + (uint32_t)(Hc + lc0), b);       // stash (1-z)*h_prev
                 a_store16<SPLIT3>(a_hi, a_lo, row, c0, a);
                 warp_store_chunk(sl_z, lane, dz, Z + wrow * H + c0, H, rows_valid);
                 warp_store_chunk(sl_r, lane, dr, R + wrow * H + c0, H, rows_valid);
                 mbar_arrive(rel_z); mbar_arrive(rel_r);
             }
-            fence_async_smem();
-            tc_fence_before();
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 5 : 9);
-            mbar_arrive(&a_ready);                 // this warp's part of the r*h tile is in place
+            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the r*h tile is in place everywhere
             // ---- epilogue 2: c, h_t ----
-            mbar_wait(&d2_full, j & 1);
+            if (CL == 1) mbar_wait(&d2_full, j & 1); else mbar_wait_cl(&d2_full, j & 1);
             tc_fence_after();
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 6 : 10);
             for (int k = k_beg; k < k_end; ++k) {
-                const int c0 = 16 * k;
+                const int lc0 = 16 * k, c0 = col0 + lc0;
                 float a[16], dc[16], zz[16], u[16];
                 uint32_t sl; uint64_t* rel;
                 ax_take(a, sl, rel);
-                tmem_ld16(tmem + tl + (uint32_t)(2 * H + c0), dc);
-                tmem_ld16(tmem + tl + (uint32_t)c0, zz);
-                tmem_ld16(tmem + tl + (uint32_t)(H + c0), u);
+                tmem_ld16(tmem + tl + (uint32_t)(2 * Hc + lc0), dc);
+                tmem_ld16(tmem + tl + (uint32_t)lc0, zz);
+                tmem_ld16(tmem + tl + (uint32_t)(Hc + lc0), u);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float cc = tanh_fast(dc[i] + a[i]);
@@ -268,10 +356,8 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 warp_store_chunk(sl, lane, u, Hs + (wrow + B) * H + c0, H, rows_valid);
                 mbar_arrive(rel);
             }
-            fence_async_smem();
-            tc_fence_before();
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 7 : 11);
-            mbar_arrive(&a_ready);                 // this warp's part of the h_t tile is in place
+            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the h_t tile is in place everywhere
         }
     } else if (warp < 10) {
         // ================================ AX producers (one warp per column half, cp.async) ================================
@@ -284,7 +370,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             const int j = (int)(ai / per_step), ti = (int)(ai % per_step);
             const int gate = ti < 2 * HCH ? (ti & 1) : 2;
             const int k = hf * HCH + (ti < 2 * HCH ? (ti >> 1) : ti - 2 * HCH);
-            const float* src = AX + ((size_t)j * B + m0) * 3 * H + gate * H + 16 * k;
+            const float* src = AX + ((size_t)j * B + m0) * 3 * H + gate * H + col0 + 16 * k;
             const uint32_t dst = ax_base + (hf * AX_STAGES + s) * AX_TILE;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -298,39 +384,44 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
     } else if (warp == 10) {
         if (lane == 0) {
             // ================================ MMA issuer ================================
-            int64_t ws = 0; uint32_t pa = 0;
-            for (int j = 0; j < T; ++j) {
-                mbar_wait(&a_ready, pa & 1); ++pa;     // h_{j-1} tile staged (and the stashes of step j-1 consumed)
-                tc_fence_after();
-                FTR(0, j, 0);
-                for (int half = 0; half < 2; ++half) {
-                    for (int kb = 0; kb < KB; ++kb, ++ws) {
-                        const int s = (int)(ws % WST);
-                        const long long tw0 = FTR_NOW();
-                        mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
-                        FTR_ADD(0, j, 13, FTR_NOW() - tw0);
-                        tc_fence_after();
-                        const uint32_t sW = w_base + s * w_stage;
-                        mma_kblock<SPLIT3>(tmem + half * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
-                        umma_commit(&w_empty[s]);
+            int64_t ws = 0; uint32_t pa = 0, ps = 0;
+            const int KBc = Hc >> 5;                            // k-blocks per owner
+            const uint32_t slice_off = (uint32_t)cr * KBc * A_KB_BYTES, slice_bytes = (uint32_t)KBc * A_KB_BYTES;
+            // one GEMM over K = H in ARRIVAL order: own k-blocks first, then owner cr-1, cr-2, ... (the order the
+            // peers send in); `tiles_per_kb` W tiles per k-block, accumulators dcol0 + t * Hc.  The Wh image of this
+            // rank is staged in exactly this order (k_stage_wh).
+            auto gemm = [&](uint32_t dcol0, int tiles_per_kb, bool exchanged, int j, int slot) {
+                for (int i = 0; i < CL; ++i) {
+                    const int o = (cr - i + CL) % CL;
+                    if (CL > 1 && i > 0 && exchanged) { mbar_wait_cl(&a_ready[o], pa & 1); tc_fence_after(); }
+                    for (int kbl = 0; kbl < KBc; ++kbl) {
+                        const int kb = o * KBc + kbl;
+                        for (int t = 0; t < tiles_per_kb; ++t, ++ws) {
+                            const int s = (int)(ws % WST);
+                            const long long tw0 = FTR_NOW();
+                            mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                            FTR_ADD(0, j, slot, FTR_NOW() - tw0);
+                            tc_fence_after();
+                            const uint32_t sW = w_base + s * w_stage;
+                            mma_kblock<SPLIT3>(tmem + dcol0 + t * Hc, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc,
+                                               i == 0 && kbl == 0);
+                            umma_commit(&w_empty[s]);
+                        }
                     }
                 }
-                umma_commit(&d1_full);
+                if (CL > 1 && exchanged) ++pa;
+            };
+            for (int j = 0; j < T; ++j) {
+                // h_{j-1}: own slice staged (j = 0: the zero tile, nothing to exchange)
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, a_lo, slice_off, slice_bytes, cr, j > 0);
+                FTR(0, j, 0);
+                gemm(0u, 2, j > 0, j, 13);                      // D1z | D1r
+                umma_commit_cl<CL>(&d1_full);
                 FTR(0, j, 1);
-                mbar_wait(&a_ready, pa & 1); ++pa;     // r*h tile staged
-                tc_fence_after();
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, a_lo, slice_off, slice_bytes, cr, true);   // r*h
                 FTR(0, j, 2);
-                for (int kb = 0; kb < KB; ++kb, ++ws) {
-                    const int s = (int)(ws % WST);
-                    const long long tw0 = FTR_NOW();
-                    mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
-                    FTR_ADD(0, j, 14, FTR_NOW() - tw0);
-                    tc_fence_after();
-                    const uint32_t sW = w_base + s * w_stage;
-                    mma_kblock<SPLIT3>(tmem + 2 * H, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, kb == 0);
-                    umma_commit(&w_empty[s]);
-                }
-                umma_commit(&d2_full);
+                gemm((uint32_t)(2 * Hc), 1, true, j, 14);       // D2
+                umma_commit_cl<CL>(&d2_full);
                 FTR(0, j, 3);
             }
         }
@@ -343,11 +434,12 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             const uint32_t bar = smem_u32(&w_full[s]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_stage) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(w_base + s * w_stage), "l"(wimg + (size_t)(ws % (3 * KB)) * w_stage), "r"(w_stage), "r"(bar) : "memory");
+                         ::"r"(w_base + s * w_stage), "l"(wimg_c + (size_t)(ws % (3 * KB)) * w_stage), "r"(w_stage), "r"(bar) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();         // no CTA leaves while a peer may still write into its A tile / barriers
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
@@ -366,41 +458,49 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
 // an image staged once per call.
 // ---------------------------------------------------------------------------------------------
 template <bool SPLIT3>
-__global__ void k_stage_wh_bwd(const float* __restrict__ wh, int H, uint8_t* __restrict__ image) {
-    const int KB = H >> 5;
+__global__ void k_stage_wh_bwd(const float* __restrict__ wh, int H, int CL, uint8_t* __restrict__ image) {
+    // image = [cluster rank][g * KB + pos] tiles of Hc = H / CL rows (the OUTPUT columns n the rank owns) x 128 B;
+    // g: Wh[2] (c), Wh[0] (z), Wh[1] (r); pos: k-blocks in arrival order (owner rank, rank-1, ...)
+    const int KB = H >> 5, Hc = H / CL, KBc = KB / CL;
     const int64_t n = (int64_t)3 * KB * H * 8;
-    const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int t12 = (int)(idx / (H * 8)), rem = (int)(idx % (H * 8)), row = rem >> 3, c = rem & 7;
-        const int g = t12 / KB, kb = t12 % KB;
-        const int gsel = g == 0 ? 2 : g - 1;             // tile order: Wh[2] (c), Wh[0] (z), Wh[1] (r)
-        // B operand row n, k-major: element (n, k) = Wh[gsel][k][n]
-        const float* src = wh + ((size_t)gsel * H + kb * 32 + c * 4) * H + row;
+        const int c = (int)(idx & 7), rl = (int)((idx >> 3) % Hc);
+        const int t = (int)((idx / (8 * Hc)) % (3 * KB)), rank = (int)(idx / ((int64_t)8 * Hc * 3 * KB));
+        const int g = t / KB, pos = t % KB;
+        const int gsel = g == 0 ? 2 : g - 1;
+        const int owner = (rank - pos / KBc + CL) % CL, kb = owner * KBc + pos % KBc;
+        // B operand row n = rank*Hc + rl, k-major: element (n, k) = Wh[gsel][k][n]
+        const float* src = wh + ((size_t)gsel * H + kb * 32 + c * 4) * H + rank * Hc + rl;
         float4 v = make_float4(src[0], src[H], src[2 * (size_t)H], src[3 * (size_t)H]);
-        uint8_t* dst = image + (size_t)t12 * w_stage + row * 128 + ((c ^ (row & 7)) << 4);
+        uint8_t* dst = image + ((size_t)rank * 3 * KB + t) * w_stage + rl * 128 + ((c ^ (rl & 7)) << 4);
         if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + w_tile) = lo; }
         else *reinterpret_cast<float4*>(dst) = v;
     }
 }
 
-template <bool SPLIT3>
+template <bool SPLIT3, int CL>
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, const float* __restrict__ R,
                 const float* __restrict__ C, const float* __restrict__ Hs, const uint8_t* __restrict__ wimg,
                 float* __restrict__ DA, int B, int T, int H) {
-    constexpr int WST = 2;
+    constexpr int WST = CL == 1 ? 2 : (CL == 2 ? 3 : 4);
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[WST], w_empty[WST], in_full[2][AX_STAGES], in_empty[2][AX_STAGES], a_ready, dm_full, dh1_done, ddh_full;
+    __shared__ uint64_t w_full[WST], w_empty[WST], in_full[2][AX_STAGES], in_empty[2][AX_STAGES], s_done, a_ready[CL], dm_full, dh1_done, ddh_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KB = H >> 5, NCH = H >> 4, HCH = NCH >> 1;
+    const int cr = CL == 1 ? 0 : (int)cluster_ctarank();
+    const int Hc = H / CL;
+    const int KB = H >> 5, NCH = Hc >> 4, HCH = NCH >> 1;
+    const int col0 = cr * Hc;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_hi = sbase, a_lo = sbase + KB * A_KB_BYTES;
-    const uint32_t w_tile = H * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
+    const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
     const uint32_t in_base = w_base + WST * w_stage;
-    const int m0 = blockIdx.x * FM;
-    uint32_t ncols = 32; while (ncols < (uint32_t)(4 * H)) ncols <<= 1;
+    const int m0 = (blockIdx.x / CL) * FM;
+    const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
+    uint32_t ncols = 32; while (ncols < (uint32_t)(4 * Hc)) ncols <<= 1;
 
     if (tid == 0) {
 #pragma unroll
@@ -409,16 +509,20 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&in_full[h][s], 32); mbar_init(&in_empty[h][s], 128); }
-        mbar_init(&a_ready, 256); mbar_init(&dm_full, 1); mbar_init(&dh1_done, 1); mbar_init(&ddh_full, 1);
+        mbar_init(&s_done, 256); mbar_init(&dm_full, CL);
+#pragma unroll
+        for (int o = 0; o < CL; ++o) mbar_init(&a_ready[o], 1);
+        mbar_init(&dh1_done, CL); mbar_init(&ddh_full, CL);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = make_idesc_tf32(FM, H);
-    const uint32_t T_M = 0, T_DH = (uint32_t)H, T_KEEP = (uint32_t)(2 * H), T_DAZ = (uint32_t)(3 * H);
+    const uint32_t idesc = make_idesc_tf32(FM, Hc);
+    const uint32_t T_M = 0, T_DH = (uint32_t)Hc, T_KEEP = (uint32_t)(2 * Hc), T_DAZ = (uint32_t)(3 * Hc);
 
     if (warp < 8) {
         // ================================ epilogue (8 warps) ================================
@@ -428,6 +532,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
         const uint32_t tl = (uint32_t)(q * 32) << 16;
         const int rows_valid = min(32, B - (m0 + q * 32));
         const int k_beg = hf * HCH, k_end = k_beg + HCH;
+        auto wait_acc = [&](uint64_t* bar, uint32_t par) { if (CL == 1) mbar_wait(bar, par); else mbar_wait_cl(bar, par); };
         int64_t ini = 0;
         auto in_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
             const int s = (int)(ini % AX_STAGES);
@@ -449,10 +554,11 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             const size_t wrow = (size_t)j * B + m0 + q * 32;
             float* DAw = DA + wrow * 3 * H;
             // ---- D + P: dh = keep + dhn (0 for the last step) ; gate derivatives ; A <- da_c ----
-            if (it > 0) { mbar_wait(&ddh_full, (it - 1) & 1); tc_fence_after(); }
+            // (every CTA's GEMM_DH2 of the previous iteration has read its A tile)
+            if (it > 0) { wait_acc(&ddh_full, (it - 1) & 1); tc_fence_after(); }
             if (lane == 0 && warp == 0) FTR(1, it, 6);
             for (int k = k_beg; k < k_end; ++k) {
-                const int c0 = 16 * k;
+                const int lc0 = 16 * k, c0 = col0 + lc0;
                 float dl[16], zz[16], cc[16], hp[16], dh[16], kp[16];
                 uint32_t s0, s1, s2, s3; uint64_t *r0, *r1, *r2, *r3;
                 // the ring has 2 stages: release the first two tiles as soon as they are in registers, keep the
@@ -461,8 +567,8 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 in_take(zz, s1, r1); mbar_arrive(r1);
                 in_take(cc, s2, r2); in_take(hp, s3, r3);
                 if (it > 0) {
-                    tmem_ld16(tmem + tl + T_DH + (uint32_t)c0, dh);
-                    tmem_ld16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
+                    tmem_ld16(tmem + tl + T_DH + (uint32_t)lc0, dh);
+                    tmem_ld16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { dh[i] = 0.f; kp[i] = 0.f; }
@@ -477,66 +583,60 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                     dl[i] = ok ? dac : 0.f;                     // da_c
                     dh[i] = ok ? daz : 0.f;                     // da_z
                 }
-                tmem_st16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
-                tmem_st16(tmem + tl + T_DAZ + (uint32_t)c0, dh);
+                tmem_st16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
+                tmem_st16(tmem + tl + T_DAZ + (uint32_t)lc0, dh);
                 a_store16<SPLIT3>(a_hi, a_lo, row, c0, dl);
                 warp_store_chunk(s2, lane, dh, DAw + c0, 3 * H, rows_valid);            // DA_z
                 warp_store_chunk(s3, lane, dl, DAw + 2 * H + c0, 3 * H, rows_valid);    // DA_c
                 mbar_arrive(r2); mbar_arrive(r3);
             }
-            fence_async_smem();
-            tc_fence_before();
             if (lane == 0 && warp == 0) FTR(1, it, 7);
-            mbar_arrive(&a_ready);                              // A = da_c
-            // ---- M1: A <- da_z (after GEMM_M has read da_c) ----
-            mbar_wait(&dm_full, it & 1);
+            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                      // A = da_c
+            // ---- M1: A <- da_z (after every CTA's GEMM_M has read da_c) ----
+            wait_acc(&dm_full, it & 1);
             tc_fence_after();
             if (lane == 0 && warp == 0) FTR(1, it, 8);
             if (j > 0) {
                 for (int k = k_beg; k < k_end; ++k) {
                     float dz[16];
                     tmem_ld16(tmem + tl + T_DAZ + (uint32_t)(16 * k), dz);
-                    a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, dz);
+                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dz);
                 }
-                fence_async_smem();
-                tc_fence_before();
                 if (lane == 0 && warp == 0) FTR(1, it, 9);
-                mbar_arrive(&a_ready);                          // A = da_z
+                fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_z
             }
             // ---- M2: da_r, keep += m r  (runs while GEMM_DH1 executes) ----
             for (int k = k_beg; k < k_end; ++k) {
-                const int c0 = 16 * k;
+                const int lc0 = 16 * k, c0 = col0 + lc0;
                 float rr[16], hp[16], mm[16], kp[16];
                 uint32_t s0, s1; uint64_t *r0, *r1;
                 in_take(rr, s0, r0); in_take(hp, s1, r1);
-                tmem_ld16(tmem + tl + T_M + (uint32_t)c0, mm);
-                tmem_ld16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
+                tmem_ld16(tmem + tl + T_M + (uint32_t)lc0, mm);
+                tmem_ld16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float m_ = ok ? mm[i] : 0.f, r_ = rr[i];
                     kp[i] = kp[i] + m_ * r_;
                     mm[i] = ok ? m_ * hp[i] * r_ * (1.f - r_) : 0.f;       // da_r
                 }
-                tmem_st16(tmem + tl + T_KEEP + (uint32_t)c0, kp);
-                tmem_st16(tmem + tl + T_M + (uint32_t)c0, mm);              // stash da_r over m
+                tmem_st16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
+                tmem_st16(tmem + tl + T_M + (uint32_t)lc0, mm);             // stash da_r over m
                 warp_store_chunk(s0, lane, mm, DAw + H + c0, 3 * H, rows_valid);        // DA_r
                 mbar_arrive(r0); mbar_arrive(r1);
             }
             if (lane == 0 && warp == 0) FTR(1, it, 10);
-            // ---- M3: A <- da_r (after GEMM_DH1 has read da_z) ----
+            // ---- M3: A <- da_r (after every CTA's GEMM_DH1 has read da_z) ----
             if (j > 0) {
-                mbar_wait(&dh1_done, it & 1);
+                wait_acc(&dh1_done, it & 1);
                 tc_fence_after();
                 if (lane == 0 && warp == 0) FTR(1, it, 11);
                 for (int k = k_beg; k < k_end; ++k) {
                     float dr[16];
                     tmem_ld16(tmem + tl + T_M + (uint32_t)(16 * k), dr);
-                    a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, dr);
+                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dr);
                 }
-                fence_async_smem();
-                tc_fence_before();
                 if (lane == 0 && warp == 0) FTR(1, it, 12);
-                mbar_arrive(&a_ready);                          // A = da_r
+                fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_r
             }
         }
     } else if (warp < 10) {
@@ -552,7 +652,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             if (ti < 4 * HCH) { kind = ti & 3; kk = ti >> 2; }
             else { const int t2 = ti - 4 * HCH; kind = (t2 & 1) ? 3 : 4; kk = t2 >> 1; }
             const float* base = kind == 0 ? DHl : kind == 1 ? Z : kind == 2 ? C : kind == 3 ? Hs : R;
-            const float* src = base + ((size_t)j * B + m0) * H + 16 * (hf * HCH + kk);
+            const float* src = base + ((size_t)j * B + m0) * H + col0 + 16 * (hf * HCH + kk);
             const uint32_t dst = in_base + (hf * AX_STAGES + s) * AX_TILE;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -566,35 +666,41 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
     } else if (warp == 10) {
         if (lane == 0) {
             // ================================ MMA issuer ================================
-            int64_t ws = 0; uint32_t pa = 0;
-            auto gemm = [&](uint32_t dcol, bool fresh) {
-                for (int kb = 0; kb < KB; ++kb, ++ws) {
-                    const int s = (int)(ws % WST);
-                    const long long tw0 = FTR_NOW();
-                    mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
-                    FTR_ADD(1, (int)(ws / (3 * KB)), 14, FTR_NOW() - tw0);
-                    tc_fence_after();
-                    const uint32_t sW = w_base + s * w_stage;
-                    mma_kblock<SPLIT3>(tmem + dcol, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc, fresh && kb == 0);
-                    umma_commit(&w_empty[s]);
+            int64_t ws = 0; uint32_t pa = 0, ps = 0;
+            const int KBc = Hc >> 5;
+            const uint32_t slice_off = (uint32_t)cr * KBc * A_KB_BYTES, slice_bytes = (uint32_t)KBc * A_KB_BYTES;
+            // operand hand-over + one GEMM over K = H in arrival order (own k-blocks, then owner cr-1, cr-2, ...)
+            auto gemm = [&](uint32_t dcol, bool fresh, int it, int slot) {
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, a_lo, slice_off, slice_bytes, cr, true);
+                FTR(1, it, slot);
+                for (int i = 0; i < CL; ++i) {
+                    const int o = (cr - i + CL) % CL;
+                    if (CL > 1 && i > 0) { mbar_wait_cl(&a_ready[o], pa & 1); tc_fence_after(); }
+                    for (int kbl = 0; kbl < KBc; ++kbl, ++ws) {
+                        const int kb = o * KBc + kbl;
+                        const int s = (int)(ws % WST);
+                        const long long tw0 = FTR_NOW();
+                        mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                        FTR_ADD(1, (int)(ws / (3 * KB)), 14, FTR_NOW() - tw0);
+                        tc_fence_after();
+                        const uint32_t sW = w_base + s * w_stage;
+                        mma_kblock<SPLIT3>(tmem + dcol, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc,
+                                           fresh && i == 0 && kbl == 0);
+                        umma_commit(&w_empty[s]);
+                    }
                 }
+                if (CL > 1) ++pa;
             };
             for (int j = T - 1; j >= 0; --j) {
-                mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_c
-                FTR(1, T - 1 - j, 0);
-                gemm(T_M, true);
-                umma_commit(&dm_full);
+                gemm(T_M, true, T - 1 - j, 0);                  // A = da_c
+                umma_commit_cl<CL>(&dm_full);
                 FTR(1, T - 1 - j, 1);
                 if (j > 0) {
-                    mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_z
-                    FTR(1, T - 1 - j, 2);
-                    gemm(T_DH, true);
-                    umma_commit(&dh1_done);
+                    gemm(T_DH, true, T - 1 - j, 2);             // A = da_z
+                    umma_commit_cl<CL>(&dh1_done);
                     FTR(1, T - 1 - j, 3);
-                    mbar_wait(&a_ready, pa & 1); ++pa; tc_fence_after();    // A = da_r
-                    FTR(1, T - 1 - j, 4);
-                    gemm(T_DH, false);
-                    umma_commit(&ddh_full);
+                    gemm(T_DH, false, T - 1 - j, 4);            // A = da_r
+                    umma_commit_cl<CL>(&ddh_full);
                     FTR(1, T - 1 - j, 5);
                 }
             }
@@ -608,28 +714,78 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             const uint32_t bar = smem_u32(&w_full[s]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_stage) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(w_base + s * w_stage), "l"(wimg + (size_t)(ws % (3 * KB)) * w_stage), "r"(w_stage), "r"(bar) : "memory");
+                         ::"r"(w_base + s * w_stage), "l"(wimg_c + (size_t)(ws % (3 * KB)) * w_stage), "r"(w_stage), "r"(bar) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+// cluster launch of the fused kernels (same bookkeeping as POI_LAUNCH)
+template <class... KArgs, class... Args>
+static int launch_clustered(poi_engine* e, const char* name, void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                            int cl, Args... args) {
+    ProfRec* pr = e->kprof ? prof_begin(e) : nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t st = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    if (pr) cudaEventRecord(pr->b, e->stream);
+    e->cur_flops = 0.0; e->cur_bytes = 0.0;
+    e->launches++;
+    if (st == cudaSuccess) st = cudaPeekAtLastError();
+    if (st != cudaSuccess) POI_FAIL(e, "launch %s failed: %s", name, cudaGetErrorString(st));
+    return 0;
+}
+
+// CTAs per 128-user group: as many as divide the gate columns into slices of >= 32 while the whole grid is still
+// co-resident (one CTA per SM); e->fused_cluster forces 1, 2 or 4
+static inline int pick_cluster(poi_engine* e, int B, int H) {
+    const int groups = (int)poi_cdiv(B, FM);
+    int cl = 1;
+    for (int c = 2; c <= 4; c *= 2)
+        if (H % (32 * c) == 0 && groups * c <= e->num_sms) cl = c;
+    if (e->fused_cluster == 1 || e->fused_cluster == 2 || e->fused_cluster == 4) {
+        cl = e->fused_cluster;
+        while (cl > 1 && H % (32 * cl) != 0) cl >>= 1;
+    }
+    return cl;
+}
+static inline size_t fused_smem(int H, int cl, bool split3) {
+    const int KB = H / 32, wst = cl == 1 ? 2 : (cl == 2 ? 3 : 4);
+    const size_t w_stage = (size_t)(H / cl) * 128 * (split3 ? 2 : 1);
+    return (size_t)KB * A_KB_BYTES * (split3 ? 2 : 1) + wst * w_stage + (size_t)2 * AX_STAGES * AX_TILE + 1024;
+}
+
+template <bool SPLIT3, int CL>
+static int launch_bwd_cl(poi_engine* e, const float* DHl, const float* Z, const float* R, const float* C, const float* Hs,
+                         const uint8_t* wimg, float* DA, int B, int T, int H) {
+    const size_t smem = fused_smem(H, CL, SPLIT3);
+    POI_CK(e, cudaFuncSetAttribute(k_gru_bwd_fused<SPLIT3, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
+    const unsigned grid = (unsigned)poi_cdiv(B, FM) * CL;
+    if (CL == 1) { POI_LAUNCH(e, (k_gru_bwd_fused<SPLIT3, 1>), grid, F_THREADS, smem, DHl, Z, R, C, Hs, wimg, DA, B, T, H); return 0; }
+    return launch_clustered(e, "k_gru_bwd_fused", k_gru_bwd_fused<SPLIT3, CL>, grid, F_THREADS, smem, CL, DHl, Z, R, C, Hs, wimg, DA, B, T, H);
 }
 
 template <bool SPLIT3>
 static int launch_bwd_inst(poi_engine* e, const float* DHl, const float* Z, const float* R, const float* C, const float* Hs,
                            const float* wh, float* DA, int B, int T, int H) {
     const int KB = H / 32;
-    const size_t w_stage = (size_t)H * 128 * (SPLIT3 ? 2 : 1);
+    const int cl = pick_cluster(e, B, H);
+    const size_t w_stage = (size_t)(H / cl) * 128 * (SPLIT3 ? 2 : 1);
     uint8_t* wimg = nullptr;
-    POI_TRY(arena_get(e, (size_t)3 * KB * w_stage, &wimg));
+    POI_TRY(arena_get(e, (size_t)cl * 3 * KB * w_stage, &wimg));
     POI_CAT(e, CAT_ELTWISE, 0, 0);
-    POI_LAUNCH(e, (k_stage_wh_bwd<SPLIT3>), 48, 256, 0, wh, H, wimg);
-    size_t smem = (size_t)KB * A_KB_BYTES * (SPLIT3 ? 2 : 1) + 2 * w_stage + (size_t)2 * AX_STAGES * AX_TILE + 1024;
-    POI_CK(e, cudaFuncSetAttribute(k_gru_bwd_fused<SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
-    POI_LAUNCH(e, (k_gru_bwd_fused<SPLIT3>), (unsigned)poi_cdiv(B, FM), F_THREADS, smem, DHl, Z, R, C, Hs, wimg, DA, B, T, H);
-    return 0;
+    POI_LAUNCH(e, (k_stage_wh_bwd<SPLIT3>), 48, 256, 0, wh, H, cl, wimg);
+    if (cl == 4) return launch_bwd_cl<SPLIT3, 4>(e, DHl, Z, R, C, Hs, wimg, DA, B, T, H);
+    if (cl == 2) return launch_bwd_cl<SPLIT3, 2>(e, DHl, Z, R, C, Hs, wimg, DA, B, T, H);
+    return launch_bwd_cl<SPLIT3, 1>(e, DHl, Z, R, C, Hs, wimg, DA, B, T, H);
 }
 
 static int launch_gru_bwd_fused(poi_engine* e, const float* DHl, const float* Z, const float* R, const float* C,
@@ -649,20 +805,30 @@ __global__ void k_mul_rh(const float* __restrict__ R, const float* __restrict__ 
     reinterpret_cast<float4*>(RH)[i] = make_float4(r.x * h.x, r.y * h.y, r.z * h.z, r.w * h.w);
 }
 
+template <bool SPLIT3, int CL>
+static int launch_fwd_cl(poi_engine* e, const float* AX, const uint8_t* wimg, float* Hs, float* Z, float* R, float* C,
+                         int B, int T, int H) {
+    const size_t smem = fused_smem(H, CL, SPLIT3);
+    POI_CK(e, cudaFuncSetAttribute(k_gru_fwd_fused<SPLIT3, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
+    const unsigned grid = (unsigned)poi_cdiv(B, FM) * CL;
+    if (CL == 1) { POI_LAUNCH(e, (k_gru_fwd_fused<SPLIT3, 1>), grid, F_THREADS, smem, AX, wimg, Hs, Z, R, C, B, T, H); return 0; }
+    return launch_clustered(e, "k_gru_fwd_fused", k_gru_fwd_fused<SPLIT3, CL>, grid, F_THREADS, smem, CL, AX, wimg, Hs, Z, R, C, B, T, H);
+}
+
 template <bool SPLIT3>
 static int launch_fwd_inst(poi_engine* e, const float* AX, const float* wh, float* Hs, float* Z, float* R, float* C,
                            int B, int T, int H) {
     const int KB = H / 32;
-    const size_t w_stage = (size_t)H * 128 * (SPLIT3 ? 2 : 1);
+    const int cl = pick_cluster(e, B, H);
+    const size_t w_stage = (size_t)(H / cl) * 128 * (SPLIT3 ? 2 : 1);
     uint8_t* wimg = nullptr;
-    POI_TRY(arena_get(e, (size_t)3 * KB * w_stage, &wimg));
+    POI_TRY(arena_get(e, (size_t)cl * 3 * KB * w_stage, &wimg));
     POI_CAT(e, CAT_ELTWISE, 0, 0);
-    POI_LAUNCH(e, (k_stage_wh<SPLIT3>), 48, 256, 0, wh, H, wimg);
-    size_t smem = (size_t)KB * A_KB_BYTES * (SPLIT3 ? 2 : 1) + 2 * w_stage + (size_t)2 * AX_STAGES * AX_TILE + 1024;
-    POI_CK(e, cudaFuncSetAttribute(k_gru_fwd_fused<SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
-    POI_LAUNCH(e, (k_gru_fwd_fused<SPLIT3>), (unsigned)poi_cdiv(B, FM), F_THREADS, smem, AX, wimg, Hs, Z, R, C, B, T, H);
-    return 0;
+    POI_LAUNCH(e, (k_stage_wh<SPLIT3>), 48, 256, 0, wh, H, cl, wimg);
+    if (cl == 4) return launch_fwd_cl<SPLIT3, 4>(e, AX, wimg, Hs, Z, R, C, B, T, H);
+    if (cl == 2) return launch_fwd_cl<SPLIT3, 2>(e, AX, wimg, Hs, Z, R, C, B, T, H);
+    return launch_fwd_cl<SPLIT3, 1>(e, AX, wimg, Hs, Z, R, C, B, T, H);
 }
 
 static int launch_gru_fwd_fused(poi_engine* e, const float* AX, const float* wh, float* Hs, float* Z, float* R,

@@ -68,6 +68,10 @@ int poi_set_gemm_mode(poi_engine* e, int mode) {
 }
 int poi_get_gemm_mode(poi_engine* e, int* mode) { *mode = e->gemm_mode; return 0; }
 int poi_set_fused_recurrence(poi_engine* e, int on) { e->fuse_recurrence = on != 0; return 0; }
+int poi_set_fused_cluster(poi_engine* e, int cl) {
+    if (cl != 0 && cl != 1 && cl != 2 && cl != 4) POI_FAIL(e, "poi_set_fused_cluster: %d (0 auto, 1, 2, 4)", cl);
+    e->fused_cluster = cl; return 0;
+}
 int poi_set_wgrad_mn(poi_engine* e, int on) { e->wgrad_mn = on != 0; return 0; }
 int poi_kprof_enable(poi_engine* e, int on) { e->kprof = on != 0; return 0; }
 int poi_kprof_reset(poi_engine* e) {

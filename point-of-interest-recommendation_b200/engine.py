@@ -114,6 +114,10 @@ class Engine:
     def set_fused_recurrence(self, on: bool):
         self._ck(lib.poi_set_fused_recurrence(self._h, 1 if on else 0))
 
+    def set_fused_cluster(self, cl: int):
+        """CTAs per 128 users in the fused recurrence kernels: 0 auto, 1, 2 or 4."""
+        self._ck(lib.poi_set_fused_cluster(self._h, int(cl)))
+
     def set_wgrad_mn(self, on: bool):
         self._ck(lib.poi_set_wgrad_mn(self._h, 1 if on else 0))
 

@@ -184,10 +184,12 @@ def test_spatial_minibatch_tensor_core_modes(engine, mode, rtol):
 
 
 @pytest.mark.parametrize("mode,rtol", [(1, 1e-4), (2, 2e-2)])
-@pytest.mark.parametrize("n_user,d", [(192, 128), (70, 64), (5, 32)])
-def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d):
-    """The persistent fused forward-recurrence kernel (gru_fused.cuh) against the oracle, ragged batch
-    sizes (partial 128-user tiles) and H in {32, 64, 128}."""
+@pytest.mark.parametrize("n_user,d,cl", [(192, 128, 0), (70, 64, 0), (5, 32, 0), (192, 128, 1), (192, 128, 2), (300, 128, 4),
+                                         (70, 64, 2), (129, 64, 1)])
+def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d, cl):
+    """The persistent fused recurrence kernels (gru_fused.cuh, forward and BPTT) against the oracle, ragged batch
+    sizes (partial 128-user tiles), H in {32, 64, 128} and every cluster split (cl CTAs per 128 users exchanging
+    the next operand through distributed shared memory; 0 = the engine's own choice)."""
     from poi_b200.public.GRU_Spatial import SpatialGru
     rs = np.random.RandomState(500 + n_user + d)
     n_item, lmax, n_dist = 2000, 13, 60
@@ -196,7 +198,7 @@ def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d):
     model = SpatialGru([P, M, Q], test, [DP, tes_d, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
     ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
     prev = engine.get_gemm_mode()
-    engine.set_gemm_mode(mode); engine.set_fused_recurrence(True)
+    engine.set_gemm_mode(mode); engine.set_fused_recurrence(True); engine.set_fused_cluster(cl)
     try:
         for _ in range(2):
             se = np.arange(n_user, dtype=np.int32)
@@ -204,10 +206,38 @@ def test_fused_recurrence_kernel(engine, mode, rtol, n_user, d):
             (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
             assert_close([los, sur, upq], [rl, rs_, ru], rtol, "losses")
     finally:
-        engine.set_gemm_mode(prev); engine.set_fused_recurrence(True)
+        engine.set_gemm_mode(prev); engine.set_fused_recurrence(True); engine.set_fused_cluster(0)
     got = state_from_model(model, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
     for k in got:
         assert_close(got[k], ref[k], rtol, k)
+
+
+def test_fused_cluster_split_consistent_and_deterministic(engine):
+    """Splitting the gate columns over a cluster changes which SM computes a column and the order in which the
+    k-blocks of the recurrent product are accumulated (arrival order), nothing else: 1, 2 and 4 CTAs per 128 users
+    agree to fp32 rounding, and each setting is bit-reproducible run to run."""
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(77)
+    n_user, n_item, d, lmax, n_dist = 400, 3000, 128, 21, 200
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    results = {}
+    try:
+        for cl in (1, 2, 4, 4):
+            engine.set_fused_cluster(cl)
+            m = SpatialGru([P, M, Q], test, [DP, [[n_dist]] * n_user, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+            outs = [m.train(np.arange(s, s + 200, dtype=np.int32))[:3] for s in (0, 200)]
+            res = (np.asarray(outs), state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs"]))
+            if cl in results:           # second run of the same setting: same bits
+                assert np.array_equal(res[0], results[cl][0])
+                for k in res[1]:
+                    assert np.array_equal(res[1][k], results[cl][1][k]), k
+            results[cl] = res
+    finally:
+        engine.set_fused_cluster(0)
+    for cl in (2, 4):
+        assert_close(results[cl][0], results[1][0], 2e-6, "losses cl=%d" % cl)
+        for k in results[cl][1]:
+            assert_close(results[cl][1][k], results[1][1][k], 2e-6, "%s cl=%d" % (k, cl))
 
 
 @pytest.mark.parametrize("mode", [0, 1])

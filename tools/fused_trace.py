@@ -35,6 +35,9 @@ tes = ds["tes"]
 m = SpatialGru([ds["P"], ds["M"], ds["Q"]], [tes, np.ones_like(tes), tes], [ds["DP"], np.full_like(tes, D), ds["DQ"]],
                [0.01, 0.001], U, I, [D, 0.2], d, d, init=st, device=0)
 users = np.arange(B, dtype=np.int32)
+CL = int(os.environ.get("POI_FUSED_CLUSTER", "0"))
+m.engine.set_fused_cluster(CL)
+print("#### fused_cluster =", CL or "auto")
 for _ in range(3):
     m.train(users)
 lib.poi_debug_fused_trace.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]

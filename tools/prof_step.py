@@ -15,6 +15,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--gemm-mode", type=int, default=0)
 ap.add_argument("--config", default="c2")
 ap.add_argument("--fused", type=int, default=1)
+ap.add_argument("--fused-cluster", type=int, default=0)
 a = ap.parse_args()
 cfg, ds, st = bench.build_workload(a.config)
 import poi_b200  # noqa
@@ -24,6 +25,7 @@ m = SpatialGru([ds["P"], ds["M"], ds["Q"]], [tes, np.ones_like(tes), tes], [ds["
                [bench.ALPHA, bench.LAM], ds["n_user"], ds["n_item"], [D, 0.2], cfg["d"], cfg["d"], init=st)
 m.engine.set_gemm_mode(a.gemm_mode)
 m.engine.set_fused_recurrence(bool(a.fused))
+m.engine.set_fused_cluster(a.fused_cluster)
 B = min(a.batch, ds["n_user"])
 for i in range(a.steps):
     s = (i * B) % ds["n_user"]
