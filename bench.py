@@ -236,7 +236,8 @@ def run_ours(args):
         from poi_b200.dist import ShardedSpatialGru
         mine = np.arange(rank, U, world)
         model = ShardedSpatialGru([ds["P"][mine], ds["M"][mine], ds["Q"][mine]], [ds["DP"][mine], ds["DQ"][mine]],
-                                  [ALPHA, LAM], I, D, d, d, st, device=local_rank)
+                                  [ALPHA, LAM], I, D, d, d, st, device=local_rank, peer=bool(args.peer),
+                                  max_batch=min(args.batch, len(mine)))
     eng = model.engine
     eng.set_gemm_mode(args.gemm_mode)
     eng.set_fused_recurrence(bool(args.fused))
@@ -277,6 +278,8 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+        if getattr(model, "trace", None) is not None:
+            model.trace.acc, model.trace.n = {}, 0         # phase trace: timed steps only
         done = 0
         losses = []
         launches0 = eng.launch_count()
@@ -324,6 +327,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    if getattr(model, "trace", None) is not None and rank == 0:
+        print("[mg phase trace, ms per step, rank 0]", json.dumps(model.trace.report()), file=sys.stderr, flush=True)
+        print("[engine kernel ms per profiled step]", json.dumps({k: round(v["ms"] / nprof, 4) for k, v in prof.items() if v["ms"] > 0}),
+              file=sys.stderr, flush=True)
     ms_max, ms_e2e_max = allmax(ms), allmax(ms_e2e)
     done_all, done_e2e_all = allsum(done), allsum(done_e2e)
     launches_all = int(allsum(launches))
@@ -406,8 +413,11 @@ def run_ours(args):
                    "gemm": {0: "fp32 FMA", 1: "tcgen05 3xTF32 (fp32-faithful), fp32 accumulate in TMEM", 2: "tcgen05 1xTF32"}[args.gemm_mode],
                    "gemm_mode": args.gemm_mode, "fused_recurrence": bool(args.fused) and args.gemm_mode != 0, "fused_cluster": args.fused_cluster or "auto", "l2": "flushed between timed steps (256 MB write)",
                    "parallelism": "1 GPU" if world == 1 else
-                   "dp%d: users sharded, item table row-sharded (row %% %d) with NCCL all-to-all of rows / row-gradients, "
-                   "dense gradients all-reduced" % (world, world)},
+                   ("dp%d: users sharded, item table row-sharded (row %% %d); rows gathered from the owners' shards and "
+                    "row-gradients pulled from the peers' outboxes by kernels over NVLink peer memory; dense gradients "
+                    "all-reduced (NCCL)" if args.peer else
+                    "dp%d: users sharded, item table row-sharded (row %% %d) with NCCL all-to-all of rows / row-gradients, "
+                    "dense gradients all-reduced") % (world, world)},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 40,
                 "ms_per_step": ms_e2e_max / K},
         "gpu_launches": launches_all,
@@ -433,6 +443,8 @@ def main():
     ap.add_argument("--fused", type=int, default=1, help="1 = persistent fused recurrence kernel (tensor-core modes)")
     ap.add_argument("--fused-cluster", type=int, default=0,
                     help="CTAs per 128 users in the fused recurrence kernels: 0 auto (default), 1, 2, 4")
+    ap.add_argument("--peer", type=int, default=1,
+                    help="multi-GPU exchange: 1 = NVLink peer-memory kernels (default), 0 = NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-obo", action="store_true")
     ap.add_argument("--no-micro", action="store_true", help="skip the stand-alone gather / scatter HBM micro-benchmark")

@@ -197,6 +197,30 @@ int poi_gru_apply_mg(poi_engine* e, const poi_gru_params* params, const float* d
                      const float* recv_grads_dev, const float* recv_cnts_dev, int64_t n_recv,
                      float alpha, float lambda, double* out_host);
 
+/* ---- the same exchanges over NVLink peer memory, no collective on the data path (csrc/peer.cuh).
+ * poi_peer_alloc: device memory exportable to the other ranks of the box (cudaMalloc + cudaIpcGetMemHandle; the
+ * 64-byte handle is sent through torch.distributed once); poi_peer_open maps a peer's buffer (peer access is
+ * enabled on first use).  poi_gather_rows_sharded: out[i] = row ids[i] of the row-sharded table, read from the
+ * OWNER's shard (owner = id % world, local row = id / world); shards_host = host array of `world` device
+ * pointers (own shard + opened peers).  poi_pull_segments: rank r's outbox is (ids, gradient rows, counts) exactly
+ * as poi_gru_mg_prepare / poi_gru_train_mg wrote them, plus perm = the record numbers grouped by owner; the
+ * owner copies the n_host[r] records perm[src_off_host[r] ...] of every rank into its receive buffers, grouped by
+ * source rank in rank order, ids converted to local rows -- the input poi_gru_apply_mg expects. */
+int poi_peer_alloc(poi_engine* e, int64_t bytes, void** ptr_out, unsigned char* handle_out64);
+int poi_peer_free(poi_engine* e, void* ptr);
+int poi_peer_open(poi_engine* e, const unsigned char* handle64, void** ptr_out);
+int poi_peer_close(poi_engine* e, void* ptr);
+int poi_gather_rows_sharded(poi_engine* e, const float* const* shards_host, int world, int dim,
+                            const int32_t* ids_dev, int64_t n_idx, float* out_dev);
+/* perm_out_dev[n] = record numbers 0..n-1 grouped by owner (ids[i] % world), original order inside a group (one
+ * stable radix pass); counts_out_dev[world] (double) = records per owner. */
+int poi_group_by_owner(poi_engine* e, const int32_t* ids_dev, int64_t n, int world, int32_t* perm_out_dev,
+                       double* counts_out_dev);
+int poi_pull_segments(poi_engine* e, int world, int dim, const int32_t* const* perm_host,
+                      const int32_t* const* ids_host, const float* const* grads_host,
+                      const float* const* cnts_host, const int64_t* src_off_host, const int64_t* n_host,
+                      int32_t* recv_local_ids_dev, float* recv_grads_dev, float* recv_cnts_dev);
+
 /* ---- BPR-MF: OboBpr.bpr_train (BPR.py:234-241) / Bpr.bpr_train (BPR.py:389-397) --------- */
 /* n sequential (u, p, q) SGD steps in the order given -- exactly n back-to-back
  * `model.train(uidx, [p, q])` calls (prog_bpr_gru_spatial.py:240-244); per-occurrence

@@ -72,6 +72,14 @@ _PROTOS = {
                                  c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "poi_gru_apply_mg": (c_int, [_E, POINTER(PoiGruParams), c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int64,
                                  c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, POINTER(c_double)]),
+    "poi_peer_alloc": (c_int, [_E, c_int64, POINTER(c_void_p), c_void_p]),
+    "poi_peer_free": (c_int, [_E, c_void_p]),
+    "poi_peer_open": (c_int, [_E, c_void_p, POINTER(c_void_p)]),
+    "poi_peer_close": (c_int, [_E, c_void_p]),
+    "poi_gather_rows_sharded": (c_int, [_E, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "poi_group_by_owner": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "poi_pull_segments": (c_int, [_E, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "poi_bpr_train_seq": (c_int, [_E, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_void_p]),
     "poi_bpr_train_batch": (c_int, [_E, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p,

@@ -334,6 +334,99 @@ int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* it
 
 }  // extern "C"
 
+// ---- NVLink peer memory (peer.cuh) ---------------------------------------------------------------
+extern "C" int poi_peer_alloc(poi_engine* e, int64_t bytes, void** ptr_out, unsigned char* handle_out64) {
+    POI_CK(e, cudaSetDevice(e->device));
+    if (bytes <= 0 || !ptr_out || !handle_out64) POI_FAIL(e, "poi_peer_alloc: bad arguments");
+    void* p = nullptr;
+    POI_CK(e, cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t st = cudaIpcGetMemHandle(&h, p);
+    if (st != cudaSuccess) { cudaFree(p); POI_FAIL(e, "cudaIpcGetMemHandle: %s", cudaGetErrorString(st)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out64, &h, 64);
+    *ptr_out = p;
+    return 0;
+}
+extern "C" int poi_peer_free(poi_engine* e, void* ptr) {
+    POI_CK(e, cudaSetDevice(e->device));
+    POI_CK(e, cudaFree(ptr));
+    return 0;
+}
+extern "C" int poi_peer_open(poi_engine* e, const unsigned char* handle64, void** ptr_out) {
+    POI_CK(e, cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    POI_CK(e, cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int poi_peer_close(poi_engine* e, void* ptr) {
+    POI_CK(e, cudaSetDevice(e->device));
+    POI_CK(e, cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+extern "C" int poi_gather_rows_sharded(poi_engine* e, const float* const* shards_host, int world, int dim,
+                                       const int32_t* ids_dev, int64_t n_idx, float* out_dev) {
+    POI_TRY(begin_call(e));
+    if (world < 1 || world > POI_MAX_PEERS) POI_FAIL(e, "world must be in [1, %d]", POI_MAX_PEERS);
+    if (dim <= 0 || dim % 4) POI_FAIL(e, "dim must be a positive multiple of 4");
+    if (n_idx <= 0) return 0;
+    PeerTable pt; memset(&pt, 0, sizeof(pt));
+    pt.world = world;
+    for (int r = 0; r < world; ++r) pt.shard[r] = shards_host[r];
+    const int dim4 = dim / 4;
+    // bytes: every row read once (world-1 of world over NVLink) and written once, plus the ids
+    POI_CAT(e, CAT_GATHER, 0, 2.0 * (double)n_idx * dim * 4 + 4.0 * (double)n_idx);
+    const int lpr = dim4 <= 8 ? 8 : (dim4 <= 16 ? 16 : 32);
+    const int64_t threads_needed = poi_cdiv(n_idx, 4) * lpr;
+    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(threads_needed, 256), (int64_t)e->num_sms * 16));
+    if (lpr == 8)       POI_LAUNCH(e, (k_gather_rows_sharded<8, 4>), grid, 256, 0, pt, dim4, ids_dev, n_idx, out_dev);
+    else if (lpr == 16) POI_LAUNCH(e, (k_gather_rows_sharded<16, 4>), grid, 256, 0, pt, dim4, ids_dev, n_idx, out_dev);
+    else                POI_LAUNCH(e, (k_gather_rows_sharded<32, 4>), grid, 256, 0, pt, dim4, ids_dev, n_idx, out_dev);
+    return 0;
+}
+
+extern "C" int poi_pull_segments(poi_engine* e, int world, int dim, const int32_t* const* perm_host,
+                                 const int32_t* const* ids_host, const float* const* grads_host,
+                                 const float* const* cnts_host, const int64_t* src_off_host, const int64_t* n_host,
+                                 int32_t* recv_local_ids_dev, float* recv_grads_dev, float* recv_cnts_dev) {
+    POI_TRY(begin_call(e));
+    if (world < 1 || world > POI_MAX_PEERS) POI_FAIL(e, "world must be in [1, %d]", POI_MAX_PEERS);
+    if (dim <= 0 || dim % 4) POI_FAIL(e, "dim must be a positive multiple of 4");
+    PullTable pt; memset(&pt, 0, sizeof(pt));
+    pt.world = world;
+    int64_t tot = 0;
+    for (int r = 0; r < world; ++r) {
+        pt.perm[r] = perm_host[r]; pt.ids[r] = ids_host[r]; pt.grads[r] = grads_host[r]; pt.cnts[r] = cnts_host[r];
+        pt.src_off[r] = src_off_host[r]; pt.dst_off[r] = tot;
+        if (n_host[r] < 0) POI_FAIL(e, "negative segment size");
+        tot += n_host[r];
+    }
+    pt.dst_off[world] = tot;
+    if (tot == 0) return 0;
+    POI_CAT(e, CAT_ROWS, 0, 2.0 * (double)tot * dim * 4 + 20.0 * (double)tot);
+    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(tot * 32, 256), (int64_t)e->num_sms * 16));
+    POI_LAUNCH(e, k_pull_segments, grid, 256, 0, pt, dim / 4, recv_local_ids_dev, recv_grads_dev, recv_cnts_dev);
+    return 0;
+}
+
+
+extern "C" int poi_group_by_owner(poi_engine* e, const int32_t* ids_dev, int64_t n, int world, int32_t* perm_out_dev,
+                                  double* counts_out_dev) {
+    POI_TRY(begin_call(e));
+    if (world < 1 || world > POI_MAX_PEERS) POI_FAIL(e, "world must be in [1, %d]", POI_MAX_PEERS);
+    if (n < 0) POI_FAIL(e, "negative count");
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    uint32_t* keys = nullptr;
+    POI_TRY(arena_get(e, (size_t)std::max<int64_t>(n, 1), &keys));
+    if (n > 0) POI_LAUNCH(e, k_owner_keys, (unsigned)poi_cdiv(n, 256), 256, 0, ids_dev, n, world, keys);
+    uint32_t *ks = nullptr, *vs = nullptr;
+    POI_TRY(sort_pairs(e, keys, n, (uint32_t)world, &ks, &vs));
+    POI_LAUNCH(e, k_owner_perm_counts, (unsigned)std::max<int64_t>(1, poi_cdiv(n, 256)), 256, 0, ks, vs, n, world, perm_out_dev, counts_out_dev);
+    return 0;
+}
+
 #ifdef POI_FUSED_TRACE
 // debugging build only (tools/fused_trace.py): clock stamps of CTA 0 of the fused recurrence kernels
 extern "C" int poi_debug_fused_trace(int dir, long long* out, int n, int clear) {

@@ -9,6 +9,7 @@
 #include "gru.cuh"
 #include "mf.cuh"
 #include "geoie.cuh"
+#include "peer.cuh"
 #include "eval.cuh"
 
 extern "C" {

@@ -5,13 +5,46 @@ runs is in libpoi_b200.so.
 from __future__ import annotations
 
 import ctypes
-from ctypes import byref, c_double, c_float, c_int, c_int64
+from ctypes import byref, c_double, c_float, c_int, c_int64, c_void_p
 
 import numpy as np
 import torch
 
 from . import _lib
 from ._lib import PoiGeoieParams, PoiGruParams, PoiSeqIndex, lib
+
+
+
+class _RawDeviceBuffer:
+    """Device memory the engine allocated (poi_peer_alloc) or mapped from a peer (poi_peer_open), presented to
+    torch through __cuda_array_interface__ -- torch stays the container, the memory is IPC-exportable."""
+
+    def __init__(self, engine, ptr: int, nbytes: int, owned: bool):
+        self.engine, self.ptr, self.nbytes, self.owned = engine, ptr, nbytes, owned
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def as_tensor(self, shape, dtype):
+        """torch view of OWN memory (never of a peer mapping: torch would place it on the peer's device)."""
+        t = torch.as_tensor(self, device=self.engine.torch_device).view(dtype)
+        t = t[:int(np.prod(shape))].view(*shape)
+        t._poi_raw = self           # keep the allocation alive as long as the tensor
+        return t
+
+    def view(self, shape):
+        """Pointer + shape of a peer mapping, for the engine calls that read peer memory."""
+        self.shape = tuple(shape)
+        return self
+
+    def data_ptr(self):
+        return self.ptr
+
+    def __del__(self):
+        try:
+            if self.ptr and getattr(self.engine, "_h", None):
+                (lib.poi_peer_free if self.owned else lib.poi_peer_close)(self.engine._h, c_void_p(self.ptr))
+        except Exception:
+            pass
+        self.ptr = 0
 
 
 class EngineError(RuntimeError):
@@ -125,6 +158,53 @@ class Engine:
         m = c_int()
         self._ck(lib.poi_get_gemm_mode(self._h, byref(m)))
         return m.value
+
+
+    # ---- NVLink peer memory (csrc/peer.cuh) ---------------------------------------------------
+    def peer_alloc(self, shape, dtype: torch.dtype):
+        """Device tensor in memory other ranks of the box can map: returns (tensor, 64-byte IPC handle)."""
+        n = int(np.prod(shape))
+        nbytes = max(n, 1) * torch.empty((), dtype=dtype).element_size()
+        ptr = c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self._ck(lib.poi_peer_alloc(self._h, nbytes, byref(ptr), handle))
+        return _RawDeviceBuffer(self, ptr.value, nbytes, owned=True).as_tensor(shape, dtype), handle.raw
+
+    def peer_open(self, handle: bytes, shape, dtype: torch.dtype):
+        """Map a peer rank's buffer (poi_peer_alloc on that rank) into this process; returns a pointer view
+        (data_ptr(), shape) for gather_rows_sharded / pull_segments."""
+        n = int(np.prod(shape))
+        nbytes = max(n, 1) * torch.empty((), dtype=dtype).element_size()
+        ptr = c_void_p()
+        self._ck(lib.poi_peer_open(self._h, ctypes.c_char_p(handle), byref(ptr)))
+        return _RawDeviceBuffer(self, ptr.value, nbytes, owned=False).view(shape)
+
+    def gather_rows_sharded(self, shards, ids: torch.Tensor, out: torch.Tensor):
+        """out[i] = row ids[i] of the row-sharded table (owner = id % world), read from the owners' shards."""
+        world = len(shards)
+        arr = (c_void_p * world)(*[s.data_ptr() for s in shards])
+        self._ck(lib.poi_gather_rows_sharded(self._h, arr, world, shards[0].shape[1], _dev_i32(ids, "ids"), ids.numel(),
+                                             _dev_f32(out, "out")))
+        return out
+
+    def group_by_owner(self, ids: torch.Tensor, world: int, perm_out: torch.Tensor, counts_out: torch.Tensor):
+        """perm_out = record numbers grouped by owner (ids % world), stable; counts_out (float64[world]) = group sizes."""
+        self._ck(lib.poi_group_by_owner(self._h, _dev_i32(ids, "ids"), ids.numel(), world, _dev_i32(perm_out, "perm"),
+                                        counts_out.data_ptr()))
+
+    def pull_segments(self, perm, ids, grads, cnts, src_off, n, recv_ids, recv_grads, recv_cnts):
+        """Copy, from every rank's outbox, the n[r] records perm[r][src_off[r] ...] (peer memory) into this rank's
+        receive buffers, grouped by source rank."""
+        world = len(ids)
+        a_pm = (c_void_p * world)(*[t.data_ptr() for t in perm])
+        a_ids = (c_void_p * world)(*[t.data_ptr() for t in ids])
+        a_gr = (c_void_p * world)(*[t.data_ptr() for t in grads])
+        a_cn = (c_void_p * world)(*[t.data_ptr() for t in cnts])
+        a_so = (c_int64 * world)(*[int(x) for x in src_off])
+        a_n = (c_int64 * world)(*[int(x) for x in n])
+        self._ck(lib.poi_pull_segments(self._h, world, grads[0].shape[1], a_pm, a_ids, a_gr, a_cn, a_so, a_n,
+                                       _dev_i32(recv_ids, "recv_ids"), _dev_f32(recv_grads, "recv_grads"),
+                                       _dev_f32(recv_cnts, "recv_cnts")))
 
     # ---- first-slice kernels ----------------------------------------------------------------
     def gather_rows(self, table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None):

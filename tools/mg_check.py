@@ -25,8 +25,9 @@ ds = synth.make_dataset(U, I, seq, ragged=True, zipf=1.2)
 st = synth.init_state(I, d, d, ds["dist_num"])
 A, L = 0.01, 0.001
 mine = np.arange(rank, U, world)                       # this rank's users
+PEER = int(os.environ.get("POI_MG_PEER", "1"))          # 1: NVLink peer-memory exchange (default), 0: NCCL all-to-all
 m = ShardedSpatialGru([ds["P"][mine], ds["M"][mine], ds["Q"][mine]], [ds["DP"][mine], ds["DQ"][mine]], [A, L], I,
-                      ds["dist_num"], d, d, st, device=lr)
+                      ds["dist_num"], d, d, st, device=lr, peer=bool(PEER), max_batch=B)
 outs = []
 for s in range(steps):
     loc = np.arange(s * B, (s + 1) * B, dtype=np.int32)
@@ -51,7 +52,7 @@ if rank == 0:
                 di=rel(m.di.get_value(), ref.di.get_value()), scal=rel(m._scal.get_value(), ref._scal.get_value()))
     print("param rel.err vs single-GPU union batch:", {k: "%.2e" % v for k, v in errs.items()})
     ok &= all(v < 1e-5 for v in errs.values())
-    print("MG_CHECK", "PASS" if ok else "FAIL", "world", world)
+    print("MG_CHECK", "PASS" if ok else "FAIL", "world", world, "peer", int(m.peer))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
