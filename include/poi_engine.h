@@ -221,6 +221,20 @@ int poi_pull_segments(poi_engine* e, int world, int dim, const int32_t* const* p
                       const float* const* cnts_host, const int64_t* src_off_host, const int64_t* n_host,
                       int32_t* recv_local_ids_dev, float* recv_grads_dev, float* recv_cnts_dev);
 
+/* ---- the reference's per-epoch host loops on the device (csrc/sampling.cuh).
+ * poi_sample_negatives = fun_random_neg_masks_tra / _tes (Load_Data_by_length.py:127-162): out[u][t] = a uniform
+ * draw from [0, n_item) redrawn while it occurs in the user's forbidden rows (sorted_a [n_user x la], optionally
+ * sorted_b [n_user x lb], each row sorted ascending), for every t with rows[u][t] != n_item; pad positions get n_item.
+ * Counter-based stream: Philox4x32-10(counter = (u, t, attempt / 4, epoch), key = seed), j = (word * n_item) >> 32 --
+ * a NEW stream (the reference's sequential Mersenne Twister cannot be reproduced in parallel), restated bit-exactly
+ * in oracle/sampling.py.  poi_neg_intervals = fun_compute_dist_neg (:165-180): out[u][t] = cal_dis interval between
+ * q[u][t] and p[u][t-1] (fp64 haversine, coords [n_item x 2] = lat, lon) for 1 <= t < lens[u], dist_num elsewhere. */
+int poi_sample_negatives(poi_engine* e, const int32_t* rows_dev, int32_t lrow, const int32_t* sorted_a_dev, int32_t la,
+                         const int32_t* sorted_b_dev, int32_t lb, int32_t n_user, int32_t n_item, uint64_t seed,
+                         uint32_t epoch, int32_t* out_dev);
+int poi_neg_intervals(poi_engine* e, const int32_t* p_dev, const int32_t* q_dev, const int32_t* lens_dev, int32_t n_user,
+                      int32_t lmax, const double* coords_dev, double dd, int32_t dist_num, int32_t* out_dev);
+
 /* ---- BPR-MF: OboBpr.bpr_train (BPR.py:234-241) / Bpr.bpr_train (BPR.py:389-397) --------- */
 /* n sequential (u, p, q) SGD steps in the order given -- exactly n back-to-back
  * `model.train(uidx, [p, q])` calls (prog_bpr_gru_spatial.py:240-244); per-occurrence

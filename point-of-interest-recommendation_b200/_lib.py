@@ -5,7 +5,7 @@ B200 is present ``poi_engine_create`` fails; both loudly.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # POI_B200_LIB: an instrumented build of the same library (tools/fused_trace.py); never a different backend
@@ -80,6 +80,9 @@ _PROTOS = {
     "poi_group_by_owner": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "poi_pull_segments": (c_int, [_E, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
+    "poi_sample_negatives": (c_int, [_E, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_uint64,
+                                     c_uint32, c_void_p]),
+    "poi_neg_intervals": (c_int, [_E, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_double, c_int32, c_void_p]),
     "poi_bpr_train_seq": (c_int, [_E, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_void_p]),
     "poi_bpr_train_batch": (c_int, [_E, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p,

@@ -427,6 +427,31 @@ extern "C" int poi_group_by_owner(poi_engine* e, const int32_t* ids_dev, int64_t
     return 0;
 }
 
+// ---- per-epoch negative sampling and negative-distance binning on the device (sampling.cuh) ----
+extern "C" int poi_sample_negatives(poi_engine* e, const int32_t* rows_dev, int32_t lrow, const int32_t* sorted_a_dev, int32_t la,
+                                    const int32_t* sorted_b_dev, int32_t lb, int32_t n_user, int32_t n_item, uint64_t seed,
+                                    uint32_t epoch, int32_t* out_dev) {
+    POI_TRY(begin_call(e));
+    if (!rows_dev || !sorted_a_dev || !out_dev) POI_FAIL(e, "poi_sample_negatives: null pointer");
+    if (n_user <= 0 || lrow <= 0 || la <= 0 || n_item <= 0) POI_FAIL(e, "poi_sample_negatives: bad sizes");
+    if ((int64_t)la + (sorted_b_dev ? lb : 0) >= n_item) POI_FAIL(e, "a user's rows could cover the whole catalogue: the rejection loop may not end");
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    const int64_t n = (int64_t)n_user * lrow;
+    POI_LAUNCH(e, k_sample_negatives, (unsigned)poi_cdiv(n, 256), 256, 0, rows_dev, lrow, sorted_a_dev, la, sorted_b_dev, lb,
+               n_user, n_item, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), epoch, out_dev);
+    return 0;
+}
+extern "C" int poi_neg_intervals(poi_engine* e, const int32_t* p_dev, const int32_t* q_dev, const int32_t* lens_dev, int32_t n_user,
+                                 int32_t lmax, const double* coords_dev, double dd, int32_t dist_num, int32_t* out_dev) {
+    POI_TRY(begin_call(e));
+    if (!p_dev || !q_dev || !lens_dev || !coords_dev || !out_dev) POI_FAIL(e, "poi_neg_intervals: null pointer");
+    if (n_user <= 0 || lmax <= 0 || !(dd > 0)) POI_FAIL(e, "poi_neg_intervals: bad sizes");
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    const int64_t n = (int64_t)n_user * lmax;
+    POI_LAUNCH(e, k_neg_intervals, (unsigned)poi_cdiv(n, 256), 256, 0, p_dev, q_dev, lens_dev, n_user, lmax, coords_dev, dd, dist_num, out_dev);
+    return 0;
+}
+
 #ifdef POI_FUSED_TRACE
 // debugging build only (tools/fused_trace.py): clock stamps of CTA 0 of the fused recurrence kernels
 extern "C" int poi_debug_fused_trace(int dir, long long* out, int n, int clear) {

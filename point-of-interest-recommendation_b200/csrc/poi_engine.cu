@@ -10,6 +10,7 @@
 #include "mf.cuh"
 #include "geoie.cuh"
 #include "peer.cuh"
+#include "sampling.cuh"
 #include "eval.cuh"
 
 extern "C" {

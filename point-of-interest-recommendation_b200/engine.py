@@ -206,6 +206,30 @@ class Engine:
                                        _dev_i32(recv_ids, "recv_ids"), _dev_f32(recv_grads, "recv_grads"),
                                        _dev_f32(recv_cnts, "recv_cnts")))
 
+
+    # ---- per-epoch negative sampling on the device (csrc/sampling.cuh) ---------------
+    def sample_negatives(self, rows: torch.Tensor, sorted_a: torch.Tensor, n_item: int, seed: int, epoch: int,
+                         sorted_b: torch.Tensor | None = None, out: torch.Tensor | None = None):
+        """out[u, t] = uniform draw from [0, n_item) not in the user's sorted rows, for positions before the first pad."""
+        if out is None:
+            out = torch.empty_like(rows)
+        self._ck(lib.poi_sample_negatives(self._h, _dev_i32(rows, "rows"), rows.shape[1], _dev_i32(sorted_a, "sorted_a"),
+                                          sorted_a.shape[1], _dev_i32(sorted_b, "sorted_b") if sorted_b is not None else None,
+                                          sorted_b.shape[1] if sorted_b is not None else 0, rows.shape[0], int(n_item),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, _dev_i32(out, "out")))
+        return out
+
+    def neg_intervals(self, p: torch.Tensor, q: torch.Tensor, lens: torch.Tensor, coords: torch.Tensor, dd: float,
+                      dist_num: int, out: torch.Tensor | None = None):
+        """Distance-interval ids between q[u, t] and p[u, t-1] (cal_dis in fp64); dist_num at t = 0 and on the padding."""
+        if coords.dtype != torch.float64 or not coords.is_contiguous():
+            raise EngineError("coords must be a contiguous float64 [n_item x 2] tensor")
+        if out is None:
+            out = torch.empty_like(p)
+        self._ck(lib.poi_neg_intervals(self._h, _dev_i32(p, "p"), _dev_i32(q, "q"), _dev_i32(lens, "lens"), p.shape[0], p.shape[1],
+                                       coords.data_ptr(), float(dd), int(dist_num), _dev_i32(out, "out")))
+        return out
+
     # ---- first-slice kernels ----------------------------------------------------------------
     def gather_rows(self, table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None):
         n = idx.numel()

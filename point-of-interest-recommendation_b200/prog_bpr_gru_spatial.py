@@ -188,7 +188,12 @@ def train_valid_or_test(pas, init=None, device=None):
     times0, times1, times2 = [], [], []
     for epoch in np.arange(ini_epoch, p['epochs']):
         print("Epoch {val} ==================================".format(val=epoch))
-        if epoch > 0:
+        if epoch > 0 and p.get('gpu_neg', 0) and p['gru'] in [1, 2]:
+            # resample on the device (same rule, counter-based stream); the host copy is only needed
+            # by drivers that read the matrix back (BPR's per-check-in loop, gru == 0)
+            model.resample_negatives_device(epoch, seed=p.get('neg_seed', 123), coords=pois_cordis if 2 == p['gru'] else None,
+                                            dd_m=dd, dist_num=dist_num)
+        elif epoch > 0:
             tra_buys_neg_masks = fun_random_neg_masks_tra(item_num, tra_buys_masks)
             tes_buys_neg_masks = fun_random_neg_masks_tes(item_num, tra_buys_masks, tes_buys_masks)
             if p['gru'] in [0, 1]:

@@ -58,6 +58,28 @@ class GruBasic(object):
         self.tra_buys_neg_masks.set_value(np.asarray(tra_buys_neg_masks, dtype="int32"))
         self.tes_buys_neg_masks.set_value(np.asarray(tes_buys_neg_masks, dtype="int32"))
 
+    def resample_negatives_device(self, epoch, seed=123, coords=None, dd_m=None, dist_num=None):
+        """the per-epoch refresh of the negatives (prog_bpr_gru_spatial.py:186-198 in the reference:
+        `fun_random_neg_masks_tra`, `fun_random_neg_masks_tes`, and for Distance2Pre `fun_compute_dist_neg`) entirely on
+        the device -- no Python rejection loops, no host round trip of the index matrices.  Same sampling rule, the
+        engine's counter-based random stream (csrc/sampling.cuh); `coords` (n_item x 2 lat/lon) enables the negative
+        distance intervals of Distance2Pre."""
+        eng, n_item = self.engine, self.n_item
+        if getattr(self, "_tra_sorted", None) is None:          # the users' own rows never change: sort once
+            self._tra_sorted = torch.sort(self.tra_buys_masks.t, dim=1).values.contiguous()
+            self._tes_sorted = torch.sort(self.tes_buys_masks.t, dim=1).values.contiguous()
+        eng.sample_negatives(self.tra_buys_masks.t, self._tra_sorted, n_item, seed, 2 * int(epoch), out=self.tra_buys_neg_masks.t)
+        eng.sample_negatives(self.tes_buys_masks.t, self._tra_sorted, n_item, seed, 2 * int(epoch) + 1,
+                             sorted_b=self._tes_sorted, out=self.tes_buys_neg_masks.t)
+        if coords is not None:
+            if getattr(self, "_coords_dev", None) is None:
+                c = np.zeros((n_item + 1, 2), dtype=np.float64)
+                c[:n_item] = np.asarray(coords, dtype=np.float64)[:n_item]
+                self._coords_dev = torch.from_numpy(c).to(eng.torch_device)
+            eng.neg_intervals(self.tra_buys_masks.t, self.tra_buys_neg_masks.t, self._lens, self._coords_dev, float(dd_m),
+                              int(dist_num), out=self.tra_dist_neg_masks.t)
+        return self.tra_buys_neg_masks.t
+
     def update_trained_items(self):
         self.trained_items.t = self.lt.t.clone()
 

@@ -74,6 +74,48 @@ def test_driver_matches_oracle_loop(engine, tmp_path, gru):
         assert np.allclose(hist[epoch]["recall"], rec, atol=1e-12), (hist[epoch]["recall"], rec)
 
 
+def test_driver_device_negative_sampling_matches_oracle_loop(engine, tmp_path):
+    """p['gpu_neg'] = 1: epoch >= 1 negatives and their distance intervals are drawn on the device.  The
+    oracle loop is fed oracle/sampling.py's restatement of the same counter-based stream: losses, l2 and Recall@K of
+    both epochs must match exactly as in the host-sampled run."""
+    from oracle import sampling as S
+    from poi_b200 import prog_bpr_gru_spatial as drv
+    from poi_b200 import synth
+    from poi_b200.driver_common import shuffled_users
+    path = _dataset(tmp_path)
+    p = drv.default_params()
+    p.update(dataset="Synth.txt", epochs=2, latent_size=8, gru=2, at_nums=[5, 10], batch_size_test=7, UD=40, dd=2000,
+             gpu_neg=1, neg_seed=77)
+    random.seed(5)
+    pas = drv.Params(p=p, path=path)
+    D = pas.dist_num
+    st = synth.init_state(pas.item_num, 8, 8, D, seed=3)
+    import os
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        model, best, hist = drv.train_valid_or_test(pas, init=st)
+    finally:
+        os.chdir(cwd)
+    P, M = np.asarray(pas.tra_buys_masks), np.asarray(pas.tra_masks)
+    DP = np.asarray(pas.tra_dist_masks)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    Q, DQ = np.asarray(pas.tra_buys_neg_masks), np.asarray(pas.tra_dist_neg_masks)
+    coords = np.zeros((pas.item_num + 1, 2)); coords[:pas.item_num] = np.asarray(pas.pois_cordis)[:pas.item_num]
+    for epoch in range(2):
+        if epoch > 0:
+            Q = S.sample_negatives(P, P, pas.item_num, 77, 2 * epoch)
+            DQ = S.neg_intervals(P, Q, M.sum(1), coords, p['dd'], D)
+            assert np.array_equal(model.tra_buys_neg_masks.get_value(), Q)
+            assert np.array_equal(model.tra_dist_neg_masks.get_value(), DQ)
+        order = shuffled_users(pas.user_num, epoch)
+        loss, l2, ref = OD.epoch_distance2pre(ref, order, P, Q, DP, DQ, M, p['alpha'], p['lambda'])
+        scores = OD.user_scores_distance2pre(ref, P, M, DP, pas.ulptai, D)
+        assert_close(hist[epoch]["loss"], loss, 1e-4, "epoch %d loss" % epoch)
+        assert_close(hist[epoch]["l2"], l2, 1e-4, "epoch %d l2" % epoch)
+        rec = _oracle_recall(scores, pas.tes_buys_masks, p['at_nums'])
+        assert np.allclose(hist[epoch]["recall"], rec, atol=1e-12), (hist[epoch]["recall"], rec)
+
+
 def test_bpr_prme_geoie_drivers_run(engine, tmp_path):
     from poi_b200 import prog_bpr_gru_spatial as d0
     from poi_b200 import prog_geoie as d2
