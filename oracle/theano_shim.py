@@ -302,6 +302,8 @@ class Subtensor(Var):
                 self.ndim = base.ndim
             elif isinstance(idx, Var) and idx.ndim is not None:
                 self.ndim = base.ndim - 1 + idx.ndim
+            elif isinstance(idx, (list, np.ndarray)):
+                self.ndim = base.ndim - 1 + np.ndim(idx)
 
     def compute(self, env):
         return ev(self.base, env)[_resolve_index(self.idx, env)]

@@ -153,6 +153,57 @@ def case_geoie(mods, name):
     save(name, g, losses=np.asarray(losses), l2=np.float64(model.l2.eval()), **final_state(model, names))
 
 
+
+def case_bpr_batch(mods, name="bpr_batch"):
+    """The reference's mini-batch `Bpr` class (BPR.py:341-397): three calls with duplicate users and items."""
+    BPR = mods[2]
+    from oracle import fixtures as Fx
+    rs = np.random.RandomState(21)
+    n_user, n_item, d, n = 9, 40, 12, 14
+    st = Fx.bpr_state(rs, n_user, n_item, d)
+    tb, tm, tn = dummy_test(n_user, n_item)
+    model = BPR.Bpr([tb, tm, tn], [tb, tm, tn], [ALPHA, LAM], n_user, n_item, d, d)
+    for k in ("ux", "lt"):
+        getattr(model, k).set_value(st[k])
+    calls, losses = {}, []
+    for c in range(3):
+        u = rs.randint(0, n_user, n); pi = rs.randint(0, n_item, n); qi = rs.randint(0, n_item, n)
+        pi[3] = pi[1]; u[5] = u[2]                                  # duplicates inside a call
+        mask = (rs.rand(n) < 0.8).astype(np.int32)
+        pi = np.where(mask == 1, pi, n_item); qi = np.where(mask == 1, qi, n_item)      # masked slots hold the pad id
+        losses.append(float(model.train(pi.astype(np.int32), qi.astype(np.int32), mask, u.astype(np.int32))))
+        calls["p%d" % c], calls["q%d" % c], calls["m%d" % c], calls["u%d" % c] = pi, qi, mask, u
+    np.savez_compressed(os.path.join(HERE, "ref_" + name + ".npz"), n_item=np.int64(n_item), losses=np.asarray(losses),
+                        init_ux=st["ux"], init_lt=st["lt"], l2=np.float64(model.l2.eval()), **calls,
+                        **final_state(model, ("ux", "lt")))
+    print("wrote ref_" + name)
+
+
+def case_scores(mods, name="scores"):
+    """compute_sub_all_scores / compute_sub_auc_preference of the reference classes (GRU.py:93-110,
+    GRU_Spatial.py:117-125) on injected trained_* arrays."""
+    GRU, GS = mods[0], mods[1]
+    rs = np.random.RandomState(31)
+    n_user, n_item, d, D, tl = 7, 30, 8, 12, 5
+    tes = rs.randint(0, n_item, size=(n_user, tl)); tes_neg = rs.randint(0, n_item, size=(n_user, tl))
+    tes_m = (np.arange(tl)[None, :] < rs.randint(1, tl + 1, size=(n_user, 1))).astype(np.int32)
+    tes = np.where(tes_m == 1, tes, n_item); tes_neg = np.where(tes_m == 1, tes_neg, n_item)
+    tra = [[0, n_item]] * n_user; tra_m = [[1, 0]] * n_user
+    users = rs.uniform(-0.5, 0.5, (n_user, d)); items = rs.uniform(-0.5, 0.5, (n_item + 1, d))
+    prob = rs.uniform(0, 1, (n_user, n_item)); wd = 0.37
+    g = GRU.OboGru([tra, tra_m, tra], [tes.tolist(), tes_m.tolist(), tes_neg.tolist()], [ALPHA, LAM], n_user, n_item, d, d)
+    g.trained_users.set_value(users); g.trained_items.set_value(items)
+    se = np.array([1, 4, 5, 6], dtype=np.int32)
+    out = dict(gru_scores=g.compute_sub_all_scores(se), gru_auc=g.compute_sub_auc_preference(se))
+    s = GS.OboSpatialGru([tra, tra_m, tra], [tes.tolist(), tes_m.tolist(), tes_neg.tolist()],
+                         [[[D, D]] * n_user, [[D] * tl] * n_user, [[D, D]] * n_user], [ALPHA, LAM], n_user, n_item, [D, 0.2], d, d)
+    s.trained_users.set_value(users); s.trained_items.set_value(items); s.wd.set_value(wd); s.update_prob(prob)
+    out.update(spatial_scores=s.compute_sub_all_scores(se), spatial_auc=s.compute_sub_auc_preference(se))
+    np.savez_compressed(os.path.join(HERE, "ref_" + name + ".npz"), tes=tes, tes_neg=tes_neg, tes_m=tes_m, users=users, items=items,
+                        prob=prob, wd=np.float64(wd), se=se, n_item=np.int64(n_item), n_dist=np.int64(D), **out)
+    print("wrote ref_" + name)
+
+
 def case_host(name="host"):
     """Host-side functions of the reference called directly (pure numpy / Python, no Theano): the per-user metric
     functions of public/Valuate.py:23-99 and the index builders of public/Load_Data_by_length.py:24-42,115-180.
@@ -213,4 +264,6 @@ if __name__ == "__main__":
     case_bpr(mods, "obo_bpr_tiny")
     case_prme(mods, "obo_prme_tiny")
     case_geoie(mods, "geoie_tiny")
+    case_bpr_batch(mods)
+    case_scores(mods)
     case_host()

@@ -33,7 +33,7 @@ def _check(st, final, tol=1e-12):
 
 def test_golden_files_present():
     assert len(glob.glob(os.path.join(G, "*.npz"))) >= 15
-    assert len(glob.glob(os.path.join(G, "ref_*.npz"))) >= 7
+    assert len(glob.glob(os.path.join(G, "ref_*.npz"))) >= 10
 
 
 @pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape", "ref_obo_gru_tiny", "ref_gru_batch2_c1shape"])
@@ -97,3 +97,16 @@ def test_bpr_prme_geoie(pre):
         l, st = OM.geoie_train(st, int(u), z["P"][u], z["Q"][u], z["dpos%d" % k], z["dneg%d" % k], z["msk%d" % k], A, L)
         losses.append(l)
     assert np.allclose(losses, z["losses"], rtol=1e-12); _check(st, final)
+
+
+def test_bpr_minibatch_against_reference_class():
+    """oracle.bpr_train_batch against the reference's `Bpr` class (BPR.py:341-397; tests/golden/ref_bpr_batch.npz)."""
+    z = np.load(os.path.join(G, "ref_bpr_batch.npz"))
+    st = {"ux": np.asarray(z["init_ux"], np.float64), "lt": np.asarray(z["init_lt"], np.float64)}
+    losses = []
+    for c in range(3):
+        l, st = OM.bpr_train_batch(st, z["p%d" % c], z["q%d" % c], z["m%d" % c], z["u%d" % c], A, L)
+        losses.append(l)
+    assert np.allclose(losses, z["losses"], rtol=1e-12)
+    assert np.max(np.abs(st["ux"] - z["final_ux"])) < 1e-13 and np.max(np.abs(st["lt"] - z["final_lt"])) < 1e-13
+    assert abs(OM.l2_value(st, ["ux", "lt"], L) - float(z["l2"])) < 1e-12

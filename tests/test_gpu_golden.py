@@ -101,3 +101,40 @@ def test_mf_geoie_golden(engine, pre):
     assert_close(losses, z["losses"], RTOL, "geoie losses")
     for k in ("g", "h", "z", "t"):
         assert_close(getattr(m, k).get_value(), final[k], RTOL, k)
+
+
+def test_bpr_minibatch_reference_golden(engine):
+    """`Bpr.train` (poi_bpr_train_batch) against the reference's mini-batch `Bpr` class (ref_bpr_batch.npz)."""
+    from poi_b200.public.BPR import Bpr
+    z = np.load(os.path.join(G, "ref_bpr_batch.npz"))
+    init = {"ux": np.asarray(z["init_ux"]), "lt": np.asarray(z["init_lt"])}
+    n_user, n_item, d = init["ux"].shape[0], int(z["n_item"]), init["ux"].shape[1]
+    t = _test_side(n_user, n_item)
+    m = Bpr([t[0], t[1], t[2]], t, [A, L], n_user, n_item, d, d, init=init)
+    losses = [m.train(z["p%d" % c].astype(np.int32), z["q%d" % c].astype(np.int32), z["m%d" % c].astype(np.int32),
+                      z["u%d" % c].astype(np.int32)) for c in range(3)]
+    assert_close(losses, z["losses"], RTOL, "losses")
+    assert_close(m.ux.get_value(), z["final_ux"], RTOL, "ux"); assert_close(m.lt.get_value(), z["final_lt"], RTOL, "lt")
+    assert_close(m.l2.eval(), float(z["l2"]), RTOL, "l2")
+
+
+def test_scores_and_auc_preference_reference_golden(engine):
+    """compute_sub_all_scores / compute_sub_auc_preference (GRU.py:93-110, GRU_Spatial.py:117-125) against the
+    reference classes' own output (ref_scores.npz); the AUC preference matrix is boolean -> exact."""
+    from poi_b200.public.GRU import OboGru
+    from poi_b200.public.GRU_Spatial import OboSpatialGru
+    z = np.load(os.path.join(G, "ref_scores.npz"))
+    n_user, d = z["users"].shape
+    n_item, D = int(z["n_item"]), int(z["n_dist"])
+    tra, tra_m = [[0, n_item]] * n_user, [[1, 0]] * n_user
+    test = [z["tes"].tolist(), z["tes_m"].tolist(), z["tes_neg"].tolist()]
+    se = z["se"]
+    g = OboGru([tra, tra_m, tra], test, [A, L], n_user, n_item, d, d)
+    g.trained_users.set_value(z["users"]); g.trained_items.set_value(z["items"])
+    assert_close(g.compute_sub_all_scores(se), z["gru_scores"], 1e-5, "gru scores")
+    assert np.array_equal(np.asarray(g.compute_sub_auc_preference(se)), z["gru_auc"])
+    s = OboSpatialGru([tra, tra_m, tra], test, [[[D, D]] * n_user, [[D] * z["tes"].shape[1]] * n_user, [[D, D]] * n_user],
+                      [A, L], n_user, n_item, [D, 0.2], d, d)
+    s.trained_users.set_value(z["users"]); s.trained_items.set_value(z["items"]); s.wd.set_value(float(z["wd"])); s.update_prob(z["prob"])
+    assert_close(s.compute_sub_all_scores(se), z["spatial_scores"], 1e-5, "spatial scores")
+    assert np.array_equal(np.asarray(s.compute_sub_auc_preference(se)), z["spatial_auc"])
