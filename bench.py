@@ -375,6 +375,10 @@ def run_ours(args):
                               "algorithmic_bytes_per_step": by, "ms_per_step": r["ms"] / nprof,
                               "traffic": traffic.get(k, {}).get("dram_bytes"),
                               "note": "table (20 MB) is L2-resident at this config; ncu DRAM traffic in profiles/"}
+    if roof["bound"] == "tensor" and args.gemm_mode == 1:
+        roof["ceiling_frac"] = 1.0 / 6.0
+        roof["ceiling_note"] = ("fp32-faithful 3xTF32: three tf32 products per algorithmic product at half the bf16 rate -> "
+                                "at most 1/6 of the bf16 peak; the category also holds the latency-bound recurrence kernels")
     if roof["kernel"] in traffic:
         roof["traffic"] = traffic[roof["kernel"]]["dram_bytes"]
         roof["traffic_note"] = "ncu capture of the largest launch of this kernel (%s)" % traffic[roof["kernel"]]["kernel"]

@@ -64,6 +64,11 @@ int         poi_set_fused_recurrence(poi_engine* e, int on);
 /* CTAs per 128 users in the fused recurrence kernels (thread-block cluster splitting the gate columns, next
  * operand exchanged through distributed shared memory): 0 = auto (default), 1, 2 or 4. */
 int         poi_set_fused_cluster(poi_engine* e, int cl);
+/* poi_gru_train calls with B <= 8 (the reference's one-by-one mode) are captured into a CUDA graph the second time a
+ * shape is seen and replayed afterwards (1 = default); 0 = always launch kernel by kernel.  poi_graph_replays: how
+ * many calls were served by a graph launch. */
+int         poi_set_graph_mode(poi_engine* e, int on);
+int         poi_graph_replays(poi_engine* e, int64_t* out);
 /* tensor-core modes only: 1 (default) = the weight-gradient GEMMs read the activation matrices as they lie in
  * memory (MN-major tcgen05 operands; bias gradients fused into the same pass), 0 = transposed copies + K-major
  * operands + a separate column-sum pass (kept for A/B measurements) */

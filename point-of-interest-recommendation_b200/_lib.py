@@ -53,6 +53,8 @@ _PROTOS = {
     "poi_get_gemm_mode": (c_int, [_E, POINTER(c_int)]),
     "poi_set_fused_recurrence": (c_int, [_E, c_int]),
     "poi_set_fused_cluster": (c_int, [_E, c_int]),
+    "poi_set_graph_mode": (c_int, [_E, c_int]),
+    "poi_graph_replays": (c_int, [_E, POINTER(c_int64)]),
     "poi_set_wgrad_mn": (c_int, [_E, c_int]),
     "poi_gather_rows": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "poi_unique": (c_int, [_E, c_void_p, c_int64, c_int32, c_void_p, c_void_p, POINTER(c_int64)]),

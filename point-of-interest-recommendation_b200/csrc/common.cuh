@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <unordered_map>
 #include <algorithm>
 
 #include "../../include/poi_engine.h"
@@ -48,6 +49,15 @@ struct poi_engine {
     bool prep_valid = false;
     int prep_B = 0, prep_lmax = 0;
     void* prep_state = nullptr;      // MgPrep*, owned
+    // CUDA-graph replay of small-batch train calls (the reference's one-by-one mode): one instantiated graph per
+    // (parameter pointers, batch size, max length, modes); valid while the arena has not been re-allocated
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0; int warm = 0; int64_t n_launch = 0; };
+    std::unordered_map<uint64_t, GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;
+    bool capturing = false;
+    int graph_mode = 1;              // 1 = replay train calls with B <= 8 as CUDA graphs, 0 = always launch kernel by kernel
+    uint64_t arena_gen = 0;          // bumped whenever the arena is (re)allocated
+    int64_t graph_replays = 0;
     // phase timing
     bool timing = false;
     cudaEvent_t ev[9] = {};
@@ -133,6 +143,7 @@ static int arena_reset(poi_engine* e) {
         char* p = nullptr;
         POI_CK(e, cudaMalloc(&p, total));
         e->chunks.push_back({p, total});
+        e->arena_gen++;
     }
     e->cur_chunk = 0; e->cur_off = 0; e->call_bytes = 0;
     return 0;
@@ -155,8 +166,10 @@ static int arena_alloc(poi_engine* e, size_t bytes, void** out) {
         }
         size_t cap = poi_align_up(std::max(bytes, (size_t)64 << 20), (size_t)1 << 20);
         char* p = nullptr;
+        if (e->capturing) POI_FAIL(e, "arena would grow during graph capture");
         POI_CK(e, cudaMalloc(&p, cap));
         e->chunks.push_back({p, cap});
+        e->arena_gen++;
     }
 }
 

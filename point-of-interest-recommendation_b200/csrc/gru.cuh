@@ -623,6 +623,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
 
     POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     phase_mark(e, 8);
+    if (e->capturing) return 0;          // graph capture (poi_gru_train): the caller launches the graph and synchronises
     POI_CK(e, cudaStreamSynchronize(e->stream));
     if (e->kprof) prof_harvest(e);
     if (out_host) for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];
@@ -647,7 +648,8 @@ static int gru_upload_i32(poi_engine* e, const int32_t* host, size_t n, int32_t*
     // page-locked caller memory goes to the device directly (the call synchronises before it returns, so the
     // buffer outlives the copy); pageable memory is staged through the engine's pinned buffer
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+    // (while a graph is being captured everything goes through the engine's own pinned buffer: the replay refreshes it)
+    if (!e->capturing && cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) {
         POI_CK(e, cudaMemcpyAsync(*dev, host, n * 4, cudaMemcpyHostToDevice, e->stream));
         return 0;
     }

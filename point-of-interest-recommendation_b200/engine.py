@@ -151,6 +151,15 @@ class Engine:
         """CTAs per 128 users in the fused recurrence kernels: 0 auto, 1, 2 or 4."""
         self._ck(lib.poi_set_fused_cluster(self._h, int(cl)))
 
+    def set_graph_mode(self, on: bool):
+        """CUDA-graph replay of train calls with B <= 8 (the reference's one-by-one mode); default on."""
+        self._ck(lib.poi_set_graph_mode(self._h, 1 if on else 0))
+
+    def graph_replays(self) -> int:
+        n = c_int64()
+        self._ck(lib.poi_graph_replays(self._h, byref(n)))
+        return n.value
+
     def set_wgrad_mn(self, on: bool):
         self._ck(lib.poi_set_wgrad_mn(self._h, 1 if on else 0))
 

@@ -289,3 +289,28 @@ def test_edge_cases_length_one_and_two(engine):
     got = state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"])
     for k in got:
         assert_close(got[k], ref[k], RTOL, k)
+
+
+def test_obo_graph_replay_is_bit_identical(engine):
+    """One-by-one calls (B = 1) are served from CUDA graphs after the second sight of a shape: the trajectory over three
+    passes of the users must be bit-identical to kernel-by-kernel launches, and replays must actually happen."""
+    from poi_b200.public.GRU_Spatial import OboSpatialGru
+    rs = np.random.RandomState(41)
+    n_user, n_item, d, lmax, n_dist = 9, 400, 64, 20, 200
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    order = [u for _ in range(3) for u in range(n_user)] + [3, 3, 3]
+    res = []
+    try:
+        for graphs in (False, True):
+            engine.set_graph_mode(graphs)
+            r0 = engine.graph_replays()
+            m = OboSpatialGru([P, M, Q], test, [DP, [[n_dist]] * n_user, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+            outs = [m.train(u)[:3] for u in order]
+            res.append((np.asarray(outs), state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"]),
+                        engine.graph_replays() - r0))
+    finally:
+        engine.set_graph_mode(True)
+    assert res[0][2] == 0 and res[1][2] >= len(order) - 2 * n_user
+    assert np.array_equal(res[0][0], res[1][0])
+    for k in res[0][1]:
+        assert np.array_equal(res[0][1][k], res[1][1][k]), k
