@@ -68,6 +68,9 @@ int         poi_set_fused_cluster(poi_engine* e, int cl);
  * shape is seen and replayed afterwards (1 = default); 0 = always launch kernel by kernel.  poi_graph_replays: how
  * many calls were served by a graph launch. */
 int         poi_set_graph_mode(poi_engine* e, int on);
+/* Batches of <= 8 users (the reference's one-by-one mode) run the recurrence on SIMT kernels that keep Wh in shared
+ * memory (csrc/gru_small.cuh; exact fp32 FMA) instead of a 128-row tensor-core tile: 1 = default, 0 = off. */
+int         poi_set_small_batch_path(poi_engine* e, int on);
 int         poi_graph_replays(poi_engine* e, int64_t* out);
 /* tensor-core modes only: 1 (default) = the weight-gradient GEMMs read the activation matrices as they lie in
  * memory (MN-major tcgen05 operands; bias gradients fused into the same pass), 0 = transposed copies + K-major

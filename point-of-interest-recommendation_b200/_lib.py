@@ -54,6 +54,7 @@ _PROTOS = {
     "poi_set_fused_recurrence": (c_int, [_E, c_int]),
     "poi_set_fused_cluster": (c_int, [_E, c_int]),
     "poi_set_graph_mode": (c_int, [_E, c_int]),
+    "poi_set_small_batch_path": (c_int, [_E, c_int]),
     "poi_graph_replays": (c_int, [_E, POINTER(c_int64)]),
     "poi_set_wgrad_mn": (c_int, [_E, c_int]),
     "poi_gather_rows": (c_int, [_E, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),

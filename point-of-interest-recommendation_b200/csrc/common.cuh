@@ -28,6 +28,7 @@ struct poi_engine {
     int gemm_mode = 1;               // default: tcgen05 3xTF32 (fp32-faithful); 0 = fp32 FMA, 2 = 1xTF32
     bool persistent_gemm = true;     // large tensor-core GEMMs: persistent CTAs, epilogue overlapped with the next tile
     bool wgrad_mn = true;            // tensor-core weight gradients read the activations as they lie (MN-major UMMA operands, no transposes)
+    bool small_batch_path = true;    // B <= 8: SIMT recurrence kernels with Wh resident in shared memory (gru_small.cuh)
     int fused_cluster = 0;           // CTAs per 128 users in the fused recurrence: 0 = auto, else 1 / 2 / 4
     bool fuse_recurrence = true;     // tensor-core modes: forward recurrence as one persistent fused kernel (gru_fused.cuh)
     // bump arena (device scratch owned by the engine); reset at the start of every call

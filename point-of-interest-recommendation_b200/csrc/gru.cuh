@@ -17,6 +17,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gru_fused.cuh"
+#include "gru_small.cuh"
 #include <string.h>
 
 // ---------------------------------------------------------------------------------------------
@@ -434,6 +435,11 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
     phase_mark(e, 2);
     // hoisted input projection: AX = X . ui^T + bi over every (t, b)
     POI_TRY(gemm_tn(e, X, din, p->ui, din, TB, 3 * H, din, EpiBiasStore{AX, 3 * H, p->bi, 3 * H}));
+    if (e->small_batch_path && small::supported(B, H)) {
+        // tiny batches (the reference's one-by-one mode): one CTA per user, Wh resident in shared memory (gru_small.cuh)
+        POI_TRY(small::launch_fwd(e, AX, p->wh, Hs, Z, R, C, RH, B, T, H));
+        return 0;
+    }
     if (e->gemm_mode != 0 && e->fuse_recurrence && fused::fwd_supported(H)) {
         // the whole recurrence in one persistent tcgen05 kernel (gru_fused.cuh)
         POI_TRY(fused::launch_gru_fwd_fused(e, AX, p->wh, Hs, Z, R, C, RH, B, T, H, e->gemm_mode == 1));
@@ -518,7 +524,9 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
             POI_CAT(e, CAT_ELTWISE, 0, 0);
             POI_LAUNCH(e, k_dhl_nohead, (unsigned)poi_cdiv(TB * (H / 4), 256), 256, 0, ev, XDiff, DHl, TB, H / 4);
         }
-        if (e->gemm_mode != 0 && e->fuse_recurrence && fused::fwd_supported(H) && H <= 128) {
+        if (e->small_batch_path && small::supported(B, H)) {
+            POI_TRY(small::launch_bwd(e, DHl, Z, R, C, Hs, p->wh, DA, B, T, H));
+        } else if (e->gemm_mode != 0 && e->fuse_recurrence && fused::fwd_supported(H) && H <= 128) {
             // BPTT through the cell as one persistent tcgen05 kernel (gru_fused.cuh); dh never leaves the SM
             POI_TRY(fused::launch_gru_bwd_fused(e, DHl, Z, R, C, Hs, p->wh, DA, B, T, H, e->gemm_mode == 1));
         } else {

@@ -72,6 +72,7 @@ int poi_set_gemm_mode(poi_engine* e, int mode) {
 }
 int poi_get_gemm_mode(poi_engine* e, int* mode) { *mode = e->gemm_mode; return 0; }
 int poi_set_fused_recurrence(poi_engine* e, int on) { e->fuse_recurrence = on != 0; return 0; }
+int poi_set_small_batch_path(poi_engine* e, int on) { e->small_batch_path = on != 0; return 0; }
 int poi_set_graph_mode(poi_engine* e, int on) { e->graph_mode = on != 0; return 0; }
 int poi_graph_replays(poi_engine* e, int64_t* out) { *out = e->graph_replays; return 0; }
 int poi_set_fused_cluster(poi_engine* e, int cl) {
@@ -201,7 +202,7 @@ int poi_gru_train(poi_engine* e, const poi_gru_params* p, const poi_seq_index* i
 
     uint64_t key = 1469598103934665603ull;
     key = fnv1a(key, p, sizeof(*p)); key = fnv1a(key, index, sizeof(*index));
-    const int32_t modes[6] = {B, max_len, e->gemm_mode, (int32_t)e->fuse_recurrence | ((int32_t)e->persistent_gemm << 1) | ((int32_t)e->wgrad_mn << 2),
+    const int32_t modes[6] = {B, max_len, e->gemm_mode, (int32_t)e->fuse_recurrence | ((int32_t)e->persistent_gemm << 1) | ((int32_t)e->wgrad_mn << 2) | ((int32_t)e->small_batch_path << 3),
                               e->fused_cluster, 0};
     key = fnv1a(key, modes, sizeof(modes)); key = fnv1a(key, &alpha, 4); key = fnv1a(key, &lambda, 4);
     const void* strm = e->stream; key = fnv1a(key, &strm, sizeof(strm));

@@ -155,6 +155,10 @@ class Engine:
         """CUDA-graph replay of train calls with B <= 8 (the reference's one-by-one mode); default on."""
         self._ck(lib.poi_set_graph_mode(self._h, 1 if on else 0))
 
+    def set_small_batch_path(self, on: bool):
+        """B <= 8: SIMT recurrence kernels with Wh resident in shared memory (default on)."""
+        self._ck(lib.poi_set_small_batch_path(self._h, 1 if on else 0))
+
     def graph_replays(self) -> int:
         n = c_int64()
         self._ck(lib.poi_graph_replays(self._h, byref(n)))

@@ -314,3 +314,32 @@ def test_obo_graph_replay_is_bit_identical(engine):
     assert np.array_equal(res[0][0], res[1][0])
     for k in res[0][1]:
         assert np.array_equal(res[0][1][k], res[1][1][k]), k
+
+
+@pytest.mark.parametrize("B,d", [(1, 128), (5, 64), (8, 20)])
+def test_small_batch_simt_path_matches_tensor_core_path(engine, B, d):
+    """B <= 8 runs the recurrence on the SIMT kernels of gru_small.cuh (exact fp32); switching them off sends the same
+    calls through the fused tcgen05 kernels.  Both must hold the 1e-4 bar against the oracle and agree with each other."""
+    from poi_b200.public.GRU_Spatial import SpatialGru
+    rs = np.random.RandomState(300 + B + d)
+    n_user, n_item, lmax, n_dist = 16, 900, 19, 60
+    P, Q, M, DP, DQ, st, test = _mk(rs, n_user, n_item, d, lmax, n_dist)
+    outs = {}
+    try:
+        for small in (True, False):
+            engine.set_small_batch_path(small)
+            m = SpatialGru([P, M, Q], test, [DP, [[n_dist]] * n_user, DQ], [ALPHA, LAM], n_user, n_item, [n_dist, 0.2], d, d, init=st)
+            ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+            for s0 in range(0, n_user - B + 1, B):
+                se = np.arange(s0, s0 + B, dtype=np.int32)
+                los, sur, upq, ls = m.train(se)
+                (rl, rs_, ru, rw), ref = E.gru_family_train_batch(ref, P[se], Q[se], M[se], ALPHA, LAM, DP[se], DQ[se])
+                assert_close([los, sur, upq], [rl, rs_, ru], RTOL, "losses (small=%s)" % small)
+            got = state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
+            for k in got:
+                assert_close(got[k], ref[k], RTOL, "%s (small=%s)" % (k, small))
+            outs[small] = got
+    finally:
+        engine.set_small_batch_path(True)
+    for k in outs[True]:
+        assert_close(outs[True][k], outs[False][k], 2e-5, k)
