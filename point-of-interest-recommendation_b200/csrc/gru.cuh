@@ -225,6 +225,8 @@ __global__ void k_dhl_nohead(const float* __restrict__ ev, const float* __restri
 // Writes e = d cost/d upq and, over the logits in place, do = d cost / d logits.
 // Block partial sums of (sur, bpr, gwd) go to part[block][4] in fp64 (fixed order).
 // ---------------------------------------------------------------------------------------------
+constexpr int LOSS_RK = 8;          // logits per lane kept in registers by k_loss_head (rows up to 256 wide)
+
 __global__ void __launch_bounds__(256)
 k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc,
             const float* __restrict__ XDiff, int H4, const int32_t* __restrict__ DPt,
@@ -261,6 +263,53 @@ k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc
                 for (int k = lane; k < nDp; k += 32) row[k] = 0.f;
             } else {
                 const int P = DPt[(int64_t)(j + 1) * B + b], Q = DQt[(int64_t)(j + 1) * B + b];
+                if (nDp <= 32 * LOSS_RK) {
+                    // the whole row lives in registers (<= LOSS_RK values per lane): one read, one exp per logit, one write
+                    float v[LOSS_RK];
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < LOSS_RK; ++i) {
+                        const int k = lane + 32 * i;
+                        v[i] = k < nD ? row[k] : -INFINITY;
+                        mx = fmaxf(mx, v[i]);
+                    }
+                    mx = warp_max(mx);
+                    float sum = 0.f, cumr = 0.f, eP = 0.f, eQ = 0.f;
+#pragma unroll
+                    for (int i = 0; i < LOSS_RK; ++i) {
+                        const int k = lane + 32 * i;
+                        const float ex = k < nD ? expf(v[i] - mx) : 0.f;
+                        v[i] = ex;
+                        sum += ex;
+                        if (k <= P) cumr += ex;
+                        if (k == P) eP = ex;
+                        if (k == Q) eQ = ex;
+                    }
+                    sum = warp_sum(sum); cumr = warp_sum(cumr); eP = warp_sum(eP); eQ = warp_sum(eQ);
+                    const float inv = 1.f / sum;
+                    const float sP = eP * inv, sQ = eQ * inv, cum = cumr * inv;
+                    const float u = dot + wd * (sP - sQ);
+                    e_ = -w1 * sigmoidf_(-u) * scale;
+                    bpr = logsigmoidf_(u);
+                    sur = cum - logf(sP);
+                    gwd = e_ * (sP - sQ);
+                    const float Ac = w0 * scale, Bc = e_ * wd;
+                    const float gs = Ac * cum - Ac + Bc * (sP - sQ);
+                    const float aP = Ac / sP;
+#pragma unroll
+                    for (int i = 0; i < LOSS_RK; ++i) {
+                        const int k = lane + 32 * i;
+                        if (k < nDp) {
+                            float o = 0.f;
+                            if (k < nD) {
+                                const float sk = v[i] * inv;
+                                const float g = (k <= P ? Ac : 0.f) - (k == P ? aP : 0.f) + Bc * ((k == P ? 1.f : 0.f) - (k == Q ? 1.f : 0.f));
+                                o = sk * (g - gs);
+                            }
+                            row[k] = o;
+                        }
+                    }
+                } else {
                 float mx = -INFINITY;
                 for (int k = lane; k < nD; k += 32) mx = fmaxf(mx, row[k]);
                 mx = warp_max(mx);
@@ -291,6 +340,7 @@ k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc
                         o = s * (g - gs);
                     }
                     row[k] = o;
+                }
                 }
             }
         } else if (valid) {

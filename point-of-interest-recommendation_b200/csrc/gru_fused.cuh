@@ -104,51 +104,80 @@ __device__ __forceinline__ void umma_commit_cl(uint64_t* bar) {
     else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                       ::"r"(smem_u32(bar)), "h"((uint16_t)((1u << CL) - 1)) : "memory");
 }
-// this CTA's k-blocks of the A tile (hi, and lo for 3xTF32) -> the same offsets in every peer CTA's shared memory;
-// bytes complete on the peer's a_ready[this rank] barrier.  One thread.
+// this CTA's k-blocks of the next A operand -> the same offsets of the hi half of every peer CTA's A tile; bytes complete
+// on the peer's a_ready[this rank] barrier.  3xTF32: the slice travels UNSPLIT (the fp32 values from `send`, half the
+// bytes of hi + lo -- the DSMEM transfer is what the GEMMs wait for) and the receiver splits it in place
+// (convert_incoming); 1xTF32: the hi tile itself is the slice.  One thread.
 template <bool SPLIT3, int CL>
-__device__ __forceinline__ void send_slice(uint32_t a_hi, uint32_t a_lo, uint32_t slice_off, uint32_t slice_bytes,
+__device__ __forceinline__ void send_slice(uint32_t a_hi, uint32_t send, uint32_t slice_off, uint32_t slice_bytes,
                                            uint64_t* a_ready, int cr) {
     const uint32_t bar = smem_u32(&a_ready[cr]);
+    const uint32_t src = SPLIT3 ? send : a_hi + slice_off;
 #pragma unroll
     for (int i = 1; i < CL; ++i) {
         const uint32_t r = (uint32_t)((cr + i) % CL);
-        const uint32_t rbar = mapa_u32(bar, r);
         asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(mapa_u32(a_hi + slice_off, r)), "r"(a_hi + slice_off), "r"(slice_bytes), "r"(rbar) : "memory");
-        if (SPLIT3)
-            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(mapa_u32(a_lo + slice_off, r)), "r"(a_lo + slice_off), "r"(slice_bytes), "r"(rbar) : "memory");
+                     ::"r"(mapa_u32(a_hi + slice_off, r)), "r"(src), "r"(slice_bytes), "r"(mapa_u32(bar, r)) : "memory");
     }
 }
 // MMA thread, once per operand hand-over: the local slice is staged (s_done); arm one transaction barrier per peer
 // and push the local slice to the peers.  The GEMM that follows starts on the LOCAL k-blocks at once and waits for
-// each peer's k-blocks (a_ready[owner]) only when it reaches them, so the transfer overlaps the MMAs.
+// each peer's k-blocks only when it reaches them, so the transfer overlaps the MMAs.
 template <bool SPLIT3, int CL>
 __device__ __forceinline__ void begin_exchange(uint64_t* s_done, uint32_t& ps, uint64_t* a_ready,
-                                               uint32_t a_hi, uint32_t a_lo, uint32_t slice_off, uint32_t slice_bytes, int cr,
+                                               uint32_t a_hi, uint32_t send, uint32_t slice_off, uint32_t slice_bytes, int cr,
                                                bool exchange) {
     mbar_wait(s_done, ps & 1); ++ps;
     if (CL > 1 && exchange) {
-        const uint32_t expect = slice_bytes * (SPLIT3 ? 2u : 1u);
 #pragma unroll
         for (int o = 0; o < CL; ++o)
             if (o != cr)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&a_ready[o])), "r"(expect) : "memory");
-        send_slice<SPLIT3, CL>(a_hi, a_lo, slice_off, slice_bytes, a_ready, cr);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&a_ready[o])), "r"(slice_bytes) : "memory");
+        send_slice<SPLIT3, CL>(a_hi, send, slice_off, slice_bytes, a_ready, cr);
     }
     tc_fence_after();
 }
+// Epilogue threads, after they have staged their own slice: as each peer's unsplit slice lands in the hi half of the A
+// tile (arrival order: owner cr-1, cr-2, ...), split it in place into hi / lo and tell the MMA thread (conv_done[owner]).
+// Thread (row, hf) converts columns [16 hf, 16 hf + 16) of its row in every k-block of the owner.
+template <bool SPLIT3, int CL>
+__device__ __forceinline__ void convert_incoming(uint64_t* a_ready, uint64_t* conv_done, uint32_t& pc, uint32_t a_hi, uint32_t a_lo,
+                                                 int cr, int KBc, int row, int hf) {
+    if (CL == 1 || !SPLIT3) return;
+#pragma unroll
+    for (int i = 1; i < CL; ++i) {
+        const int o = (cr - i + CL) % CL;
+        mbar_wait_cl(&a_ready[o], pc & 1);
+        for (int kbl = 0; kbl < KBc; ++kbl) {
+            const uint32_t base = (uint32_t)(o * KBc + kbl) * A_KB_BYTES + row * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t off = base + (((hf * 4 + q) ^ (row & 7)) << 4);
+                float4 hi, lo;
+                split4(lds4(a_hi + off), hi, lo);
+                sts4(a_hi + off, hi); sts4(a_lo + off, lo);
+            }
+        }
+        fence_async_smem();
+        mbar_arrive(&conv_done[o]);
+    }
+    ++pc;
+}
 
+// send != 0: also the unsplit values into the send buffer (k-block kb - kb0 of the slice this CTA owns)
 template <bool SPLIT3>
-__device__ __forceinline__ void a_store16(uint32_t a_hi, uint32_t a_lo, int row, int col, const float (&v)[16]) {
+__device__ __forceinline__ void a_store16(uint32_t a_hi, uint32_t a_lo, int row, int col, const float (&v)[16],
+                                          uint32_t send = 0u, int kb0 = 0) {
     const int kb = col >> 5, cc0 = (col & 31) >> 2;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const uint32_t off = kb * A_KB_BYTES + row * 128 + (((cc0 + q) ^ (row & 7)) << 4);
+        const uint32_t in_kb = row * 128 + (((cc0 + q) ^ (row & 7)) << 4);
+        const uint32_t off = kb * A_KB_BYTES + in_kb;
         float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        if (SPLIT3) { float4 hi, lo; split4(x, hi, lo); sts4(a_hi + off, hi); sts4(a_lo + off, lo); }
-        else sts4(a_hi + off, x);
+        if (SPLIT3) {
+            float4 hi, lo; split4(x, hi, lo); sts4(a_hi + off, hi); sts4(a_lo + off, lo);
+            if (send) sts4(send + (kb - kb0) * A_KB_BYTES + in_kb, x);
+        } else sts4(a_hi + off, x);
     }
 }
 // exact fp32 values of the A tile (hi + lo is exact by construction)
@@ -228,9 +257,9 @@ template <bool SPLIT3, int CL>
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, float* __restrict__ Hs, float* __restrict__ Z,
                 float* __restrict__ R, float* __restrict__ C, int B, int T, int H) {
-    constexpr int WST = CL == 1 ? 2 : (CL == 2 ? 3 : 4);
+    constexpr int WST = CL == 4 ? 4 : 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[2][AX_STAGES], ax_empty[2][AX_STAGES], s_done, a_ready[CL], d1_full, d2_full;
+    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[2][AX_STAGES], ax_empty[2][AX_STAGES], s_done, a_ready[CL], conv_done[CL], d1_full, d2_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cr = CL == 1 ? 0 : (int)cluster_ctarank();      // this CTA's slice of the gate columns
@@ -242,6 +271,9 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
     const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
     const uint32_t ax_base = w_base + WST * w_stage;           // [half][stage] tiles of AX_TILE bytes
+    const int KBc = Hc >> 5;                                    // k-blocks of the operand this CTA owns
+    // unsplit copy of the own slice, the source of the bulk copies to the peers (3xTF32 clusters only)
+    const uint32_t send = (CL > 1 && SPLIT3) ? ax_base + 2 * AX_STAGES * AX_TILE : 0u;
     const int m0 = (blockIdx.x / CL) * FM;
     const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
     uint32_t ncols = 32; while (ncols < (uint32_t)(3 * Hc)) ncols <<= 1;
@@ -255,7 +287,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&ax_full[h][s], 32); mbar_init(&ax_empty[h][s], 128); }
         mbar_init(&s_done, 256); mbar_init(&d1_full, CL);
 #pragma unroll
-        for (int o = 0; o < CL; ++o) mbar_init(&a_ready[o], 1);
+        for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], 1); mbar_init(&conv_done[o], 256); }
         mbar_init(&d2_full, CL);
         fence_barrier_init();
     }
@@ -284,6 +316,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);
         }
         int64_t axi = 0;                                       // position in this half's AX ring
+        uint32_t pc = 0;                                       // operand hand-overs converted so far (barrier phase)
         // wait for the next AX tile, read this thread's row, return this warp's 2 KB slice of the tile (free to
         // be reused as output staging once the whole warp has read) and the barrier to release it on
         auto ax_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
@@ -326,13 +359,14 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 }
                 tmem_st16(tmem + tl + (uint32_t)lc0, dz);             // stash z
                 tmem_st16(tmem + tl + (uint32_t)(Hc + lc0), b);       // stash (1-z)*h_prev
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, a);
+                a_store16<SPLIT3>(a_hi, a_lo, row, c0, a, send, cr * KBc);
                 warp_store_chunk(sl_z, lane, dz, Z + wrow * H + c0, H, rows_valid);
                 warp_store_chunk(sl_r, lane, dr, R + wrow * H + c0, H, rows_valid);
                 mbar_arrive(rel_z); mbar_arrive(rel_r);
             }
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 5 : 9);
-            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the r*h tile is in place everywhere
+            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the r*h slice is staged
+            convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);     // the peers' r*h slices
             // ---- epilogue 2: c, h_t ----
             if (CL == 1) mbar_wait(&d2_full, j & 1); else mbar_wait_cl(&d2_full, j & 1);
             tc_fence_after();
@@ -351,13 +385,14 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                     dc[i] = cc;
                     u[i] = ok ? u[i] + zz[i] * cc : 0.f;   // h_t = (1-z) h_prev + z c
                 }
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, u);
+                a_store16<SPLIT3>(a_hi, a_lo, row, c0, u, send, cr * KBc);
                 warp_store_chunk(sl, lane, dc, C + wrow * H + c0, H, rows_valid);
                 warp_store_chunk(sl, lane, u, Hs + (wrow + B) * H + c0, H, rows_valid);
                 mbar_arrive(rel);
             }
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 7 : 11);
-            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the h_t tile is in place everywhere
+            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the h_t slice is staged
+            if (j + 1 < T) convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);   // the peers' h_t slices
         }
     } else if (warp < 10) {
         // ================================ AX producers (one warp per column half, cp.async) ================================
@@ -385,7 +420,6 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
         if (lane == 0) {
             // ================================ MMA issuer ================================
             int64_t ws = 0; uint32_t pa = 0, ps = 0;
-            const int KBc = Hc >> 5;                            // k-blocks per owner
             const uint32_t slice_off = (uint32_t)cr * KBc * A_KB_BYTES, slice_bytes = (uint32_t)KBc * A_KB_BYTES;
             // one GEMM over K = H in ARRIVAL order: own k-blocks first, then owner cr-1, cr-2, ... (the order the
             // peers send in); `tiles_per_kb` W tiles per k-block, accumulators dcol0 + t * Hc.  The Wh image of this
@@ -393,7 +427,10 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             auto gemm = [&](uint32_t dcol0, int tiles_per_kb, bool exchanged, int j, int slot) {
                 for (int i = 0; i < CL; ++i) {
                     const int o = (cr - i + CL) % CL;
-                    if (CL > 1 && i > 0 && exchanged) { mbar_wait_cl(&a_ready[o], pa & 1); tc_fence_after(); }
+                    if (CL > 1 && i > 0 && exchanged) {
+                        if (SPLIT3) mbar_wait(&conv_done[o], pa & 1); else mbar_wait_cl(&a_ready[o], pa & 1);
+                        tc_fence_after();
+                    }
                     for (int kbl = 0; kbl < KBc; ++kbl) {
                         const int kb = o * KBc + kbl;
                         for (int t = 0; t < tiles_per_kb; ++t, ++ws) {
@@ -413,12 +450,12 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             };
             for (int j = 0; j < T; ++j) {
                 // h_{j-1}: own slice staged (j = 0: the zero tile, nothing to exchange)
-                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, a_lo, slice_off, slice_bytes, cr, j > 0);
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, j > 0);
                 FTR(0, j, 0);
                 gemm(0u, 2, j > 0, j, 13);                      // D1z | D1r
                 umma_commit_cl<CL>(&d1_full);
                 FTR(0, j, 1);
-                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, a_lo, slice_off, slice_bytes, cr, true);   // r*h
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, true);   // r*h
                 FTR(0, j, 2);
                 gemm((uint32_t)(2 * Hc), 1, true, j, 14);       // D2
                 umma_commit_cl<CL>(&d2_full);
@@ -484,9 +521,9 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, const float* __restrict__ R,
                 const float* __restrict__ C, const float* __restrict__ Hs, const uint8_t* __restrict__ wimg,
                 float* __restrict__ DA, int B, int T, int H) {
-    constexpr int WST = CL == 1 ? 2 : (CL == 2 ? 3 : 4);
+    constexpr int WST = CL == 4 ? 4 : 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[WST], w_empty[WST], in_full[2][AX_STAGES], in_empty[2][AX_STAGES], s_done, a_ready[CL], dm_full, dh1_done, ddh_full;
+    __shared__ uint64_t w_full[WST], w_empty[WST], in_full[2][AX_STAGES], in_empty[2][AX_STAGES], s_done, a_ready[CL], conv_done[CL], dm_full, dh1_done, ddh_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cr = CL == 1 ? 0 : (int)cluster_ctarank();
@@ -498,6 +535,8 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
     const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
     const uint32_t in_base = w_base + WST * w_stage;
+    const int KBc = Hc >> 5;
+    const uint32_t send = (CL > 1 && SPLIT3) ? in_base + 2 * AX_STAGES * AX_TILE : 0u;
     const int m0 = (blockIdx.x / CL) * FM;
     const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
     uint32_t ncols = 32; while (ncols < (uint32_t)(4 * Hc)) ncols <<= 1;
@@ -511,7 +550,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&in_full[h][s], 32); mbar_init(&in_empty[h][s], 128); }
         mbar_init(&s_done, 256); mbar_init(&dm_full, CL);
 #pragma unroll
-        for (int o = 0; o < CL; ++o) mbar_init(&a_ready[o], 1);
+        for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], 1); mbar_init(&conv_done[o], 256); }
         mbar_init(&dh1_done, CL); mbar_init(&ddh_full, CL);
         fence_barrier_init();
     }
@@ -534,6 +573,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
         const int k_beg = hf * HCH, k_end = k_beg + HCH;
         auto wait_acc = [&](uint64_t* bar, uint32_t par) { if (CL == 1) mbar_wait(bar, par); else mbar_wait_cl(bar, par); };
         int64_t ini = 0;
+        uint32_t pc = 0;
         auto in_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
             const int s = (int)(ini % AX_STAGES);
             const long long tw0 = FTR_NOW();
@@ -585,13 +625,14 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 }
                 tmem_st16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
                 tmem_st16(tmem + tl + T_DAZ + (uint32_t)lc0, dh);
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, dl);
+                a_store16<SPLIT3>(a_hi, a_lo, row, c0, dl, send, cr * KBc);
                 warp_store_chunk(s2, lane, dh, DAw + c0, 3 * H, rows_valid);            // DA_z
                 warp_store_chunk(s3, lane, dl, DAw + 2 * H + c0, 3 * H, rows_valid);    // DA_c
                 mbar_arrive(r2); mbar_arrive(r3);
             }
             if (lane == 0 && warp == 0) FTR(1, it, 7);
             fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                      // A = da_c
+            convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             // ---- M1: A <- da_z (after every CTA's GEMM_M has read da_c) ----
             wait_acc(&dm_full, it & 1);
             tc_fence_after();
@@ -600,10 +641,11 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 for (int k = k_beg; k < k_end; ++k) {
                     float dz[16];
                     tmem_ld16(tmem + tl + T_DAZ + (uint32_t)(16 * k), dz);
-                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dz);
+                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dz, send, cr * KBc);
                 }
                 if (lane == 0 && warp == 0) FTR(1, it, 9);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_z
+                convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             }
             // ---- M2: da_r, keep += m r  (runs while GEMM_DH1 executes) ----
             for (int k = k_beg; k < k_end; ++k) {
@@ -633,10 +675,11 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 for (int k = k_beg; k < k_end; ++k) {
                     float dr[16];
                     tmem_ld16(tmem + tl + T_M + (uint32_t)(16 * k), dr);
-                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dr);
+                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dr, send, cr * KBc);
                 }
                 if (lane == 0 && warp == 0) FTR(1, it, 12);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_r
+                convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             }
         }
     } else if (warp < 10) {
@@ -667,15 +710,17 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
         if (lane == 0) {
             // ================================ MMA issuer ================================
             int64_t ws = 0; uint32_t pa = 0, ps = 0;
-            const int KBc = Hc >> 5;
             const uint32_t slice_off = (uint32_t)cr * KBc * A_KB_BYTES, slice_bytes = (uint32_t)KBc * A_KB_BYTES;
             // operand hand-over + one GEMM over K = H in arrival order (own k-blocks, then owner cr-1, cr-2, ...)
             auto gemm = [&](uint32_t dcol, bool fresh, int it, int slot) {
-                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, a_lo, slice_off, slice_bytes, cr, true);
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, true);
                 FTR(1, it, slot);
                 for (int i = 0; i < CL; ++i) {
                     const int o = (cr - i + CL) % CL;
-                    if (CL > 1 && i > 0) { mbar_wait_cl(&a_ready[o], pa & 1); tc_fence_after(); }
+                    if (CL > 1 && i > 0) {
+                        if (SPLIT3) mbar_wait(&conv_done[o], pa & 1); else mbar_wait_cl(&a_ready[o], pa & 1);
+                        tc_fence_after();
+                    }
                     for (int kbl = 0; kbl < KBc; ++kbl, ++ws) {
                         const int kb = o * KBc + kbl;
                         const int s = (int)(ws % WST);
@@ -757,9 +802,10 @@ static inline int pick_cluster(poi_engine* e, int B, int H) {
     return cl;
 }
 static inline size_t fused_smem(int H, int cl, bool split3) {
-    const int KB = H / 32, wst = cl == 1 ? 2 : (cl == 2 ? 3 : 4);
+    const int KB = H / 32, wst = cl == 4 ? 4 : 2;
     const size_t w_stage = (size_t)(H / cl) * 128 * (split3 ? 2 : 1);
-    return (size_t)KB * A_KB_BYTES * (split3 ? 2 : 1) + wst * w_stage + (size_t)2 * AX_STAGES * AX_TILE + 1024;
+    const size_t send = (cl > 1 && split3) ? (size_t)(KB / cl) * A_KB_BYTES : 0;       // unsplit copy of the own slice
+    return (size_t)KB * A_KB_BYTES * (split3 ? 2 : 1) + wst * w_stage + (size_t)2 * AX_STAGES * AX_TILE + send + 1024;
 }
 
 template <bool SPLIT3, int CL>
