@@ -224,6 +224,90 @@ __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint3
     for (int k = 0; k < 4; ++k) { umma_tf32(d_tmem, dA + 2 * k, dW + 2 * k, idesc, acc); acc = 1u; }
 }
 
+// ---- TS mode: the A operand lives in TENSOR MEMORY (lane = row, column = k; hi at tA, lo at tA + H) ----
+// Measured (tools/umma_rate.cu, B200): one tcgen05.mma.kind::tf32 M = 128, K = 8 takes 105 cycles with A in shared
+// memory and 63.5 with A in tensor memory, for every N <= 128 -- at the N = 32..64 of a cluster-split recurrence the
+// instruction count, not N, sets the GEMM time, so the clustered 3xTF32 kernels keep A in TMEM: the epilogue threads
+// (thread = row = TMEM lane) write their slice with tcgen05.st, the peers' slices are split out of the landing buffer
+// into TMEM by the same threads.
+constexpr uint32_t TS_A_COL = 256;          // first TMEM column of the A operand (accumulators and stashes stay below)
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one 32-column k-block of A (TMEM columns ta_hi.., ta_lo..) against a W tile (hi, lo) in shared memory
+__device__ __forceinline__ void mma_kblock_ts(uint32_t d_tmem, uint32_t ta_hi, uint32_t ta_lo, uint32_t w_hi, uint32_t w_lo,
+                                              uint32_t idesc, bool first) {
+    const uint64_t dW = make_sdesc(w_hi), dWl = make_sdesc(w_lo);
+    uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { umma_tf32_ts(d_tmem, ta_lo + 8 * k, dW + 2 * k, idesc, acc); acc = 1u; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, ta_hi + 8 * k, dWl + 2 * k, idesc, 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, ta_hi + 8 * k, dW + 2 * k, idesc, 1u);
+}
+// 16 values of this thread's row (columns col..col+15 of the operand): hi / lo into TMEM, the unsplit values into the
+// send buffer (k-block kb - kb0 of the slice this CTA owns).  tl = this warp's TMEM lane offset.
+__device__ __forceinline__ void a_put16_ts(uint32_t tmem, uint32_t tl, int H, int row, int col, const float (&v)[16],
+                                           uint32_t send, int kb0) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { hi[i] = tf32_rn(v[i]); lo[i] = v[i] - hi[i]; }
+    tmem_st16(tmem + tl + TS_A_COL + (uint32_t)col, hi);
+    tmem_st16(tmem + tl + TS_A_COL + (uint32_t)(H + col), lo);
+    if (send) {
+        const int kb = col >> 5, cc0 = (col & 31) >> 2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            sts4(send + (kb - kb0) * A_KB_BYTES + row * 128 + (((cc0 + q) ^ (row & 7)) << 4),
+                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    }
+}
+// the unsplit values of this thread's own slice, as a_put16_ts left them in the send buffer
+__device__ __forceinline__ void send_load16(uint32_t send, int kb0, int row, int col, float (&v)[16]) {
+    const int kb = col >> 5, cc0 = (col & 31) >> 2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 x = lds4(send + (kb - kb0) * A_KB_BYTES + row * 128 + (((cc0 + q) ^ (row & 7)) << 4));
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+}
+// TS variant of convert_incoming: the peers' unsplit slices go from the landing buffer (the hi half of the smem A
+// tile) into TMEM as hi / lo
+template <int CL>
+__device__ __forceinline__ void convert_incoming_ts(uint64_t* a_ready, uint64_t* conv_done, uint32_t& pc, uint32_t landing,
+                                                    uint32_t tmem, uint32_t tl, int H, int cr, int KBc, int row, int hf) {
+#pragma unroll
+    for (int i = 1; i < CL; ++i) {
+        const int o = (cr - i + CL) % CL;
+        mbar_wait_cl(&a_ready[o], pc & 1);
+        for (int kbl = 0; kbl < KBc; ++kbl) {
+            const int kb = o * KBc + kbl;
+            const uint32_t base = (uint32_t)kb * A_KB_BYTES + row * 128;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 x = lds4(landing + base + (((hf * 4 + q) ^ (row & 7)) << 4));
+                float4 h4, l4; split4(x, h4, l4);
+                hi[4 * q] = h4.x; hi[4 * q + 1] = h4.y; hi[4 * q + 2] = h4.z; hi[4 * q + 3] = h4.w;
+                lo[4 * q] = l4.x; lo[4 * q + 1] = l4.y; lo[4 * q + 2] = l4.z; lo[4 * q + 3] = l4.w;
+            }
+            const uint32_t col = (uint32_t)(kb * 32 + hf * 16);
+            tmem_st16(tmem + tl + TS_A_COL + col, hi);
+            tmem_st16(tmem + tl + TS_A_COL + (uint32_t)H + col, lo);
+        }
+        tc_fence_before();
+        mbar_arrive(&conv_done[o]);
+    }
+    ++pc;
+}
+
 // Wh staged ONCE per call in the exact shared-memory image the UMMA wants (tile = one gate x one 32-float
 // k-block: H rows x 128 B, 128B-swizzled, hi then lo for 3xTF32), so that inside the recurrence a tile is one
 // bulk async copy (TMA, cp.async.bulk) issued by a single thread instead of 64 threads converting it
@@ -276,7 +360,9 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
     const uint32_t send = (CL > 1 && SPLIT3) ? ax_base + 2 * AX_STAGES * AX_TILE : 0u;
     const int m0 = (blockIdx.x / CL) * FM;
     const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
+    constexpr bool TS = SPLIT3 && CL > 1;                       // A operand in tensor memory (see TS mode above)
     uint32_t ncols = 32; while (ncols < (uint32_t)(3 * Hc)) ncols <<= 1;
+    if (TS) ncols = 512;
 
     if (tid == 0) {
 #pragma unroll
@@ -312,7 +398,11 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             float zero[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) zero[i] = 0.f;
-            for (int k = hf * (H >> 5); k < (hf + 1) * (H >> 5); ++k) a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, zero);
+            for (int k = hf * (H >> 5); k < (hf + 1) * (H >> 5); ++k) {
+                if (TS) a_put16_ts(tmem, tl, H, row, 16 * k, zero, 0u, 0);
+                else a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, zero);
+            }
+            if (TS) for (int k = k_beg; k < k_end; ++k) a_put16_ts(tmem, tl, H, row, col0 + 16 * k, zero, send, cr * KBc);   // own h_{-1} slice, unsplit
             fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);
         }
         int64_t axi = 0;                                       // position in this half's AX ring
@@ -347,7 +437,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 ax_take(a, sl_z, rel_z); ax_take(b, sl_r, rel_r);
                 tmem_ld16(tmem + tl + (uint32_t)lc0, dz);
                 tmem_ld16(tmem + tl + (uint32_t)(Hc + lc0), dr);
-                a_load16<SPLIT3>(a_hi, a_lo, row, c0, hv);
+                if (TS) send_load16(send, cr * KBc, row, c0, hv); else a_load16<SPLIT3>(a_hi, a_lo, row, c0, hv);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float zz = sigmoid_fast(dz[i] + a[i]);
@@ -359,14 +449,15 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 }
                 tmem_st16(tmem + tl + (uint32_t)lc0, dz);             // stash z
                 tmem_st16(tmem + tl + (uint32_t)(Hc + lc0), b);       // stash (1-z)*h_prev
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, a, send, cr * KBc);
+                if (TS) a_put16_ts(tmem, tl, H, row, c0, a, send, cr * KBc); else a_store16<SPLIT3>(a_hi, a_lo, row, c0, a, send, cr * KBc);
                 warp_store_chunk(sl_z, lane, dz, Z + wrow * H + c0, H, rows_valid);
                 warp_store_chunk(sl_r, lane, dr, R + wrow * H + c0, H, rows_valid);
                 mbar_arrive(rel_z); mbar_arrive(rel_r);
             }
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 5 : 9);
             fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the r*h slice is staged
-            convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);     // the peers' r*h slices
+            if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
+            else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);     // the peers' r*h slices
             // ---- epilogue 2: c, h_t ----
             if (CL == 1) mbar_wait(&d2_full, j & 1); else mbar_wait_cl(&d2_full, j & 1);
             tc_fence_after();
@@ -385,14 +476,17 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                     dc[i] = cc;
                     u[i] = ok ? u[i] + zz[i] * cc : 0.f;   // h_t = (1-z) h_prev + z c
                 }
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, u, send, cr * KBc);
+                if (TS) a_put16_ts(tmem, tl, H, row, c0, u, send, cr * KBc); else a_store16<SPLIT3>(a_hi, a_lo, row, c0, u, send, cr * KBc);
                 warp_store_chunk(sl, lane, dc, C + wrow * H + c0, H, rows_valid);
                 warp_store_chunk(sl, lane, u, Hs + (wrow + B) * H + c0, H, rows_valid);
                 mbar_arrive(rel);
             }
             if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 7 : 11);
             fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the h_t slice is staged
-            if (j + 1 < T) convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);   // the peers' h_t slices
+            if (j + 1 < T) {                                                                               // the peers' h_t slices
+                if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
+                else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
+            }
         }
     } else if (warp < 10) {
         // ================================ AX producers (one warp per column half, cp.async) ================================
@@ -440,8 +534,10 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                             FTR_ADD(0, j, slot, FTR_NOW() - tw0);
                             tc_fence_after();
                             const uint32_t sW = w_base + s * w_stage;
-                            mma_kblock<SPLIT3>(tmem + dcol0 + t * Hc, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc,
-                                               i == 0 && kbl == 0);
+                            if (TS) mma_kblock_ts(tmem + dcol0 + t * Hc, tmem + TS_A_COL + kb * 32, tmem + TS_A_COL + H + kb * 32, sW, sW + w_tile,
+                                                  idesc, i == 0 && kbl == 0);
+                            else mma_kblock<SPLIT3>(tmem + dcol0 + t * Hc, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc,
+                                                    i == 0 && kbl == 0);
                             umma_commit(&w_empty[s]);
                         }
                     }
@@ -539,7 +635,9 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
     const uint32_t send = (CL > 1 && SPLIT3) ? in_base + 2 * AX_STAGES * AX_TILE : 0u;
     const int m0 = (blockIdx.x / CL) * FM;
     const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
+    constexpr bool TS = SPLIT3 && CL > 1;
     uint32_t ncols = 32; while (ncols < (uint32_t)(4 * Hc)) ncols <<= 1;
+    if (TS) ncols = 512;
 
     if (tid == 0) {
 #pragma unroll
@@ -625,14 +723,15 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 }
                 tmem_st16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
                 tmem_st16(tmem + tl + T_DAZ + (uint32_t)lc0, dh);
-                a_store16<SPLIT3>(a_hi, a_lo, row, c0, dl, send, cr * KBc);
+                if (TS) a_put16_ts(tmem, tl, H, row, c0, dl, send, cr * KBc); else a_store16<SPLIT3>(a_hi, a_lo, row, c0, dl, send, cr * KBc);
                 warp_store_chunk(s2, lane, dh, DAw + c0, 3 * H, rows_valid);            // DA_z
                 warp_store_chunk(s3, lane, dl, DAw + 2 * H + c0, 3 * H, rows_valid);    // DA_c
                 mbar_arrive(r2); mbar_arrive(r3);
             }
             if (lane == 0 && warp == 0) FTR(1, it, 7);
             fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                      // A = da_c
-            convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
+            if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
+            else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             // ---- M1: A <- da_z (after every CTA's GEMM_M has read da_c) ----
             wait_acc(&dm_full, it & 1);
             tc_fence_after();
@@ -641,11 +740,13 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 for (int k = k_beg; k < k_end; ++k) {
                     float dz[16];
                     tmem_ld16(tmem + tl + T_DAZ + (uint32_t)(16 * k), dz);
-                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dz, send, cr * KBc);
+                    if (TS) a_put16_ts(tmem, tl, H, row, col0 + 16 * k, dz, send, cr * KBc);
+                    else a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dz, send, cr * KBc);
                 }
                 if (lane == 0 && warp == 0) FTR(1, it, 9);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_z
-                convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
+                if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
+                else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             }
             // ---- M2: da_r, keep += m r  (runs while GEMM_DH1 executes) ----
             for (int k = k_beg; k < k_end; ++k) {
@@ -675,11 +776,13 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 for (int k = k_beg; k < k_end; ++k) {
                     float dr[16];
                     tmem_ld16(tmem + tl + T_M + (uint32_t)(16 * k), dr);
-                    a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dr, send, cr * KBc);
+                    if (TS) a_put16_ts(tmem, tl, H, row, col0 + 16 * k, dr, send, cr * KBc);
+                    else a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dr, send, cr * KBc);
                 }
                 if (lane == 0 && warp == 0) FTR(1, it, 12);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_r
-                convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
+                if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
+                else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             }
         }
     } else if (warp < 10) {
@@ -729,8 +832,10 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                         FTR_ADD(1, (int)(ws / (3 * KB)), 14, FTR_NOW() - tw0);
                         tc_fence_after();
                         const uint32_t sW = w_base + s * w_stage;
-                        mma_kblock<SPLIT3>(tmem + dcol, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc,
-                                           fresh && i == 0 && kbl == 0);
+                        if (TS) mma_kblock_ts(tmem + dcol, tmem + TS_A_COL + kb * 32, tmem + TS_A_COL + H + kb * 32, sW, sW + w_tile, idesc,
+                                              fresh && i == 0 && kbl == 0);
+                        else mma_kblock<SPLIT3>(tmem + dcol, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc,
+                                                fresh && i == 0 && kbl == 0);
                         umma_commit(&w_empty[s]);
                     }
                 }
