@@ -72,6 +72,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// issue-only variants: several TMEM accesses in flight, one wait for all of them
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16_issue(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+          "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 64-byte rows (16 floats): XOR the 16-byte chunk index with bits 1..2 of the row -> lane=row accesses
 // and 4-lanes-per-row accesses are both bank-conflict free
 __device__ __forceinline__ uint32_t sw64(int row, int c) { return row * 64 + ((c ^ ((row >> 1) & 3)) << 4); }
@@ -252,15 +269,15 @@ __device__ __forceinline__ void mma_kblock_ts(uint32_t d_tmem, uint32_t ta_hi, u
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, ta_hi + 8 * k, dW + 2 * k, idesc, 1u);
 }
-// 16 values of this thread's row (columns col..col+15 of the operand): hi / lo into TMEM, the unsplit values into the
-// send buffer (k-block kb - kb0 of the slice this CTA owns).  tl = this warp's TMEM lane offset.
+// 16 values of this thread's row (columns col..col+15 of the operand): hi / lo into TMEM (stores ISSUED, not awaited), the
+// unsplit values into the send buffer (k-block kb - kb0 of the slice this CTA owns).  tl = this warp's TMEM lane offset.
 __device__ __forceinline__ void a_put16_ts(uint32_t tmem, uint32_t tl, int H, int row, int col, const float (&v)[16],
                                            uint32_t send, int kb0) {
     float hi[16], lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { hi[i] = tf32_rn(v[i]); lo[i] = v[i] - hi[i]; }
-    tmem_st16(tmem + tl + TS_A_COL + (uint32_t)col, hi);
-    tmem_st16(tmem + tl + TS_A_COL + (uint32_t)(H + col), lo);
+    tmem_st16_issue(tmem + tl + TS_A_COL + (uint32_t)col, hi);          // the caller waits (tmem_wait_st) before it signals
+    tmem_st16_issue(tmem + tl + TS_A_COL + (uint32_t)(H + col), lo);
     if (send) {
         const int kb = col >> 5, cc0 = (col & 31) >> 2;
 #pragma unroll
@@ -299,9 +316,10 @@ __device__ __forceinline__ void convert_incoming_ts(uint64_t* a_ready, uint64_t*
                 lo[4 * q] = l4.x; lo[4 * q + 1] = l4.y; lo[4 * q + 2] = l4.z; lo[4 * q + 3] = l4.w;
             }
             const uint32_t col = (uint32_t)(kb * 32 + hf * 16);
-            tmem_st16(tmem + tl + TS_A_COL + col, hi);
-            tmem_st16(tmem + tl + TS_A_COL + (uint32_t)H + col, lo);
+            tmem_st16_issue(tmem + tl + TS_A_COL + col, hi);
+            tmem_st16_issue(tmem + tl + TS_A_COL + (uint32_t)H + col, lo);
         }
+        tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&conv_done[o]);
     }
@@ -403,6 +421,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 else a_store16<SPLIT3>(a_hi, a_lo, row, 16 * k, zero);
             }
             if (TS) for (int k = k_beg; k < k_end; ++k) a_put16_ts(tmem, tl, H, row, col0 + 16 * k, zero, send, cr * KBc);   // own h_{-1} slice, unsplit
+            if (TS) tmem_wait_st();
             fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);
         }
         int64_t axi = 0;                                       // position in this half's AX ring
@@ -434,10 +453,11 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 const int lc0 = 16 * k, c0 = col0 + lc0;       // local (TMEM) / global (A tile, memory) column
                 float a[16], b[16], hv[16], dz[16], dr[16];
                 uint32_t sl_z, sl_r; uint64_t *rel_z, *rel_r;
+                tmem_ld16_issue(tmem + tl + (uint32_t)lc0, dz);
+                tmem_ld16_issue(tmem + tl + (uint32_t)(Hc + lc0), dr);
                 ax_take(a, sl_z, rel_z); ax_take(b, sl_r, rel_r);
-                tmem_ld16(tmem + tl + (uint32_t)lc0, dz);
-                tmem_ld16(tmem + tl + (uint32_t)(Hc + lc0), dr);
                 if (TS) send_load16(send, cr * KBc, row, c0, hv); else a_load16<SPLIT3>(a_hi, a_lo, row, c0, hv);
+                tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float zz = sigmoid_fast(dz[i] + a[i]);
@@ -447,15 +467,18 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                     a[i] = rr * h_;                 // r*h -> next A operand
                     b[i] = (1.f - zz) * h_;         // (1-z)*h_prev, used by epilogue 2
                 }
-                tmem_st16(tmem + tl + (uint32_t)lc0, dz);             // stash z
-                tmem_st16(tmem + tl + (uint32_t)(Hc + lc0), b);       // stash (1-z)*h_prev
+                tmem_st16_issue(tmem + tl + (uint32_t)lc0, dz);             // stash z
+                tmem_st16_issue(tmem + tl + (uint32_t)(Hc + lc0), b);       // stash (1-z)*h_prev
                 if (TS) a_put16_ts(tmem, tl, H, row, c0, a, send, cr * KBc); else a_store16<SPLIT3>(a_hi, a_lo, row, c0, a, send, cr * KBc);
+                tmem_wait_st();
+                if (k == k_end - 1) {       // the operand slice is complete: hand it over BEFORE the stores to global memory
+                    if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 5 : 9);
+                    fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);
+                }
                 warp_store_chunk(sl_z, lane, dz, Z + wrow * H + c0, H, rows_valid);
                 warp_store_chunk(sl_r, lane, dr, R + wrow * H + c0, H, rows_valid);
                 mbar_arrive(rel_z); mbar_arrive(rel_r);
             }
-            if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 5 : 9);
-            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the r*h slice is staged
             if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
             else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);     // the peers' r*h slices
             // ---- epilogue 2: c, h_t ----
@@ -466,23 +489,27 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 const int lc0 = 16 * k, c0 = col0 + lc0;
                 float a[16], dc[16], zz[16], u[16];
                 uint32_t sl; uint64_t* rel;
+                tmem_ld16_issue(tmem + tl + (uint32_t)(2 * Hc + lc0), dc);
+                tmem_ld16_issue(tmem + tl + (uint32_t)lc0, zz);
+                tmem_ld16_issue(tmem + tl + (uint32_t)(Hc + lc0), u);
                 ax_take(a, sl, rel);
-                tmem_ld16(tmem + tl + (uint32_t)(2 * Hc + lc0), dc);
-                tmem_ld16(tmem + tl + (uint32_t)lc0, zz);
-                tmem_ld16(tmem + tl + (uint32_t)(Hc + lc0), u);
+                tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float cc = tanh_fast(dc[i] + a[i]);
                     dc[i] = cc;
                     u[i] = ok ? u[i] + zz[i] * cc : 0.f;   // h_t = (1-z) h_prev + z c
                 }
-                if (TS) a_put16_ts(tmem, tl, H, row, c0, u, send, cr * KBc); else a_store16<SPLIT3>(a_hi, a_lo, row, c0, u, send, cr * KBc);
+                if (TS) { a_put16_ts(tmem, tl, H, row, c0, u, send, cr * KBc); tmem_wait_st(); }
+                else a_store16<SPLIT3>(a_hi, a_lo, row, c0, u, send, cr * KBc);
+                if (k == k_end - 1) {       // the h_t slice is complete: hand it over before the stores to global memory
+                    if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 7 : 11);
+                    fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);
+                }
                 warp_store_chunk(sl, lane, dc, C + wrow * H + c0, H, rows_valid);
                 warp_store_chunk(sl, lane, u, Hs + (wrow + B) * H + c0, H, rows_valid);
                 mbar_arrive(rel);
             }
-            if (lane == 0 && (warp == 0 || warp == 7)) FTR(0, j, warp == 0 ? 7 : 11);
-            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);         // this thread's part of the h_t slice is staged
             if (j + 1 < T) {                                                                               // the peers' h_t slices
                 if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
                 else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
@@ -701,12 +728,15 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 uint32_t s0, s1, s2, s3; uint64_t *r0, *r1, *r2, *r3;
                 // the ring has 2 stages: release the first two tiles as soon as they are in registers, keep the
                 // slices of the last two as store staging
+                if (it > 0) {
+                    tmem_ld16_issue(tmem + tl + T_DH + (uint32_t)lc0, dh);
+                    tmem_ld16_issue(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
+                }
                 in_take(dl, s0, r0); mbar_arrive(r0);
                 in_take(zz, s1, r1); mbar_arrive(r1);
                 in_take(cc, s2, r2); in_take(hp, s3, r3);
                 if (it > 0) {
-                    tmem_ld16(tmem + tl + T_DH + (uint32_t)lc0, dh);
-                    tmem_ld16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
+                    tmem_wait_ld();
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { dh[i] = 0.f; kp[i] = 0.f; }
@@ -721,15 +751,18 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                     dl[i] = ok ? dac : 0.f;                     // da_c
                     dh[i] = ok ? daz : 0.f;                     // da_z
                 }
-                tmem_st16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
-                tmem_st16(tmem + tl + T_DAZ + (uint32_t)lc0, dh);
+                tmem_st16_issue(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
+                tmem_st16_issue(tmem + tl + T_DAZ + (uint32_t)lc0, dh);
                 if (TS) a_put16_ts(tmem, tl, H, row, c0, dl, send, cr * KBc); else a_store16<SPLIT3>(a_hi, a_lo, row, c0, dl, send, cr * KBc);
+                tmem_wait_st();
+                if (k == k_end - 1) {       // A = da_c is complete: hand it over before the stores to global memory
+                    if (lane == 0 && warp == 0) FTR(1, it, 7);
+                    fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);
+                }
                 warp_store_chunk(s2, lane, dh, DAw + c0, 3 * H, rows_valid);            // DA_z
                 warp_store_chunk(s3, lane, dl, DAw + 2 * H + c0, 3 * H, rows_valid);    // DA_c
                 mbar_arrive(r2); mbar_arrive(r3);
             }
-            if (lane == 0 && warp == 0) FTR(1, it, 7);
-            fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                      // A = da_c
             if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
             else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             // ---- M1: A <- da_z (after every CTA's GEMM_M has read da_c) ----
@@ -743,6 +776,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                     if (TS) a_put16_ts(tmem, tl, H, row, col0 + 16 * k, dz, send, cr * KBc);
                     else a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dz, send, cr * KBc);
                 }
+                if (TS) tmem_wait_st();
                 if (lane == 0 && warp == 0) FTR(1, it, 9);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_z
                 if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
@@ -753,17 +787,19 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 const int lc0 = 16 * k, c0 = col0 + lc0;
                 float rr[16], hp[16], mm[16], kp[16];
                 uint32_t s0, s1; uint64_t *r0, *r1;
+                tmem_ld16_issue(tmem + tl + T_M + (uint32_t)lc0, mm);
+                tmem_ld16_issue(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
                 in_take(rr, s0, r0); in_take(hp, s1, r1);
-                tmem_ld16(tmem + tl + T_M + (uint32_t)lc0, mm);
-                tmem_ld16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
+                tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float m_ = ok ? mm[i] : 0.f, r_ = rr[i];
                     kp[i] = kp[i] + m_ * r_;
                     mm[i] = ok ? m_ * hp[i] * r_ * (1.f - r_) : 0.f;       // da_r
                 }
-                tmem_st16(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
-                tmem_st16(tmem + tl + T_M + (uint32_t)lc0, mm);             // stash da_r over m
+                tmem_st16_issue(tmem + tl + T_KEEP + (uint32_t)lc0, kp);
+                tmem_st16_issue(tmem + tl + T_M + (uint32_t)lc0, mm);       // stash da_r over m
+                tmem_wait_st();
                 warp_store_chunk(s0, lane, mm, DAw + H + c0, 3 * H, rows_valid);        // DA_r
                 mbar_arrive(r0); mbar_arrive(r1);
             }
@@ -779,6 +815,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                     if (TS) a_put16_ts(tmem, tl, H, row, col0 + 16 * k, dr, send, cr * KBc);
                     else a_store16<SPLIT3>(a_hi, a_lo, row, col0 + 16 * k, dr, send, cr * KBc);
                 }
+                if (TS) tmem_wait_st();
                 if (lane == 0 && warp == 0) FTR(1, it, 12);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_r
                 if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
