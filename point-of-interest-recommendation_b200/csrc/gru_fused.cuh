@@ -646,7 +646,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 float* __restrict__ DA, int B, int T, int H) {
     constexpr int WST = CL == 4 ? 4 : 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[WST], w_empty[WST], in_full[2][AX_STAGES], in_empty[2][AX_STAGES], s_done, a_ready[CL], conv_done[CL], dm_full, dh1_done, ddh_full;
+    __shared__ uint64_t w_full[WST], w_empty[WST], in_full[2][4], in_empty[2][4], s_done, a_ready[CL], conv_done[CL], dm_full, dh1_done, ddh_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cr = CL == 1 ? 0 : (int)cluster_ctarank();
@@ -657,9 +657,12 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
     const uint32_t a_hi = sbase, a_lo = sbase + KB * A_KB_BYTES;
     const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
-    const uint32_t in_base = w_base + WST * w_stage;
     const int KBc = Hc >> 5;
-    const uint32_t send = (CL > 1 && SPLIT3) ? in_base + 2 * AX_STAGES * AX_TILE : 0u;
+    const uint32_t send = (CL > 1 && SPLIT3) ? w_base + WST * w_stage + 2 * AX_STAGES * AX_TILE : 0u;
+    // input ring: with the A operand in tensor memory the lo half of the smem A tile is free -- a 4-stage ring there
+    // holds the whole input set of the P phase one step ahead (2 stages: the epilogue waited ~2 k cycles per step)
+    const int AXS = (SPLIT3 && CL > 1 && KB * A_KB_BYTES >= 8 * AX_TILE) ? 4 : AX_STAGES;
+    const uint32_t in_base = AXS == 4 ? a_lo : w_base + WST * w_stage;
     const int m0 = (blockIdx.x / CL) * FM;
     const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
     constexpr bool TS = SPLIT3 && CL > 1;
@@ -672,7 +675,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&in_full[h][s], 32); mbar_init(&in_empty[h][s], 128); }
+            for (int s = 0; s < 4; ++s) { mbar_init(&in_full[h][s], 32); mbar_init(&in_empty[h][s], 128); }
         mbar_init(&s_done, 256); mbar_init(&dm_full, CL);
 #pragma unroll
         for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], 1); mbar_init(&conv_done[o], 256); }
@@ -700,11 +703,11 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
         int64_t ini = 0;
         uint32_t pc = 0;
         auto in_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
-            const int s = (int)(ini % AX_STAGES);
+            const int s = (int)(ini % AXS);
             const long long tw0 = FTR_NOW();
-            mbar_wait(&in_full[hf][s], (uint32_t)(ini / AX_STAGES) & 1);
+            mbar_wait(&in_full[hf][s], (uint32_t)(ini / AXS) & 1);
             if (warp == 0 && lane == 0) FTR_ADD(1, (int)(ini / (6 * HCH)), 13, FTR_NOW() - tw0);
-            slice = in_base + (hf * AX_STAGES + s) * AX_TILE + q * OUT_STG;
+            slice = in_base + (hf * AXS + s) * AX_TILE + q * OUT_STG;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float4 x = lds4(slice + sw64(lane, c));
@@ -828,15 +831,15 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
         const int per_step = 6 * HCH;
         const int64_t n_tiles = (int64_t)T * per_step;
         for (int64_t ai = 0; ai < n_tiles; ++ai) {
-            const int s = (int)(ai % AX_STAGES);
-            if (ai >= AX_STAGES) mbar_wait(&in_empty[hf][s], (uint32_t)((ai / AX_STAGES) - 1) & 1);
+            const int s = (int)(ai % AXS);
+            if (ai >= AXS) mbar_wait(&in_empty[hf][s], (uint32_t)((ai / AXS) - 1) & 1);
             const int j = T - 1 - (int)(ai / per_step), ti = (int)(ai % per_step);
             int kind, kk;                                       // 0 DHl, 1 Z, 2 C, 3 H_prev, 4 R
             if (ti < 4 * HCH) { kind = ti & 3; kk = ti >> 2; }
             else { const int t2 = ti - 4 * HCH; kind = (t2 & 1) ? 3 : 4; kk = t2 >> 1; }
             const float* base = kind == 0 ? DHl : kind == 1 ? Z : kind == 2 ? C : kind == 3 ? Hs : R;
             const float* src = base + ((size_t)j * B + m0) * H + col0 + 16 * (hf * HCH + kk);
-            const uint32_t dst = in_base + (hf * AX_STAGES + s) * AX_TILE;
+            const uint32_t dst = in_base + (hf * AXS + s) * AX_TILE;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 int f = lane + i * 32, rw = f >> 2, c = f & 3;
