@@ -330,10 +330,11 @@ __device__ __forceinline__ void convert_incoming_ts(uint64_t* a_ready, uint64_t*
 // k-block: H rows x 128 B, 128B-swizzled, hi then lo for 3xTF32), so that inside the recurrence a tile is one
 // bulk async copy (TMA, cp.async.bulk) issued by a single thread instead of 64 threads converting it
 template <bool SPLIT3>
-__global__ void k_stage_wh(const float* __restrict__ wh, int H, int CL, uint8_t* __restrict__ image) {
+__global__ void k_stage_wh(const float* __restrict__ wh, int H, int CL, int merge, uint8_t* __restrict__ image) {
     // image = [cluster rank][tile t] of Hc = H / CL rows (the rows of Wh the rank owns) x 128 B, tiles in the order
     // the rank's MMA thread consumes them: GEMM1 k-blocks in arrival order (owner rank, rank-1, ...), z and r tile
-    // of each; then GEMM2 (c gate) over the same k-block order
+    // of each; then GEMM2 (c gate) over the same k-block order.  merge: the z and r tiles of a k-block form ONE tile of
+    // 2 Hc rows (hi: z rows, r rows; lo: z rows, r rows) so that GEMM1 is a single N = 2 Hc instruction per k-step.
     const int KB = H >> 5, Hc = H / CL, KBc = KB / CL;
     const int64_t n = (int64_t)3 * KB * H * 8;
     const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
@@ -344,9 +345,19 @@ __global__ void k_stage_wh(const float* __restrict__ wh, int H, int CL, uint8_t*
         if (t < 2 * KB) { pos = t >> 1; gate = t & 1; } else { pos = t - 2 * KB; gate = 2; }
         const int owner = (rank - pos / KBc + CL) % CL, kb = owner * KBc + pos % KBc;
         float4 v = *reinterpret_cast<const float4*>(wh + ((size_t)gate * H + rank * Hc + rl) * H + kb * 32 + c * 4);
-        uint8_t* dst = image + ((size_t)rank * 3 * KB + t) * w_stage + rl * 128 + ((c ^ (rl & 7)) << 4);
-        if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + w_tile) = lo; }
-        else *reinterpret_cast<float4*>(dst) = v;
+        const uint32_t in_tile = rl * 128 + ((c ^ (rl & 7)) << 4);
+        uint8_t* rank_base = image + (size_t)rank * 3 * KB * w_stage;
+        uint8_t *dst_hi, *dst_lo;
+        if (merge && SPLIT3) {
+            uint8_t* tb = gate < 2 ? rank_base + (size_t)pos * 2 * w_stage : rank_base + (size_t)KB * 2 * w_stage + (size_t)pos * w_stage;
+            dst_hi = tb + (gate == 1 ? w_tile : 0) + in_tile;
+            dst_lo = tb + (gate < 2 ? 2 * w_tile : w_tile) + (gate == 1 ? w_tile : 0) + in_tile;
+        } else {
+            dst_hi = rank_base + (size_t)t * w_stage + in_tile;
+            dst_lo = dst_hi + w_tile;
+        }
+        if (SPLIT3) { float4 hi, lo; split4(v, hi, lo); *reinterpret_cast<float4*>(dst_hi) = hi; *reinterpret_cast<float4*>(dst_lo) = lo; }
+        else *reinterpret_cast<float4*>(dst_hi) = v;
     }
 }
 
@@ -361,7 +372,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 float* __restrict__ R, float* __restrict__ C, int B, int T, int H) {
     constexpr int WST = CL == 4 ? 4 : 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_full[WST], w_empty[WST], ax_full[2][AX_STAGES], ax_empty[2][AX_STAGES], s_done, a_ready[CL], conv_done[CL], d1_full, d2_full;
+    __shared__ uint64_t w_full[4], w_empty[4], ax_full[2][4], ax_empty[2][4], s_done, a_ready[CL], conv_done[CL], d1_full, d2_full;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cr = CL == 1 ? 0 : (int)cluster_ctarank();      // this CTA's slice of the gate columns
@@ -372,10 +383,16 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
     const uint32_t a_hi = sbase, a_lo = sbase + KB * A_KB_BYTES;
     const uint32_t w_tile = Hc * 128, w_stage = w_tile * (SPLIT3 ? 2 : 1);
     const uint32_t w_base = sbase + KB * A_KB_BYTES * (SPLIT3 ? 2 : 1);
-    const uint32_t ax_base = w_base + WST * w_stage;           // [half][stage] tiles of AX_TILE bytes
     const int KBc = Hc >> 5;                                    // k-blocks of the operand this CTA owns
     // unsplit copy of the own slice, the source of the bulk copies to the peers (3xTF32 clusters only)
-    const uint32_t send = (CL > 1 && SPLIT3) ? ax_base + 2 * AX_STAGES * AX_TILE : 0u;
+    const uint32_t send = (CL > 1 && SPLIT3) ? w_base + WST * w_stage + 2 * AX_STAGES * AX_TILE : 0u;
+    // TS mode (A operand in tensor memory) frees the lo half of the smem A tile: the AX ring moves there (4 stages when
+    // it fits) and the W ring takes the old AX region too, in slots of 2 * w_stage -- room for the merged z|r tiles
+    const bool merge = SPLIT3 && CL > 1 && KB * A_KB_BYTES >= 4 * AX_TILE;
+    const int AXS = merge && KB * A_KB_BYTES >= 8 * AX_TILE ? 4 : AX_STAGES;
+    const uint32_t ax_base = merge ? a_lo : w_base + WST * w_stage;           // [half][stage] tiles of AX_TILE bytes
+    const uint32_t w_slot = merge ? 2 * w_stage : w_stage;
+    const int NWS = merge ? min(4, (int)((WST * w_stage + 2 * AX_STAGES * AX_TILE) / w_slot)) : WST;
     const int m0 = (blockIdx.x / CL) * FM;
     const uint8_t* wimg_c = wimg + (size_t)cr * 3 * KB * w_stage;
     constexpr bool TS = SPLIT3 && CL > 1;                       // A operand in tensor memory (see TS mode above)
@@ -384,11 +401,11 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int s = 0; s < AX_STAGES; ++s) { mbar_init(&ax_full[h][s], 32); mbar_init(&ax_empty[h][s], 128); }
+            for (int s = 0; s < 4; ++s) { mbar_init(&ax_full[h][s], 32); mbar_init(&ax_empty[h][s], 128); }
         mbar_init(&s_done, 256); mbar_init(&d1_full, CL);
 #pragma unroll
         for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], 1); mbar_init(&conv_done[o], 256); }
@@ -401,7 +418,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
     if (CL > 1) cluster_sync_all();                             // every CTA's barriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = make_idesc_tf32(FM, Hc);
+    const uint32_t idesc = make_idesc_tf32(FM, Hc), idesc2 = make_idesc_tf32(FM, 2 * Hc);
 
     if (warp < 8) {
         // ================================ epilogue (8 warps) ================================
@@ -429,11 +446,11 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
         // wait for the next AX tile, read this thread's row, return this warp's 2 KB slice of the tile (free to
         // be reused as output staging once the whole warp has read) and the barrier to release it on
         auto ax_take = [&](float (&v)[16], uint32_t& slice, uint64_t*& rel) {
-            const int s = (int)(axi % AX_STAGES);
+            const int s = (int)(axi % AXS);
             const long long tw0 = FTR_NOW();
-            mbar_wait(&ax_full[hf][s], (uint32_t)(axi / AX_STAGES) & 1);
+            mbar_wait(&ax_full[hf][s], (uint32_t)(axi / AXS) & 1);
             if (warp == 0 && lane == 0) FTR_ADD(0, (int)(axi / (3 * HCH)), 12, FTR_NOW() - tw0);
-            slice = ax_base + (hf * AX_STAGES + s) * AX_TILE + q * OUT_STG;
+            slice = ax_base + (hf * AXS + s) * AX_TILE + q * OUT_STG;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float4 x = lds4(slice + sw64(lane, c));
@@ -521,13 +538,13 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
         const int per_step = 3 * HCH;
         const int64_t n_tiles = (int64_t)T * per_step;
         for (int64_t ai = 0; ai < n_tiles; ++ai) {
-            const int s = (int)(ai % AX_STAGES);
-            if (ai >= AX_STAGES) mbar_wait(&ax_empty[hf][s], (uint32_t)((ai / AX_STAGES) - 1) & 1);
+            const int s = (int)(ai % AXS);
+            if (ai >= AXS) mbar_wait(&ax_empty[hf][s], (uint32_t)((ai / AXS) - 1) & 1);
             const int j = (int)(ai / per_step), ti = (int)(ai % per_step);
             const int gate = ti < 2 * HCH ? (ti & 1) : 2;
             const int k = hf * HCH + (ti < 2 * HCH ? (ti >> 1) : ti - 2 * HCH);
             const float* src = AX + ((size_t)j * B + m0) * 3 * H + gate * H + col0 + 16 * k;
-            const uint32_t dst = ax_base + (hf * AX_STAGES + s) * AX_TILE;
+            const uint32_t dst = ax_base + (hf * AXS + s) * AX_TILE;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 int f = lane + i * 32, rw = f >> 2, c = f & 3;
@@ -545,7 +562,8 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             // one GEMM over K = H in ARRIVAL order: own k-blocks first, then owner cr-1, cr-2, ... (the order the
             // peers send in); `tiles_per_kb` W tiles per k-block, accumulators dcol0 + t * Hc.  The Wh image of this
             // rank is staged in exactly this order (k_stage_wh).
-            auto gemm = [&](uint32_t dcol0, int tiles_per_kb, bool exchanged, int j, int slot) {
+            // nmul = 2: the tile holds the z and the r rows (merged GEMM1 tile, N = 2 Hc)
+            auto gemm = [&](uint32_t dcol0, int tiles_per_kb, int nmul, bool exchanged, int j, int slot) {
                 for (int i = 0; i < CL; ++i) {
                     const int o = (cr - i + CL) % CL;
                     if (CL > 1 && i > 0 && exchanged) {
@@ -555,14 +573,14 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                     for (int kbl = 0; kbl < KBc; ++kbl) {
                         const int kb = o * KBc + kbl;
                         for (int t = 0; t < tiles_per_kb; ++t, ++ws) {
-                            const int s = (int)(ws % WST);
+                            const int s = (int)(ws % NWS);
                             const long long tw0 = FTR_NOW();
-                            mbar_wait(&w_full[s], (uint32_t)(ws / WST) & 1);
+                            mbar_wait(&w_full[s], (uint32_t)(ws / NWS) & 1);
                             FTR_ADD(0, j, slot, FTR_NOW() - tw0);
                             tc_fence_after();
-                            const uint32_t sW = w_base + s * w_stage;
-                            if (TS) mma_kblock_ts(tmem + dcol0 + t * Hc, tmem + TS_A_COL + kb * 32, tmem + TS_A_COL + H + kb * 32, sW, sW + w_tile,
-                                                  idesc, i == 0 && kbl == 0);
+                            const uint32_t sW = w_base + s * w_slot;
+                            if (TS) mma_kblock_ts(tmem + dcol0 + t * Hc, tmem + TS_A_COL + kb * 32, tmem + TS_A_COL + H + kb * 32, sW, sW + nmul * w_tile,
+                                                  nmul == 2 ? idesc2 : idesc, i == 0 && kbl == 0);
                             else mma_kblock<SPLIT3>(tmem + dcol0 + t * Hc, a_hi + kb * A_KB_BYTES, a_lo + kb * A_KB_BYTES, sW, sW + w_tile, idesc,
                                                     i == 0 && kbl == 0);
                             umma_commit(&w_empty[s]);
@@ -575,26 +593,34 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 // h_{j-1}: own slice staged (j = 0: the zero tile, nothing to exchange)
                 begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, j > 0);
                 FTR(0, j, 0);
-                gemm(0u, 2, j > 0, j, 13);                      // D1z | D1r
+                if (merge) gemm(0u, 1, 2, j > 0, j, 13);        // D1z | D1r in one N = 2 Hc instruction per k-step
+                else gemm(0u, 2, 1, j > 0, j, 13);              // D1z, D1r
                 umma_commit_cl<CL>(&d1_full);
                 FTR(0, j, 1);
                 begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, true);   // r*h
                 FTR(0, j, 2);
-                gemm((uint32_t)(2 * Hc), 1, true, j, 14);       // D2
+                gemm((uint32_t)(2 * Hc), 1, 1, true, j, 14);    // D2
                 umma_commit_cl<CL>(&d2_full);
                 FTR(0, j, 3);
             }
         }
     } else if (lane == 0) {
         // ================================ Wh tiles: one bulk async copy (TMA) per tile ================================
-        const int64_t n_tiles = (int64_t)T * 3 * KB;
+        const int per_step = merge ? 2 * KB : 3 * KB;           // merged: KB z|r tiles of 2 * w_stage, then KB c tiles of w_stage
+        const int64_t n_tiles = (int64_t)T * per_step;
         for (int64_t ws = 0; ws < n_tiles; ++ws) {
-            const int s = (int)(ws % WST);
-            if (ws >= WST) mbar_wait(&w_empty[s], (uint32_t)((ws / WST) - 1) & 1);
+            const int s = (int)(ws % NWS);
+            if (ws >= NWS) mbar_wait(&w_empty[s], (uint32_t)((ws / NWS) - 1) & 1);
+            const int ti = (int)(ws % per_step);
+            uint32_t bytes = w_stage; size_t src = (size_t)ti * w_stage;
+            if (merge) {
+                if (ti < KB) { bytes = 2 * w_stage; src = (size_t)ti * 2 * w_stage; }
+                else src = (size_t)KB * 2 * w_stage + (size_t)(ti - KB) * w_stage;
+            }
             const uint32_t bar = smem_u32(&w_full[s]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_stage) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(w_base + s * w_stage), "l"(wimg_c + (size_t)(ws % (3 * KB)) * w_stage), "r"(w_stage), "r"(bar) : "memory");
+                         ::"r"(w_base + s * w_slot), "l"(wimg_c + src), "r"(bytes), "r"(bar) : "memory");
         }
     }
     tc_fence_before();
@@ -1016,7 +1042,8 @@ static int launch_fwd_inst(poi_engine* e, const float* AX, const float* wh, floa
     uint8_t* wimg = nullptr;
     POI_TRY(arena_get(e, (size_t)cl * 3 * KB * w_stage, &wimg));
     POI_CAT(e, CAT_ELTWISE, 0, 0);
-    POI_LAUNCH(e, (k_stage_wh<SPLIT3>), 48, 256, 0, wh, H, cl, wimg);
+    const int merge = (SPLIT3 && cl > 1 && (size_t)KB * A_KB_BYTES >= (size_t)4 * AX_TILE) ? 1 : 0;    // as in k_gru_fwd_fused
+    POI_LAUNCH(e, (k_stage_wh<SPLIT3>), 48, 256, 0, wh, H, cl, merge, wimg);
     if (cl == 4) return launch_fwd_cl<SPLIT3, 4>(e, AX, wimg, Hs, Z, R, C, B, T, H);
     if (cl == 2) return launch_fwd_cl<SPLIT3, 2>(e, AX, wimg, Hs, Z, R, C, B, T, H);
     return launch_fwd_cl<SPLIT3, 1>(e, AX, wimg, Hs, Z, R, C, B, T, H);
