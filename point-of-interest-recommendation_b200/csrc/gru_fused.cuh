@@ -295,6 +295,37 @@ __device__ __forceinline__ void send_load16(uint32_t send, int kb0, int row, int
         v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
 }
+// TS mode, PUSH variant of the exchange: once the 8 epilogue warps have staged the own slice (unsplit) in `send`, the same
+// 256 threads copy it into every peer's landing buffer with COALESCED distributed-shared-memory stores (a warp writes 512
+// contiguous bytes per instruction; the first version of this kernel stored with a 128-byte lane stride and paid ~370
+// cycles per instruction) and arrive (release.cluster) on the peer's a_ready[this rank].  No copy engine, no async
+// proxy: the receiver reads the landing buffer with ordinary loads.  et = 0..255, the thread's index among the epilogue
+// threads.
+// MEASURED (c2, CL = 4): the push makes an exchange + GEMM phase ~10.6 k cycles against ~6.9 k with the bulk copies
+// (step 2.78 ms vs 2.49 ms) -- distributed-shared-memory STORES are slow even when coalesced; kept for reference, off.
+constexpr int POI_FUSED_PUSH = 0;           // 1: coalesced st.shared::cluster push; 0: bulk copies issued by the MMA thread
+__device__ __forceinline__ void stc4(uint32_t caddr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <int CL>
+__device__ __forceinline__ void push_slice_ts(uint32_t send, uint32_t landing_slice, uint32_t slice_bytes, uint64_t* a_ready, int cr, int et) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");                       // the whole slice is in `send`
+    uint32_t dst[CL], bar[CL];
+#pragma unroll
+    for (int i = 1; i < CL; ++i) {
+        const uint32_t r = (uint32_t)((cr + i) % CL);
+        dst[i] = mapa_u32(landing_slice, r); bar[i] = mapa_u32(smem_u32(&a_ready[cr]), r);
+    }
+    for (uint32_t off = (uint32_t)et * 16u; off < slice_bytes; off += 4096u) {
+        const float4 v = lds4(send + off);
+#pragma unroll
+        for (int i = 1; i < CL; ++i) stc4(dst[i] + off, v);
+    }
+#pragma unroll
+    for (int i = 1; i < CL; ++i)
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar[i]) : "memory");
+}
+
 // TS variant of convert_incoming: the peers' unsplit slices go from the landing buffer (the hi half of the smem A
 // tile) into TMEM as hi / lo
 template <int CL>
@@ -408,7 +439,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             for (int s = 0; s < 4; ++s) { mbar_init(&ax_full[h][s], 32); mbar_init(&ax_empty[h][s], 128); }
         mbar_init(&s_done, 256); mbar_init(&d1_full, CL);
 #pragma unroll
-        for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], 1); mbar_init(&conv_done[o], 256); }
+        for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], (SPLIT3 && CL > 1 && POI_FUSED_PUSH) ? 256 : 1); mbar_init(&conv_done[o], 256); }
         mbar_init(&d2_full, CL);
         fence_barrier_init();
     }
@@ -496,6 +527,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 warp_store_chunk(sl_r, lane, dr, R + wrow * H + c0, H, rows_valid);
                 mbar_arrive(rel_z); mbar_arrive(rel_r);
             }
+            if (TS && POI_FUSED_PUSH) push_slice_ts<CL>(send, a_hi + (uint32_t)cr * KBc * A_KB_BYTES, (uint32_t)KBc * A_KB_BYTES, a_ready, cr, (int)threadIdx.x);
             if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
             else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);     // the peers' r*h slices
             // ---- epilogue 2: c, h_t ----
@@ -528,6 +560,7 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
                 mbar_arrive(rel);
             }
             if (j + 1 < T) {                                                                               // the peers' h_t slices
+                if (TS && POI_FUSED_PUSH) push_slice_ts<CL>(send, a_hi + (uint32_t)cr * KBc * A_KB_BYTES, (uint32_t)KBc * A_KB_BYTES, a_ready, cr, (int)threadIdx.x);
                 if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
                 else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             }
@@ -591,13 +624,13 @@ k_gru_fwd_fused(const float* __restrict__ AX, const uint8_t* __restrict__ wimg, 
             };
             for (int j = 0; j < T; ++j) {
                 // h_{j-1}: own slice staged (j = 0: the zero tile, nothing to exchange)
-                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, j > 0);
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, j > 0 && !(TS && POI_FUSED_PUSH));
                 FTR(0, j, 0);
                 if (merge) gemm(0u, 1, 2, j > 0, j, 13);        // D1z | D1r in one N = 2 Hc instruction per k-step
                 else gemm(0u, 2, 1, j > 0, j, 13);              // D1z, D1r
                 umma_commit_cl<CL>(&d1_full);
                 FTR(0, j, 1);
-                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, true);   // r*h
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, !(TS && POI_FUSED_PUSH));   // r*h
                 FTR(0, j, 2);
                 gemm((uint32_t)(2 * Hc), 1, 1, true, j, 14);    // D2
                 umma_commit_cl<CL>(&d2_full);
@@ -704,7 +737,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             for (int s = 0; s < 4; ++s) { mbar_init(&in_full[h][s], 32); mbar_init(&in_empty[h][s], 128); }
         mbar_init(&s_done, 256); mbar_init(&dm_full, CL);
 #pragma unroll
-        for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], 1); mbar_init(&conv_done[o], 256); }
+        for (int o = 0; o < CL; ++o) { mbar_init(&a_ready[o], (SPLIT3 && CL > 1 && POI_FUSED_PUSH) ? 256 : 1); mbar_init(&conv_done[o], 256); }
         mbar_init(&dh1_done, CL); mbar_init(&ddh_full, CL);
         fence_barrier_init();
     }
@@ -792,6 +825,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 warp_store_chunk(s3, lane, dl, DAw + 2 * H + c0, 3 * H, rows_valid);    // DA_c
                 mbar_arrive(r2); mbar_arrive(r3);
             }
+            if (TS && POI_FUSED_PUSH) push_slice_ts<CL>(send, a_hi + (uint32_t)cr * KBc * A_KB_BYTES, (uint32_t)KBc * A_KB_BYTES, a_ready, cr, (int)threadIdx.x);
             if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
             else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             // ---- M1: A <- da_z (after every CTA's GEMM_M has read da_c) ----
@@ -808,6 +842,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 if (TS) tmem_wait_st();
                 if (lane == 0 && warp == 0) FTR(1, it, 9);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_z
+                if (TS && POI_FUSED_PUSH) push_slice_ts<CL>(send, a_hi + (uint32_t)cr * KBc * A_KB_BYTES, (uint32_t)KBc * A_KB_BYTES, a_ready, cr, (int)threadIdx.x);
                 if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
                 else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             }
@@ -847,6 +882,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
                 if (TS) tmem_wait_st();
                 if (lane == 0 && warp == 0) FTR(1, it, 12);
                 fence_async_smem(); tc_fence_before(); mbar_arrive(&s_done);                  // A = da_r
+                if (TS && POI_FUSED_PUSH) push_slice_ts<CL>(send, a_hi + (uint32_t)cr * KBc * A_KB_BYTES, (uint32_t)KBc * A_KB_BYTES, a_ready, cr, (int)threadIdx.x);
                 if (TS) convert_incoming_ts<CL>(a_ready, conv_done, pc, a_hi, tmem, tl, H, cr, KBc, row, hf);
                 else convert_incoming<SPLIT3, CL>(a_ready, conv_done, pc, a_hi, a_lo, cr, KBc, row, hf);
             }
@@ -882,7 +918,7 @@ k_gru_bwd_fused(const float* __restrict__ DHl, const float* __restrict__ Z, cons
             const uint32_t slice_off = (uint32_t)cr * KBc * A_KB_BYTES, slice_bytes = (uint32_t)KBc * A_KB_BYTES;
             // operand hand-over + one GEMM over K = H in arrival order (own k-blocks, then owner cr-1, cr-2, ...)
             auto gemm = [&](uint32_t dcol, bool fresh, int it, int slot) {
-                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, true);
+                begin_exchange<SPLIT3, CL>(&s_done, ps, a_ready, a_hi, send, slice_off, slice_bytes, cr, !(TS && POI_FUSED_PUSH));
                 FTR(1, it, slot);
                 for (int i = 0; i < CL; ++i) {
                     const int o = (cr - i + CL) % CL;
