@@ -187,6 +187,19 @@ class Var:
         env = Env(bind={k: to_tensor(v) for k, v in (inputs_to_values or {}).items()})
         return _to_numpy(ev(self, env))
 
+    # numpy ufuncs applied to symbolic variables (PRME.py:121 calls Load_Data_prme.cal_dis, which is written with
+    # np.sin / np.cos / np.arcsin / np.sqrt / np.power / np.multiply, on Theano variables)
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        f = _UFUNCS.get(ufunc.__name__)
+        if method != "__call__" or f is None or kw:
+            return NotImplemented
+        return Op(tuple(as_var(i) for i in inputs), lambda *a: f(*[x.to(FLOAT) if not x.is_floating_point() else x for x in a]))
+
+
+_UFUNCS = {"multiply": torch.mul, "add": torch.add, "subtract": torch.sub, "true_divide": torch.div, "divide": torch.div,
+           "power": torch.pow, "sin": torch.sin, "cos": torch.cos, "arcsin": torch.asin, "sqrt": torch.sqrt, "exp": torch.exp,
+           "log": torch.log, "negative": torch.neg, "absolute": torch.abs}
+
 
 def _true_div(a, b):
     if not a.is_floating_point() and not b.is_floating_point():
@@ -304,6 +317,17 @@ class Subtensor(Var):
                 self.ndim = base.ndim - 1 + idx.ndim
             elif isinstance(idx, (list, np.ndarray)):
                 self.ndim = base.ndim - 1 + np.ndim(idx)
+        elif base.ndim is not None:
+            n_int, adv = 0, []
+            for i in idx:
+                if isinstance(i, (int, np.integer)):
+                    n_int += 1
+                elif isinstance(i, Var):
+                    adv.append(i.ndim)
+                elif isinstance(i, (list, np.ndarray)):
+                    adv.append(np.ndim(i))
+            if all(a is not None for a in adv):
+                self.ndim = base.ndim - n_int - len(adv) + (max(adv) if adv else 0)
 
     def compute(self, env):
         return ev(self.base, env)[_resolve_index(self.idx, env)]
@@ -387,7 +411,9 @@ def t_concatenate(items, axis=0):
     def f(*vals):
         dt = FLOAT if any(v.is_floating_point() for v in vals) else INT
         return torch.cat([v.to(dt) for v in vals], dim=axis)
-    return Op(items, f)
+    out = Op(items, f)
+    out.ndim = next((i.ndim for i in items if i.ndim is not None), None)
+    return out
 
 
 def _shape_list(shape, env):

@@ -204,6 +204,41 @@ def case_scores(mods, name="scores"):
     print("wrote ref_" + name)
 
 
+
+def case_scores_prme_geoie(mods, name="scores_prme_geoie"):
+    """compute_sub_all_scores of the reference's PRME (PRME.py:109-132, incl. the haversine weight through
+    Load_Data_prme.cal_dis) and GeoIE (GeoIE.py:117-127, incl. its `n_H` quirk) classes on injected trained_* arrays."""
+    PRME, GeoIE = mods[3], mods[4]
+    rs = np.random.RandomState(41)
+    n_user, n_item, d, tl, lmax = 6, 25, 8, 4, 7
+    lens = rs.randint(2, lmax + 1, size=n_user)
+    tra = np.full((n_user, lmax), n_item); tra_m = np.zeros((n_user, lmax), dtype=np.int32)
+    for u in range(n_user):
+        tra[u, :lens[u]] = rs.randint(0, n_item, lens[u]); tra_m[u, :lens[u]] = 1
+    tes = rs.randint(0, n_item, size=(n_user, tl)); tes_m = np.ones((n_user, tl), dtype=np.int32)
+    tes_m[0, 3:] = 0; tes[0, 3:] = n_item
+    cordi = np.stack([rs.uniform(1.22, 1.47, n_item + 1), rs.uniform(103.60, 104.04, n_item + 1)], 1)
+    ds_, dp_, du_ = rs.uniform(-0.5, 0.5, (n_item + 1, d)), rs.uniform(-0.5, 0.5, (n_item, d)), rs.uniform(-0.5, 0.5, (n_user, d))
+    zeros_t = np.zeros_like(tra); zeros_f = np.zeros(tra.shape)
+    train5 = [tra.tolist(), zeros_t.tolist(), zeros_f.tolist(), tra_m.tolist(), tra.tolist()]
+    test5 = [tes.tolist(), np.zeros_like(tes).tolist(), np.zeros(tes.shape).tolist(), tes_m.tolist(), tes.tolist()]
+    m = PRME.OboPrme(train5, test5, [ALPHA, LAM], 360, 0.2, cordi, n_user, n_item, d)
+    m.trained_ds.set_value(ds_); m.trained_dp.set_value(dp_); m.trained_du.set_value(du_)
+    se = np.array([0, 2, 3, 5], dtype=np.int32)
+    prme_scores = m.compute_sub_all_scores(se)
+    g_, h_, z_ = (rs.uniform(-0.5, 0.5, (n_item + 1, d)) for _ in range(3))
+    t_ = rs.uniform(-0.5, 0.5, (n_user, d))
+    ulptai = np.zeros((n_user, 1))
+    gm = GeoIE.GeoIE([tra.tolist(), tra.tolist(), lens.tolist(), tra_m.tolist()], [tes.tolist(), tes.tolist()], [ALPHA, LAM],
+                     n_user, n_item, d, d, ulptai)
+    gm.trained_g.set_value(g_); gm.trained_h.set_value(h_); gm.trained_z.set_value(z_); gm.trained_t.set_value(t_)
+    geo_scores = gm.compute_sub_all_scores(se)
+    np.savez_compressed(os.path.join(HERE, "ref_" + name + ".npz"), tra=tra, tra_m=tra_m, tes=tes, tes_m=tes_m, cordi=cordi, ds=ds_, dp=dp_,
+                        du=du_, g=g_, h=h_, z=z_, t=t_, se=se, n_item=np.int64(n_item), cw=np.float64(0.2), prme_scores=prme_scores,
+                        geo_scores=geo_scores)
+    print("wrote ref_" + name)
+
+
 def case_host(name="host"):
     """Host-side functions of the reference called directly (pure numpy / Python, no Theano): the per-user metric
     functions of public/Valuate.py:23-99 and the index builders of public/Load_Data_by_length.py:24-42,115-180.
@@ -266,4 +301,5 @@ if __name__ == "__main__":
     case_geoie(mods, "geoie_tiny")
     case_bpr_batch(mods)
     case_scores(mods)
+    case_scores_prme_geoie(mods)
     case_host()

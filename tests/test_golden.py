@@ -33,7 +33,7 @@ def _check(st, final, tol=1e-12):
 
 def test_golden_files_present():
     assert len(glob.glob(os.path.join(G, "*.npz"))) >= 15
-    assert len(glob.glob(os.path.join(G, "ref_*.npz"))) >= 10
+    assert len(glob.glob(os.path.join(G, "ref_*.npz"))) >= 11
 
 
 @pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape", "ref_obo_gru_tiny", "ref_gru_batch2_c1shape"])

@@ -138,3 +138,23 @@ def test_scores_and_auc_preference_reference_golden(engine):
     s.trained_users.set_value(z["users"]); s.trained_items.set_value(z["items"]); s.wd.set_value(float(z["wd"])); s.update_prob(z["prob"])
     assert_close(s.compute_sub_all_scores(se), z["spatial_scores"], 1e-5, "spatial scores")
     assert np.array_equal(np.asarray(s.compute_sub_auc_preference(se)), z["spatial_auc"])
+
+
+def test_prme_geoie_scores_reference_golden(engine):
+    """compute_sub_all_scores of PRME (PRME.py:109-132: haversine-weighted metric distances) and GeoIE (GeoIE.py:117-127,
+    with its `n_H` = sum-of-ids quirk) against the reference classes' own output (ref_scores_prme_geoie.npz)."""
+    from poi_b200.public.GeoIE import GeoIE
+    from poi_b200.public.PRME import OboPrme
+    z = np.load(os.path.join(G, "ref_scores_prme_geoie.npz"))
+    tra, tra_m, tes, tes_m = z["tra"], z["tra_m"], z["tes"], z["tes_m"]
+    n_user, n_item, d = tra.shape[0], int(z["n_item"]), z["du"].shape[1]
+    se = z["se"]
+    zt, zf = np.zeros_like(tra), np.zeros(tra.shape)
+    train5 = [tra, zt, zf, tra_m, tra]
+    test5 = [tes, np.zeros_like(tes), np.zeros(tes.shape), tes_m, tes]
+    m = OboPrme(train5, test5, [A, L], 360, float(z["cw"]), z["cordi"], n_user, n_item, d)
+    m.trained_ds.set_value(z["ds"]); m.trained_dp.set_value(z["dp"]); m.trained_du.set_value(z["du"])
+    assert_close(m.compute_sub_all_scores(se), z["prme_scores"], 2e-5, "prme scores")
+    gm = GeoIE([tra, tra, tra_m.sum(1), tra_m], [tes, tes], [A, L], n_user, n_item, d, d, np.zeros((n_user, 1)))
+    gm.trained_g.set_value(z["g"]); gm.trained_h.set_value(z["h"]); gm.trained_z.set_value(z["z"]); gm.trained_t.set_value(z["t"])
+    assert_close(gm.compute_sub_all_scores(se), z["geo_scores"], 2e-5, "geoie scores")
