@@ -1,5 +1,9 @@
+"""One-by-one (B = 1) trajectories of the c2 workload under the four combinations of graph replay and the SIMT
+small-batch path, against the kernel-by-kernel tensor-core path: graph replay must be bit-identical; the SIMT path
+agrees to fp32 rounding on the first calls and then diverges like the float32 vs float64 oracles do (the trajectory is
+chaotic at this scale)."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 import poi_b200
