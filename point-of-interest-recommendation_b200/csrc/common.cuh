@@ -190,6 +190,7 @@ static int stage_reserve(poi_engine* e, size_t bytes) {
     size_t cap = poi_align_up(bytes + (bytes >> 2), 4096);
     POI_CK(e, cudaMallocHost((void**)&e->h_stage, cap));
     e->h_stage_cap = cap;
+    e->arena_gen++;          // captured graphs copy from the old staging buffer: invalidate them
     return 0;
 }
 
