@@ -227,7 +227,7 @@ __global__ void k_dhl_nohead(const float* __restrict__ ev, const float* __restri
 // ---------------------------------------------------------------------------------------------
 constexpr int LOSS_RK = 8;          // logits per lane kept in registers by k_loss_head (rows up to 256 wide)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc,
             const float* __restrict__ XDiff, int H4, const int32_t* __restrict__ DPt,
             const int32_t* __restrict__ DQt, const int32_t* __restrict__ lensB,
