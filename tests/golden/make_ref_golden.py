@@ -239,6 +239,43 @@ def case_scores_prme_geoie(mods, name="scores_prme_geoie"):
     print("wrote ref_" + name)
 
 
+
+def case_revisit(mods, name="revisit"):
+    """Longer one-by-one trajectories with revisited users (three passes), short users (L = 2: a single scan step) and
+    duplicate POIs, through the reference's OboSpatialGru and OboGru.  CPU pin only (oracle vs reference); inputs are
+    generated here, not taken from an oracle-made golden."""
+    from oracle import fixtures as Fx
+    GRU, GS = mods[0], mods[1]
+    rs = np.random.RandomState(51)
+    n_user, n_item, d, lmax, D = 5, 40, 12, 11, 30
+    P, Q, M = Fx.ragged_sequences(rs, n_user, n_item, lmax, min_len=2, dup_prob=0.5)
+    P[1, 2:] = n_item; Q[1, 2:] = n_item; M[1, 2:] = 0                   # user 1: L = 2
+    DP, DQ = Fx.interval_matrices(rs, P, Q, M, D)
+    st = Fx.nonzero_bias(rs, Fx.gru_state(rs, n_item, d, d, D), dtype=np.float64)
+    order = [0, 1, 2, 3, 4] * 3 + [1, 1]
+    tb, tm, tn = dummy_test(n_user, n_item)
+    m = GS.OboSpatialGru([P.tolist(), M.tolist(), Q.tolist()], [tb, tm, tn], [DP.tolist(), [[D]] * n_user, DQ.tolist()],
+                         [ALPHA, LAM], n_user, n_item, [D, 0.2], d, d)
+    names = ("lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight")
+    for k in names:
+        getattr(m, k).set_value(st[k])
+    outs = []
+    for u in order:
+        los, sur, upq, w = m.train(int(u))
+        outs.append([float(los), float(sur), float(upq), float(w[0]), float(w[1])])
+    stg = {k: st[k] for k in ("lt", "wh", "bi")}
+    stg["ui"] = rs.uniform(-0.5, 0.5, (3, d, d))
+    g = GRU.OboGru([P.tolist(), M.tolist(), Q.tolist()], [tb, tm, tn], [ALPHA, LAM], n_user, n_item, d, d)
+    for k in ("lt", "ui", "wh", "bi"):
+        getattr(g, k).set_value(stg[k])
+    glosses = [float(g.train(int(u))) for u in order]
+    np.savez_compressed(os.path.join(HERE, "ref_" + name + ".npz"), P=P, Q=Q, M=M, DP=DP, DQ=DQ, n_dist=np.int64(D), order=np.asarray(order),
+                        outs=np.asarray(outs), gru_losses=np.asarray(glosses),
+                        **{"init_" + k: np.asarray(v) for k, v in st.items()}, init_gru_ui=stg["ui"],
+                        **final_state(m, names), **{"gfinal_" + k: np.asarray(getattr(g, k).get_value()) for k in ("lt", "ui", "wh", "bi")})
+    print("wrote ref_" + name)
+
+
 def case_host(name="host"):
     """Host-side functions of the reference called directly (pure numpy / Python, no Theano): the per-user metric
     functions of public/Valuate.py:23-99 and the index builders of public/Load_Data_by_length.py:24-42,115-180.
@@ -302,4 +339,5 @@ if __name__ == "__main__":
     case_bpr_batch(mods)
     case_scores(mods)
     case_scores_prme_geoie(mods)
+    case_revisit(mods)
     case_host()

@@ -33,7 +33,7 @@ def _check(st, final, tol=1e-12):
 
 def test_golden_files_present():
     assert len(glob.glob(os.path.join(G, "*.npz"))) >= 15
-    assert len(glob.glob(os.path.join(G, "ref_*.npz"))) >= 11
+    assert len(glob.glob(os.path.join(G, "ref_*.npz"))) >= 12
 
 
 @pytest.mark.parametrize("name", ["obo_gru_tiny", "gru_batch2_c1shape", "ref_obo_gru_tiny", "ref_gru_batch2_c1shape"])
@@ -110,3 +110,32 @@ def test_bpr_minibatch_against_reference_class():
     assert np.allclose(losses, z["losses"], rtol=1e-12)
     assert np.max(np.abs(st["ux"] - z["final_ux"])) < 1e-13 and np.max(np.abs(st["lt"] - z["final_lt"])) < 1e-13
     assert abs(OM.l2_value(st, ["ux", "lt"], L) - float(z["l2"])) < 1e-12
+
+
+def test_revisit_trajectories_against_reference_classes():
+    """Three passes over revisited users (incl. an L = 2 user and duplicate POIs) through the reference's OboSpatialGru and
+    OboGru (tests/golden/ref_revisit.npz): both oracle statements must follow the reference step for step."""
+    z = np.load(os.path.join(G, "ref_revisit.npz"))
+    P, Q, M, DP, DQ = z["P"], z["Q"], z["M"], z["DP"], z["DQ"]
+    names = ["lt", "di", "ui", "wh", "bi", "vs", "bs", "wd", "loss_weight"]
+    st = {k: np.asarray(z["init_" + k], dtype=np.float64) for k in names}
+    st2 = dict(st)
+    outs, outs2 = [], []
+    for u in z["order"]:
+        (los, sur, upq, w), st = OM.obo_spatial_gru_train(st, P[u], Q[u], DP[u], DQ[u], M[u], A, L)
+        outs.append([los, sur, upq, w[0], w[1]])
+        (los, sur, upq, w), st2 = E.gru_family_train_batch(st2, P[u:u + 1], Q[u:u + 1], M[u:u + 1], A, L, DP[u:u + 1], DQ[u:u + 1])
+        outs2.append([los, sur, upq, w[0], w[1]])
+    assert np.allclose(outs, z["outs"], rtol=1e-10) and np.allclose(outs2, z["outs"], rtol=1e-9)
+    for k in names:
+        assert np.max(np.abs(np.asarray(st[k]) - z["final_" + k])) < 1e-11, k
+        assert np.max(np.abs(np.asarray(st2[k]) - z["final_" + k])) < 1e-10, k
+    g = {"lt": np.asarray(z["init_lt"], np.float64), "wh": np.asarray(z["init_wh"], np.float64),
+         "bi": np.asarray(z["init_bi"], np.float64), "ui": np.asarray(z["init_gru_ui"], np.float64)}
+    gl = []
+    for u in z["order"]:
+        l, g = OM.obo_gru_train(g, P[u], Q[u], M[u], A, L)
+        gl.append(l)
+    assert np.allclose(gl, z["gru_losses"], rtol=1e-10)
+    for k in ("lt", "ui", "wh", "bi"):
+        assert np.max(np.abs(g[k] - z["gfinal_" + k])) < 1e-11, k

@@ -89,7 +89,7 @@ def test_committed_ref_goldens_are_what_the_reference_code_produces(tmp_path):
              "for name, case in (('obo_gru_tiny', 'case_gru'), ('gru_batch2_c1shape', 'case_gru'), ('obo_spatial_tiny', 'case_spatial'),\n"
              "                   ('obo_bpr_tiny', 'case_bpr'), ('obo_prme_tiny', 'case_prme'), ('geoie_tiny', 'case_geoie')):\n"
              "    g[case](mods, name)\n"
-             "g['case_bpr_batch'](mods); g['case_scores'](mods); g['case_scores_prme_geoie'](mods)\n"
+             "g['case_bpr_batch'](mods); g['case_scores'](mods); g['case_scores_prme_geoie'](mods); g['case_revisit'](mods)\n"
              "g['case_host']()\n" % str(scratch))
     subprocess.check_call([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.DEVNULL)
     checked = 0
@@ -101,7 +101,7 @@ def test_committed_ref_goldens_are_what_the_reference_code_produces(tmp_path):
         for k in new.files:
             assert np.allclose(new[k], old[k], rtol=1e-12, atol=1e-14), (f, k)
         checked += 1
-    assert checked == 10          # every case but the slow obo_spatial_d20_D200
+    assert checked == 11          # every case but the slow obo_spatial_d20_D200
 
 
 def test_numpy_ufuncs_on_symbolic_variables():
