@@ -34,7 +34,12 @@ import types
 import numpy as np
 import torch
 
-FLOAT = torch.float64
+import os
+
+# POI_SHIM_FLOAT=32 evaluates the same graphs in float32 (the reference's `floatX=float32` setting) -- used only to measure
+# how far float32 arithmetic moves the reference's own trajectories from the float64 vectors (tests/test_theano_shim.py)
+FLOAT = torch.float32 if os.environ.get("POI_SHIM_FLOAT") == "32" else torch.float64
+NP_FLOAT = np.float32 if FLOAT == torch.float32 else np.float64
 INT = torch.int64
 
 
@@ -95,7 +100,7 @@ def to_tensor(x):
     a = np.asarray(x)
     if a.dtype.kind in "iub":
         return torch.as_tensor(a.astype(np.int64))
-    return torch.as_tensor(a.astype(np.float64))
+    return torch.as_tensor(a.astype(NP_FLOAT))
 
 
 def ev(v, env):
@@ -737,7 +742,7 @@ def install():
 
     th = mod("theano")
     th.__poi_shim__ = True
-    th.config = types.SimpleNamespace(floatX="float64")
+    th.config = types.SimpleNamespace(floatX="float32" if FLOAT == torch.float32 else "float64")
     th.shared, th.function, th.scan, th.grad = shared, function, scan, grad
 
     T = mod("theano.tensor")

@@ -109,3 +109,31 @@ def test_numpy_ufuncs_on_symbolic_variables():
     x = th.shared(np.array([0.1, 0.7]))
     y = np.sqrt(np.power(np.sin(np.multiply(x, 2.0)), 2) + np.cos(x))
     assert np.allclose(y.eval(), np.sqrt(np.sin(np.array([0.2, 1.4])) ** 2 + np.cos(np.array([0.1, 0.7]))))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/public"), reason="reference tree not mounted (GPU box)")
+def test_float32_reference_stays_close_to_the_float64_vectors(tmp_path):
+    """The reference runs with floatX = float32.  Evaluate its OboSpatialGru / OboGru graphs in float32 on the shim and
+    measure the distance to the committed float64 vectors: it must be a small part of the 1e-4 parity budget."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    scratch = tmp_path / "golden"
+    scratch.mkdir()
+    for f in os.listdir(gold):
+        if f.endswith(".npz") and not f.startswith("ref_"):
+            os.symlink(os.path.join(gold, f), scratch / f)
+    code = ("import runpy, sys, types; sys.argv=['x']; g = runpy.run_path(%r, run_name='gen')\n"
+            "for fn in g.values():\n"
+            "    if isinstance(fn, types.FunctionType): fn.__globals__['HERE'] = %r\n"
+            "mods = g['load_reference']()\n"
+            "g['case_gru'](mods, 'obo_gru_tiny'); g['case_spatial'](mods, 'obo_spatial_tiny')\n"
+            % (os.path.join(gold, "make_ref_golden.py"), str(scratch)))
+    env = dict(os.environ, POI_SHIM_FLOAT="32")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.DEVNULL, env=env)
+    worst = 0.0
+    for f, keys in (("ref_obo_gru_tiny.npz", ("losses", "final_lt", "final_ui", "final_wh")),
+                    ("ref_obo_spatial_tiny.npz", ("outs", "final_lt", "final_di", "final_ui", "final_wh", "final_vs", "hts", "sts"))):
+        new, old = np.load(scratch / f), np.load(os.path.join(gold, f))
+        for k in keys:
+            a, b = np.asarray(new[k], np.float64), np.asarray(old[k], np.float64)
+            worst = max(worst, float(np.max(np.abs(a - b)) / np.max(np.abs(b))))
+    assert worst < 2e-5, worst
