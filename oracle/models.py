@@ -354,6 +354,39 @@ def obo_prme_train(state, uidx, pq, dist, gap, alpha, lam, thd, cw, dtype=F64):
     return float(upq.detach()), new
 
 
+def obo_prme_train_k(state, uidx, p, qs, prev, dist, gap, alpha, lam, thd, cw, dtype=F64):
+    """BASELINE.json's C3 line ("PRME ... neg=20"): K negatives per positive.  NOT a reference function -- the reference
+    draws one negative (PRME.py:172-219); this is the driver-defined generalisation SURVEY.md 8(a6) allows, stated so that
+    it reduces to ``obo_prme_train`` at K = 1: pqidx = [p, q_1 .. q_K, prev], upq = sum_k log sigmoid(Dq_k - Dp), L2 over
+    every gathered row, rows written back in pqidx order (last occurrence wins).  Checker for a future K-negative kernel;
+    no product code calls it."""
+    qs = [int(q) for q in np.asarray(qs).reshape(-1)]
+    K = len(qs)
+    pq = np.asarray([int(p)] + qs + [int(prev)], dtype=np.int64)
+    du = _t(state["du"][uidx], dtype, True)
+    dppq = _t(state["dp"][pq], dtype, True)
+    dspq = _t(state["ds"][pq], dtype, True)
+    w = (1.0 + float(dist)) ** 0.25
+    gate = int(np.int32(gap)) > int(thd)
+
+    def D(i):
+        Dp_ = ((du - dppq[i]) ** 2).sum()
+        if gate:
+            return Dp_
+        return w * (cw * Dp_ + (1 - cw) * ((dspq[i] - dspq[K + 1]) ** 2).sum())
+    Dp = D(0)
+    upq = sum(_logsig(-Dp + D(1 + k)) for k in range(K))
+    cost = upq - 0.5 * lam * ((du ** 2).sum() + (dppq ** 2).sum() + (dspq ** 2).sum())
+    cost.backward()
+    g_ds = dspq.grad if dspq.grad is not None else torch.zeros_like(dspq)
+    new = dict(state)
+    tab = state["du"].copy(); tab[uidx] = _np(du + alpha * du.grad).astype(tab.dtype)
+    new["du"] = tab
+    new["dp"] = _last_writer_set(state["dp"], pq, _np(dppq + alpha * dppq.grad).astype(state["dp"].dtype))
+    new["ds"] = _last_writer_set(state["ds"], pq, _np(dspq + alpha * g_ds).astype(state["ds"].dtype))
+    return float(upq.detach()), new
+
+
 # ----------------------------------------------------------------------------------------------
 # GeoIE  (public/GeoIE.py:129-194)
 # ----------------------------------------------------------------------------------------------

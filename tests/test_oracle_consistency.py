@@ -78,3 +78,23 @@ def test_updates_use_pre_update_values_and_unique_rows(prob):
     pad = st["lt"].shape[0] - 1
     n_pad = 2 * (M.shape[1] - int(M[u].sum()))
     assert np.allclose(new["lt"][pad], st["lt"][pad] * (1 - A * L * n_pad), rtol=1e-13)
+
+
+def test_prme_k_negatives_reduces_to_the_reference_at_k1():
+    """The K-negative statement of PRME (checker for BASELINE.json's C3 'neg=20' line) equals the reference's single-negative
+    step at K = 1, in both branches of the time-gap gate, and for K > 1 its loss is the sum over the negatives."""
+    import numpy as np
+    from oracle import fixtures as Fx
+    from oracle import models as OM
+    rs = np.random.RandomState(9)
+    st = {k: np.asarray(v, dtype=np.float64) for k, v in Fx.prme_state(rs, 4, 30, 8).items()}
+    for gap in (100, 500):                                     # below / above the 360-minute threshold
+        l1, s1 = OM.obo_prme_train(st, 2, [5, 9, 7], 3.3, gap, 0.01, 0.001, 360, 0.2)
+        lk, sk = OM.obo_prme_train_k(st, 2, 5, [9], 7, 3.3, gap, 0.01, 0.001, 360, 0.2)
+        assert abs(l1 - lk) < 1e-15
+        for k in ("du", "dp", "ds"):
+            assert np.array_equal(s1[k], sk[k]), k
+    l3, s3 = OM.obo_prme_train_k(st, 2, 5, [9, 11, 9], 7, 3.3, 100, 0.01, 0.001, 360, 0.2)
+    parts = [OM.obo_prme_train(st, 2, [5, q, 7], 3.3, 100, 0.01, 0.001, 360, 0.2)[0] for q in (9, 11, 9)]
+    assert abs(l3 - sum(parts)) < 1e-12
+    assert not np.array_equal(s3["dp"][11], st["dp"][11]) and np.array_equal(s3["dp"][12], st["dp"][12])
