@@ -89,6 +89,15 @@ class RowExchange:
         return self._a2a(payload[self.order].contiguous(), self.send_split, self.recv_split)
 
 
+def pull_plan(count_matrix, me: int):
+    """Peer-memory exchange, owner side.  count_matrix[p, o] = number of records rank p addresses to owner o; rank p's
+    permutation list groups its record numbers by owner in owner order 0..W-1.  Returns, for owner `me`, the first
+    entry of its group in every rank's list and the group sizes -- the arguments of `poi_pull_segments`."""
+    cm = np.asarray(count_matrix, dtype=np.int64)
+    world = cm.shape[0]
+    return [int(cm[p, :me].sum()) for p in range(world)], [int(cm[p, me]) for p in range(world)]
+
+
 def shard_rows(table: np.ndarray, rank: int, world: int) -> np.ndarray:
     """Rows owned by `rank`: table[rank::world] (local index = global // world)."""
     return np.ascontiguousarray(table[rank::world])
@@ -307,8 +316,7 @@ class ShardedSpatialGru:
         if self.trace: self.trace.mark('allreduce(dense+sums)')
         cm = self._sums[3:].cpu().numpy().reshape(W, W).astype(np.int64)       # cm[p, o]: records p -> o (one host sync)
         if self.trace: self.trace.mark('counts_to_host')
-        src_off = [int(cm[p, :me].sum()) for p in range(W)]
-        n = [int(cm[p, me]) for p in range(W)]
+        src_off, n = pull_plan(cm, me)
         n_recv = int(sum(n))
         recv_local = torch.empty(n_recv, dtype=torch.int32, device=dev)
         recv_grads = torch.empty((n_recv, d), dtype=torch.float32, device=dev)
