@@ -48,13 +48,15 @@ int         poi_launch_count(poi_engine* e, int64_t* out);
 int         poi_last_phase_ms(poi_engine* e, float* out8);
 int         poi_enable_phase_timing(poi_engine* e, int on);
 /* Built-in per-launch profiler: when enabled every kernel the engine launches is bracketed by CUDA
- * events on the engine stream and accumulated per category.  out = double[12][4] =
+ * events on the engine stream and accumulated per category.  out = double[POI_KPROF_NCAT][4] =
  * {ms, launches, algorithmic flops, algorithmic bytes} for categories
- * 0 other, 1 index prep/sort/unique, 2 gather, 3 GEMM (TN), 4 weight-gradient GEMM + dense update,
- * 5 loss head, 6 elementwise, 7 sparse row update, 8 BPR/PRME, 9 GeoIE, 10 eval, 11 reductions. */
+ * 0 other, 1 index prep/sort/unique, 2 gather, 3 GEMM (TN: input projection, head, dgrad), 4 weight-gradient GEMM +
+ * dense update, 5 loss head, 6 elementwise, 7 sparse row update, 8 BPR/PRME, 9 GeoIE, 10 eval, 11 reductions,
+ * 12 forward recurrence kernel(s), 13 backward recurrence kernel(s). */
+#define POI_KPROF_NCAT 14
 int         poi_kprof_enable(poi_engine* e, int on);
 int         poi_kprof_reset(poi_engine* e);
-int         poi_kprof_get(poi_engine* e, double* out48);
+int         poi_kprof_get(poi_engine* e, double* out /* [POI_KPROF_NCAT * 4] */);
 /* 0 = SIMT fp32 FMA GEMMs, 1 = tcgen05 3xTF32 (fp32-faithful), 2 = tcgen05 1xTF32 */
 int         poi_set_gemm_mode(poi_engine* e, int mode);
 int         poi_get_gemm_mode(poi_engine* e, int* mode);

@@ -16,6 +16,29 @@ if not os.path.exists(LIB_PATH):
         "libpoi_b200.so is not built (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "from the repository root. There is no CPU fallback." % LIB_PATH)
 
+
+
+def _source_hash():
+    """Same digest as __graft_entry__.source_hash(): csrc/*, include/poi_engine.h and the nvcc flags."""
+    import hashlib
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+    csrc = os.path.join(_HERE, "csrc")
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "poi_engine.h")
+    h = hashlib.sha256(" ".join(flags).encode())
+    for f in [os.path.join(csrc, f) for f in sorted(os.listdir(csrc))] + [hdr]:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+# a prebuilt binary that no longer matches its sources must not run silently (it travels to the GPU box as a file)
+_stamp = LIB_PATH + ".srchash"
+if not os.environ.get("POI_B200_LIB") and os.path.exists(_stamp) and os.path.isdir(os.path.join(_HERE, "csrc")):
+    if open(_stamp).read().strip() != _source_hash():
+        raise ImportError("libpoi_b200.so is stale: csrc/ or include/poi_engine.h changed since it was built. Rebuild with "
+                          "`python -c 'import __graft_entry__ as g; g.build()'`.")
+
 lib = ctypes.CDLL(LIB_PATH)
 
 

@@ -16,7 +16,8 @@ struct PoiChunk { char* ptr; size_t cap; };
 
 // kernel categories for the built-in per-launch profiler (bench.py's roofline numbers)
 enum PoiCat { CAT_OTHER = 0, CAT_INDEX = 1, CAT_GATHER = 2, CAT_GEMM = 3, CAT_WGRAD = 4, CAT_LOSS = 5,
-              CAT_ELTWISE = 6, CAT_ROWS = 7, CAT_MF = 8, CAT_GEOIE = 9, CAT_EVAL = 10, CAT_REDUCE = 11, POI_NCAT = 12 };
+              CAT_ELTWISE = 6, CAT_ROWS = 7, CAT_MF = 8, CAT_GEOIE = 9, CAT_EVAL = 10, CAT_REDUCE = 11,
+              CAT_RECUR_FWD = 12, CAT_RECUR_BWD = 13, POI_NCAT = POI_KPROF_NCAT };
 struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
 
 struct poi_engine {
@@ -41,6 +42,7 @@ struct poi_engine {
     // per-launch profiler: CUDA events around every kernel on the engine stream
     bool kprof = false;
     int cur_cat = CAT_OTHER;
+    int gemm_cat = -1;               // >= 0: GEMM launches are booked under this category (per-step recurrence GEMMs)
     double cur_flops = 0.0, cur_bytes = 0.0;
     std::vector<ProfRec> recs;
     size_t nrec = 0;
@@ -91,7 +93,7 @@ static inline ProfRec* prof_begin(poi_engine* e);
 
 // every kernel launch goes through here so that poi_launch_count is exact; `cat`/work set by
 // POI_CAT apply to the launches that follow
-#define POI_CAT(e, c, fl, by) do { (e)->cur_cat = (c); (e)->cur_flops = (double)(fl); (e)->cur_bytes = (double)(by); } while (0)
+#define POI_CAT(e, c, fl, by) do { (e)->cur_cat = ((c) == CAT_GEMM && (e)->gemm_cat >= 0) ? (e)->gemm_cat : (c); (e)->cur_flops = (double)(fl); (e)->cur_bytes = (double)(by); } while (0)
 #define POI_LAUNCH(e, kern, grid, block, smem, ...)                              \
     do {                                                                         \
         ProfRec* _pr = (e)->kprof ? prof_begin(e) : nullptr;                     \

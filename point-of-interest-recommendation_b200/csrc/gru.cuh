@@ -495,6 +495,7 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
         POI_TRY(fused::launch_gru_fwd_fused(e, AX, p->wh, Hs, Z, R, C, RH, B, T, H, e->gemm_mode == 1));
         return 0;
     }
+    e->gemm_cat = CAT_RECUR_FWD;
     for (int j = 0; j < T; ++j) {
         const float* hp = Hs + (size_t)j * B * H;
         const float* AXj = AX + (size_t)j * B * 3 * H;
@@ -503,6 +504,7 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
         POI_TRY(gemm_tn(e, RH + o, H, p->wh + (size_t)2 * H * H, H, B, H, j == 0 ? 0 : H,
                         EpiC{AXj, hp, Z + o, C + o, Hs + o + (size_t)B * H, H}));
     }
+    e->gemm_cat = -1;
     return 0;
 }
 
@@ -586,6 +588,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
                 POI_LAUNCH(e, k_bwd_prep, (unsigned)poi_cdiv((int64_t)B * H / 4, 256), 256, 0, DHl + o, Z + o, C + o,
                            Hs + o, DA + (size_t)(T - 1) * B * 3 * H, DHK, B, H);
             }
+            e->gemm_cat = CAT_RECUR_BWD;
             for (int j = T - 1; j >= 0; --j) {
                 size_t o = (size_t)j * B * H;
                 float* DAj = DA + (size_t)j * B * 3 * H;
@@ -596,6 +599,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
                                     EpiDH{DHK, DHl + op, Z + op, C + op, Hs + op, DA + (size_t)(j - 1) * B * 3 * H, H}));
                 }
             }
+            e->gemm_cat = -1;
         }
         POI_TRY(gemm_tn(e, DA, 3 * H, U2T, 3 * H, TB, din, 3 * H, EpiBiasStore{DX, din, nullptr, din}));
     }

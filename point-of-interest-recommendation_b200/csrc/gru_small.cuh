@@ -122,7 +122,7 @@ static int launch_fwd(poi_engine* e, const float* AX, const float* wh, float* Hs
                       int B, int T, int H) {
     const size_t smem = smem_bytes(H);
     POI_CK(e, cudaFuncSetAttribute(k_gru_fwd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
+    POI_CAT(e, CAT_RECUR_FWD, 2.0 * (double)B * T * 3 * H * H, 0);
     POI_LAUNCH(e, k_gru_fwd_small, (unsigned)B, S_THREADS, smem, AX, wh, Hs, Z, R, C, RH, B, T, H);
     return 0;
 }
@@ -130,7 +130,7 @@ static int launch_bwd(poi_engine* e, const float* DHl, const float* Z, const flo
                       const float* wh, float* DA, int B, int T, int H) {
     const size_t smem = smem_bytes(H);
     POI_CK(e, cudaFuncSetAttribute(k_gru_bwd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    POI_CAT(e, CAT_GEMM, 2.0 * (double)B * T * 3 * H * H, 0);
+    POI_CAT(e, CAT_RECUR_BWD, 2.0 * (double)B * T * 3 * H * H, 0);
     POI_LAUNCH(e, k_gru_bwd_small, (unsigned)B, S_THREADS, smem, DHl, Z, R, C, Hs, wh, DA, B, T, H);
     return 0;
 }

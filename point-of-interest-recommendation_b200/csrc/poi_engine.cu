@@ -98,6 +98,7 @@ int poi_kprof_get(poi_engine* e, double* out) {
 static int begin_call(poi_engine* e) {
     POI_CK(e, cudaSetDevice(e->device));
     if (e->nrec > 4096) { POI_CK(e, cudaStreamSynchronize(e->stream)); prof_harvest(e); }
+    e->gemm_cat = -1;
     POI_CAT(e, CAT_OTHER, 0, 0);
     // between poi_gru_mg_prepare and poi_gru_train_mg the arena holds the prepared segments: append, don't reset
     if (!e->prep_valid) POI_TRY(arena_reset(e));

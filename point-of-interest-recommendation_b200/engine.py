@@ -126,7 +126,8 @@ class Engine:
         self._ck(lib.poi_last_phase_ms(self._h, buf))
         return list(buf)
 
-    KPROF_CATS = ["other", "index", "gather", "gemm", "wgrad", "loss", "eltwise", "rows", "mf", "geoie", "eval", "reduce"]
+    KPROF_CATS = ["other", "index", "gather", "gemm", "wgrad", "loss", "eltwise", "rows", "mf", "geoie", "eval", "reduce",
+                  "recur_fwd", "recur_bwd"]
 
     def kprof_enable(self, on: bool):
         self._ck(lib.poi_kprof_enable(self._h, 1 if on else 0))
@@ -136,7 +137,7 @@ class Engine:
 
     def kprof_get(self):
         """{category: dict(ms, launches, flops, bytes)} accumulated since the last reset."""
-        buf = (c_double * 48)()
+        buf = (c_double * (4 * len(self.KPROF_CATS)))()
         self._ck(lib.poi_kprof_get(self._h, buf))
         return {c: dict(ms=buf[i * 4], launches=int(buf[i * 4 + 1]), flops=buf[i * 4 + 2], bytes=buf[i * 4 + 3])
                 for i, c in enumerate(self.KPROF_CATS)}

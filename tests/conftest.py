@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with `-m gpu` on the GPU box)")
+    config.addinivalue_line("markers", "multigpu: spawns torch.distributed.run over >= 2 GPUs of the box (skips on fewer)")
 
 
 @pytest.fixture(scope="session")

@@ -116,29 +116,128 @@ def test_driver_device_negative_sampling_matches_oracle_loop(engine, tmp_path):
         assert np.allclose(hist[epoch]["recall"], rec, atol=1e-12), (hist[epoch]["recall"], rec)
 
 
-def test_bpr_prme_geoie_drivers_run(engine, tmp_path):
-    from poi_b200 import prog_bpr_gru_spatial as d0
-    from poi_b200 import prog_geoie as d2
-    from poi_b200 import prog_prme as d1
+def _valuate_recall(scores, tes_masks_rows, tes_masks, at_nums):
+    """Recall@K of a score matrix through the ported Valuate (ranking + metric definitions are host logic shared by both
+    sides; tests/test_valuate.py pins them to the reference)."""
+    from poi_b200.public.Valuate import _metrics_at, _rank_rows
+    ranks = _rank_rows(np.asarray(scores), at_nums[-1])
+    return _metrics_at(ranks, np.asarray(tes_masks_rows), np.asarray(tes_masks), at_nums)["recall"]
+
+
+def test_bpr_driver_matches_oracle_loop(engine, tmp_path):
+    """prog_bpr_gru_spatial with p['gru'] = 0 (OboBpr; the reference's shipped default): per-epoch loss, l2 and Recall@K
+    against the same ordered (u, p, q) call list run on oracle.models.obo_bpr_train."""
+    from poi_b200 import prog_bpr_gru_spatial as drv
+    from poi_b200.driver_common import shuffled_users
+    from poi_b200.public import Load_Data_by_length as LD
+    from oracle import fixtures as Fx
     path = _dataset(tmp_path)
+    p = drv.default_params()
+    p.update(dataset="Synth.txt", epochs=2, latent_size=8, gru=0, at_nums=[5, 10], batch_size_test=7)
+    random.seed(5)
+    pas = drv.Params(p=p, path=path)
+    st = Fx.bpr_state(np.random.RandomState(3), pas.user_num, pas.item_num, 8)
+    Q = np.asarray([list(r) for r in pas.tra_buys_neg_masks])
+    rstate = random.getstate()
     import os
     cwd = os.getcwd(); os.chdir(tmp_path)
     try:
-        p = d0.default_params(); p.update(dataset="Synth.txt", epochs=3, latent_size=8, gru=0, at_nums=[5, 10])
-        random.seed(1)
-        _, _, h0 = d0.train_valid_or_test(d0.Params(p=p, path=path))
-        assert np.isfinite(h0[-1]["loss"])
-        p = d1.default_params(); p.update(dataset="Synth.txt", epochs=2, latent_size=8, at_nums=[5, 10], batch_size_test=6)
-        random.seed(1)
-        _, _, h1 = d1.train_valid_or_test(d1.Params(p=p, path=path))
-        assert np.isfinite(h1[-1]["loss"]) and h1[-1]["loss"] < 0                  # sum of log sigmoid
-        p = d2.default_params(); p.update(dataset="Synth.txt", epochs=2, latent_size=8, at_nums=[5, 10], batch_size_test=6)
-        random.seed(1); np.random.seed(4)
-        pas = d2.Params(p=p, path=path)
-        _, _, h2 = d2.train_valid_or_test(pas, init=dict(a=0.3, b=0.2))
-        assert np.isfinite(h2[-1]["loss"])
+        model, best, hist = drv.train_valid_or_test(pas, init=st)
     finally:
         os.chdir(cwd)
+    random.setstate(rstate)
+    P, M = np.asarray(pas.tra_buys_masks), np.asarray(pas.tra_masks)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for epoch in range(2):
+        if epoch > 0:
+            Q = np.asarray(LD.fun_random_neg_masks_tra(pas.item_num, pas.tra_buys_masks))
+            LD.fun_random_neg_masks_tes(pas.item_num, pas.tra_buys_masks, pas.tes_buys_masks)   # consumes RNG like the driver
+        loss, l2, ref = OD.epoch_bpr(ref, shuffled_users(pas.user_num, epoch), P, Q, M, p['alpha'], p['lambda'])
+        assert_close(hist[epoch]["loss"], loss, 1e-4, "epoch %d loss" % epoch)
+        assert_close(hist[epoch]["l2"], l2, 1e-4, "epoch %d l2" % epoch)
+        rec = _valuate_recall(OD.user_scores_bpr(ref), pas.tes_buys_masks, pas.tes_masks, p['at_nums'])
+        assert np.allclose(hist[epoch]["recall"], rec, atol=1e-12), (hist[epoch]["recall"], rec)
+    assert_close(model.lt.get_value(), ref["lt"], 1e-4, "lt"); assert_close(model.ux.get_value(), ref["ux"], 1e-4, "ux")
+
+
+def test_prme_driver_matches_oracle_loop(engine, tmp_path):
+    """prog_prme: per-epoch loss (sum of log sigmoid), l2 and Recall@K against the same ordered call list on
+    oracle.models.obo_prme_train; scores through the restated PRME.py:109-132."""
+    from poi_b200 import prog_prme as drv
+    from poi_b200.driver_common import shuffled_users
+    from poi_b200.public import Load_Data_prme as LD
+    from oracle import fixtures as Fx
+    path = _dataset(tmp_path)
+    p = drv.default_params(); p.update(dataset="Synth.txt", epochs=2, latent_size=8, at_nums=[5, 10], batch_size_test=6)
+    random.seed(5)
+    pas = drv.Params(p=p, path=path)
+    st = Fx.prme_state(np.random.RandomState(3), pas.user_num, pas.item_num, 8)
+    Q = np.asarray([list(r) for r in pas.tra_pois_neg_masks])
+    rstate = random.getstate()
+    import os
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        model, best, hist = drv.train_valid_or_test(pas, init=st)
+    finally:
+        os.chdir(cwd)
+    random.setstate(rstate)
+    P, M = np.asarray(pas.tra_pois_masks), np.asarray(pas.tra_masks)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for epoch in range(2):
+        if epoch > 0:
+            Q = np.asarray(LD.fun_random_neg_masks_tra(pas.item_num, pas.tra_pois_masks))
+            LD.fun_random_neg_masks_tes(pas.item_num, pas.tra_pois_masks, pas.tes_pois_masks)
+        loss, l2, ref = OD.epoch_prme(ref, shuffled_users(pas.user_num, epoch), P, Q, M, pas.tra_all_dist, pas.tra_all_times,
+                                      p['alpha'], p['lambda'], p['threshold'], p['component_weight'])
+        assert hist[epoch]["loss"] < 0                                             # sum of log sigmoid
+        assert_close(hist[epoch]["loss"], loss, 1e-4, "epoch %d loss" % epoch)
+        assert_close(hist[epoch]["l2"], l2, 1e-4, "epoch %d l2" % epoch)
+        sc = OD.user_scores_prme(ref, P, M, pas.tes_pois_masks, pas.tes_masks, pas.cordi, p['component_weight'])
+        rec = _valuate_recall(sc, pas.tes_pois_masks, pas.tes_masks, p['at_nums'])
+        assert np.allclose(hist[epoch]["recall"], rec, atol=1e-12), (hist[epoch]["recall"], rec)
+    for k in ("dp", "ds", "du"):
+        assert_close(getattr(model, k).get_value(), ref[k], 1e-4, k)
+
+
+def test_geoie_driver_matches_oracle_loop(engine, tmp_path):
+    """prog_geoie: per-epoch loss, l2, the scalars a, b and Recall@K against oracle.models.geoie_train in the driver's call
+    order, including the reference quirk that the model's negatives stay those of epoch 0 while the negative DISTANCES are
+    recomputed from freshly drawn negatives (prog_geoie.py:162-167)."""
+    from poi_b200 import prog_geoie as drv
+    from poi_b200.driver_common import shuffled_users
+    from poi_b200.public import Load_Data_GeoIE as LD
+    from oracle import fixtures as Fx
+    path = _dataset(tmp_path)
+    p = drv.default_params(); p.update(dataset="Synth.txt", epochs=2, latent_size=8, at_nums=[5, 10], batch_size_test=6)
+    random.seed(5)
+    pas = drv.Params(p=p, path=path)
+    st = Fx.geoie_state(np.random.RandomState(3), pas.user_num, pas.item_num, 8)
+    st["a"], st["b"] = np.float64(0.3), np.float64(0.2)            # b > 0: no 0 * inf on the padded distances
+    Q0 = np.asarray([list(r) for r in pas.tra_buys_neg_masks])
+    dpos, dneg, dmsk = pas.tra_dist_pos_masks, pas.tra_dist_neg_masks, pas.tra_dist_masks
+    rstate = random.getstate()
+    import os
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        model, best, hist = drv.train_valid_or_test(pas, init=st)
+    finally:
+        os.chdir(cwd)
+    random.setstate(rstate)
+    P, M = np.asarray(pas.tra_buys_masks), np.asarray(pas.tra_masks)
+    ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
+    for epoch in range(2):
+        if epoch > 0:
+            neg = LD.fun_random_neg_masks_tra(pas.item_num, pas.tra_buys_masks)
+            dpos, dneg, dmsk = LD.fun_compute_dist_neg(pas.tra_buys_masks, pas.tra_masks, neg, pas.pois_cordis)
+        loss, l2, ref = OD.epoch_geoie(ref, shuffled_users(pas.user_num, epoch), P, Q0, dpos, dneg, dmsk, p['alpha'], p['lambda'])
+        assert np.isfinite(loss)
+        assert_close(hist[epoch]["loss"], loss, 1e-4, "epoch %d loss" % epoch)
+        assert_close(hist[epoch]["l2"], l2, 1e-4, "epoch %d l2" % epoch)
+        rec = _valuate_recall(OD.user_scores_geoie(ref, P, M), pas.tes_buys_masks, pas.tes_masks, p['at_nums'])
+        assert np.allclose(hist[epoch]["recall"], rec, atol=1e-12), (hist[epoch]["recall"], rec)
+    for k in ("g", "h", "z", "t"):
+        assert_close(getattr(model, k).get_value(), ref[k], 1e-4, k)
+    assert_close([model.a.eval(), model.b.eval()], [ref["a"], ref["b"]], 1e-4, "a, b")
 
 
 def test_checkpoint_roundtrip(engine, tmp_path):

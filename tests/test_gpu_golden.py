@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.util import assert_close
+from tests.util import assert_close, assert_close_global
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -131,12 +131,12 @@ def test_scores_and_auc_preference_reference_golden(engine):
     se = z["se"]
     g = OboGru([tra, tra_m, tra], test, [A, L], n_user, n_item, d, d)
     g.trained_users.set_value(z["users"]); g.trained_items.set_value(z["items"])
-    assert_close(g.compute_sub_all_scores(se), z["gru_scores"], 1e-5, "gru scores")
+    assert_close_global(g.compute_sub_all_scores(se), z["gru_scores"], 1e-5, "gru scores")
     assert np.array_equal(np.asarray(g.compute_sub_auc_preference(se)), z["gru_auc"])
     s = OboSpatialGru([tra, tra_m, tra], test, [[[D, D]] * n_user, [[D] * z["tes"].shape[1]] * n_user, [[D, D]] * n_user],
                       [A, L], n_user, n_item, [D, 0.2], d, d)
     s.trained_users.set_value(z["users"]); s.trained_items.set_value(z["items"]); s.wd.set_value(float(z["wd"])); s.update_prob(z["prob"])
-    assert_close(s.compute_sub_all_scores(se), z["spatial_scores"], 1e-5, "spatial scores")
+    assert_close_global(s.compute_sub_all_scores(se), z["spatial_scores"], 1e-5, "spatial scores")
     assert np.array_equal(np.asarray(s.compute_sub_auc_preference(se)), z["spatial_auc"])
 
 
@@ -154,7 +154,7 @@ def test_prme_geoie_scores_reference_golden(engine):
     test5 = [tes, np.zeros_like(tes), np.zeros(tes.shape), tes_m, tes]
     m = OboPrme(train5, test5, [A, L], 360, float(z["cw"]), z["cordi"], n_user, n_item, d)
     m.trained_ds.set_value(z["ds"]); m.trained_dp.set_value(z["dp"]); m.trained_du.set_value(z["du"])
-    assert_close(m.compute_sub_all_scores(se), z["prme_scores"], 2e-5, "prme scores")
+    assert_close_global(m.compute_sub_all_scores(se), z["prme_scores"], 2e-5, "prme scores")
     gm = GeoIE([tra, tra, tra_m.sum(1), tra_m], [tes, tes], [A, L], n_user, n_item, d, d, np.zeros((n_user, 1)))
     gm.trained_g.set_value(z["g"]); gm.trained_h.set_value(z["h"]); gm.trained_z.set_value(z["z"]); gm.trained_t.set_value(z["t"])
-    assert_close(gm.compute_sub_all_scores(se), z["geo_scores"], 2e-5, "geoie scores")
+    assert_close_global(gm.compute_sub_all_scores(se), z["geo_scores"], 2e-5, "geoie scores")

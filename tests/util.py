@@ -3,11 +3,33 @@ import numpy as np
 
 
 def relerr(a, b):
+    """max|a-b| / max|b|: a whole-array figure -- fine for loss scalars, too loose for tables (use elem_err)."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
 
 
-def assert_close(a, b, rtol, what=""):
+def elem_err(a, b, floor=1e-3):
+    """Element-wise relative error: max_i |a_i - b_i| / max(|b_i|, floor * max|b|).  An entry 1000 times smaller than the
+    largest one is still held to the tolerance relative to ITSELF; only entries below floor * max|b| are measured
+    against that floor (so exact zeros and cancellation residue do not divide by ~0)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        raise AssertionError("shape mismatch %s vs %s" % (a.shape, b.shape))
+    if a.size == 0:
+        return 0.0
+    den = np.maximum(np.abs(b), floor * np.max(np.abs(b)) + 1e-300)
+    return float(np.max(np.abs(a - b) / den))
+
+
+def assert_close(a, b, rtol, what="", floor=1e-3):
+    """|a - b| <= rtol * max(|b|, floor * max|b|) for every element."""
+    e = elem_err(a, b, floor)
+    assert e <= rtol, "%s: element-wise relative error %.3e > %.1e (whole-array figure %.3e)" % (what, e, rtol, relerr(a, b))
+
+
+def assert_close_global(a, b, rtol, what=""):
+    """Whole-array figure max|a-b| <= rtol * max|b| -- for consistency checks between two GPU paths that differ only in
+    accumulation order (not a parity statement)."""
     e = relerr(a, b)
     assert e <= rtol, "%s: relative error %.3e > %.1e" % (what, e, rtol)
 
