@@ -582,6 +582,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch users per GPU per step; strong: --batch users per step split over the GPUs")
     ap.add_argument("--batch", type=int, default=4096, help="users per step per GPU (weak) / per step (strong)")
+    ap.add_argument("--positions", type=int, default=4, help="c3 / c4: consecutive positions of every user in one mini-batch step")
     ap.add_argument("--cpu-batch", type=int, default=512, help="users per CPU-oracle step")
     ap.add_argument("--gemm-mode", type=int, default=1,
                     help="0 fp32 FMA, 1 tcgen05 3xTF32 (fp32-faithful, default), 2 tcgen05 1xTF32")

@@ -269,6 +269,27 @@ int poi_prme_train_seq(poi_engine* e, float* du_dev, float* dp_dev, float* ds_de
                        int64_t n, int32_t threshold, double component_weight,
                        float alpha, float lambda, double* loss_host);
 
+/* K negatives per positive (BASELINE.json C3 "PRME ... neg=20").  The reference draws one negative (PRME.py:172-219);
+ * this is the driver-defined generalisation of SURVEY.md 8(a6): pqidx = [p, q_1..q_K, prev], upq = sum_k log
+ * sigmoid(D(q_k) - D(p)), L2 over every gathered row; q_host is [n x K] row-major.
+ *  poi_prme_train_seq_k   : n sequential ascent steps (parity mode; K = 1 is exactly poi_prme_train_seq), rows written
+ *                           back in pqidx order, last occurrence wins.  loss_host[n] = upq of each step.
+ *  poi_prme_train_batch_k : ONE mini-batch step over n check-ins (throughput mode, EXTENSION semantics): every term from
+ *                           pre-update values, gradients summed over duplicate occurrences, one step per unique row --
+ *                           the reference's own mini-batch rule (Bpr, BPR.py:351-397) applied to PRME.  The six index
+ *                           arrays are device resident (on_host = 0) or host memory copied inside the call (on_host = 1,
+ *                           the end-to-end path); dist is float km, gap int32 minutes.  *loss_sum_host = sum of upq. */
+int poi_prme_train_seq_k(poi_engine* e, float* du_dev, float* dp_dev, float* ds_dev, int32_t d,
+                         const int32_t* u_host, const int32_t* p_host, const int32_t* q_host,
+                         const int32_t* prev_host, const double* dist_host, const int32_t* gap_host,
+                         int64_t n, int32_t K, int32_t threshold, double component_weight,
+                         float alpha, float lambda, double* loss_host);
+int poi_prme_train_batch_k(poi_engine* e, float* du_dev, int64_t n_user, float* dp_dev, float* ds_dev, int64_t n_rows,
+                           int32_t d, const int32_t* u, const int32_t* p, const int32_t* q, const int32_t* prev,
+                           const float* dist, const int32_t* gap, int64_t n, int32_t K, int32_t on_host,
+                           int32_t threshold, double component_weight, float alpha, float lambda,
+                           double* loss_sum_host);
+
 /* ---- GeoIE: GeoIE.seq_train (GeoIE.py:185-194) ------------------------------------------ */
 typedef struct {
     float*  g;  float* h;  float* z;   /* [(n_item+1) x H]  (GeoIE.py:65-72) */

@@ -444,3 +444,41 @@ def l2_value(state, names, lam):
     for k in names:
         tot += float(np.sum(np.asarray(state[k], dtype=np.float64) ** 2))
     return 0.5 * lam * tot
+
+
+# ----------------------------------------------------------------------------------------------
+# K-negative MINI-BATCH steps (BASELINE.json C3 "PRME neg=20", C4 "GeoIE neg=100", throughput mode).
+# EXTENSION SEMANTICS -- the reference trains these models one check-in / one user at a time with one
+# negative.  Defined by applying the reference's own mini-batch recipe (Bpr, BPR.py:351-397: every term of
+# the batch from pre-update values, `T.grad(costs, table)[idx]` = gradient SUMMED over duplicate
+# occurrences, one step per unique row, L2 over every gathered occurrence) to the K-negative statements
+# above.  A batch of one check-in with distinct rows is exactly the sequential step.
+# ----------------------------------------------------------------------------------------------
+def prme_train_batch_k(state, us, ps, Q, prevs, dists, gaps, alpha, lam, thd, cw, dtype=F64):
+    """N check-ins at once: us, ps, prevs, dists, gaps [N]; Q [N, K].  Objective sum_i sum_k log sigmoid(D(q_ik) - D(p_i))
+    - 0.5*lam*(L2 of every gathered row), ascent (PRME.py:195-208).  Returns (sum of upq, new_state)."""
+    us = np.asarray(us, dtype=np.int64); ps = np.asarray(ps, dtype=np.int64); prevs = np.asarray(prevs, dtype=np.int64)
+    Q = np.asarray(Q, dtype=np.int64)
+    N, K = Q.shape
+    idx = np.concatenate((ps[:, None], Q, prevs[:, None]), axis=1)            # [N, K+2] = [p, q_1..q_K, prev]
+    du = _t(state["du"][us], dtype, True)                                     # [N, d]
+    dp = _t(state["dp"][idx], dtype, True)                                    # [N, K+2, d]
+    ds = _t(state["ds"][idx], dtype, True)
+    w = _t((1.0 + np.asarray(dists, dtype=np.float64)) ** 0.25, dtype)
+    far = torch.as_tensor(np.asarray(gaps).astype(np.int32) > int(thd))
+    cp = torch.where(far, torch.ones_like(w), w * cw)
+    cs = torch.where(far, torch.zeros_like(w), w * (1 - cw))
+    Dp = ((du[:, None, :] - dp[:, :K + 1, :]) ** 2).sum(2)                    # [N, K+1]
+    Ds = ((ds[:, :K + 1, :] - ds[:, K + 1:, :]) ** 2).sum(2)
+    D = cp[:, None] * Dp + cs[:, None] * Ds
+    upq = _logsig(D[:, 1:] - D[:, :1]).sum()
+    cost = upq - 0.5 * lam * ((du ** 2).sum() + (dp ** 2).sum() + (ds ** 2).sum())
+    cost.backward()
+    g_ds = ds.grad if ds.grad is not None else torch.zeros_like(ds)
+    d_ = dp.shape[2]
+    new = dict(state)
+    # ascent: row + alpha * sum_occ grad  ==  _unique_rows_update with -grad
+    new["du"], _ = _unique_rows_update(state["du"], us, -du.grad, alpha)
+    new["dp"], _ = _unique_rows_update(state["dp"], idx.reshape(-1), -dp.grad.reshape(-1, d_), alpha)
+    new["ds"], _ = _unique_rows_update(state["ds"], idx.reshape(-1), -g_ds.reshape(-1, d_), alpha)
+    return float(upq.detach()), new

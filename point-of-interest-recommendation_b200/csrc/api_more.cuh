@@ -459,3 +459,98 @@ extern "C" int poi_debug_fused_trace(int dir, long long* out, int n, int clear) 
     return (int)cudaMemcpyFromSymbol(out, fused::g_trace, (size_t)n * sizeof(long long), (size_t)dir * 512 * 16 * sizeof(long long));
 }
 #endif
+
+// ---- K-negative PRME (prme_k.cuh) ------------------------------------------------------------------
+extern "C" int poi_prme_train_seq_k(poi_engine* e, float* du, float* dp, float* ds_, int32_t d, const int32_t* u,
+                                    const int32_t* p, const int32_t* q, const int32_t* prev, const double* dist,
+                                    const int32_t* gap, int64_t n, int32_t K, int32_t threshold, double cw, float alpha,
+                                    float lambda, double* loss_host) {
+    POI_TRY(begin_call(e));
+    if (d <= 0 || d % 4) POI_FAIL(e, "d must be a positive multiple of 4");
+    if (K < 1 || K > PRME_MAXK) POI_FAIL(e, "K must be in [1, %d]", PRME_MAXK);
+    if (n <= 0) return 0;
+    const size_t smem = prme_seq_k_smem(d, K);
+    if (smem > 227 * 1024) POI_FAIL(e, "K * d too large for the sequential kernel (%zu bytes of shared memory)", smem);
+    const void* hs[6] = {u, p, q, prev, dist, gap};
+    size_t bs[6] = {(size_t)n * 4, (size_t)n * 4, (size_t)n * K * 4, (size_t)n * 4, (size_t)n * 8, (size_t)n * 4};
+    void* dv[6];
+    POI_TRY(upload_many(e, hs, bs, 6, dv));
+    double* loss_dev = nullptr;
+    POI_TRY(arena_get(e, (size_t)n, &loss_dev));
+    POI_CK(e, cudaFuncSetAttribute(k_prme_seq_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POI_CAT(e, CAT_MF, 0, (double)n * (2 * (K + 2) + 1) * d * 4 * 2);
+    POI_LAUNCH(e, k_prme_seq_k, 1, 256, smem, du, dp, ds_, (int)d, (int)K, (const int32_t*)dv[0], (const int32_t*)dv[1],
+               (const int32_t*)dv[2], (const int32_t*)dv[3], (const double*)dv[4], (const int32_t*)dv[5], n, (int)threshold,
+               (float)cw, alpha, lambda, loss_dev);
+    POI_CK(e, cudaMemcpyAsync(loss_host, loss_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    return 0;
+}
+
+extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, float* dp, float* ds_, int64_t n_rows, int32_t d,
+                                      const int32_t* u, const int32_t* p, const int32_t* q, const int32_t* prev,
+                                      const float* dist, const int32_t* gap, int64_t n, int32_t K, int32_t on_host,
+                                      int32_t threshold, double cw, float alpha, float lambda, double* loss_sum_host) {
+    POI_TRY(begin_call(e));
+    if (d <= 0 || d % 4 || d > 1024) POI_FAIL(e, "d must be a multiple of 4, <= 1024");
+    if (K < 1 || K > PRME_MAXK) POI_FAIL(e, "K must be in [1, %d]", PRME_MAXK);
+    if (n <= 0) { if (loss_sum_host) *loss_sum_host = 0.0; return 0; }
+    if (n * (K + 2) >= (int64_t)1 << 31) POI_FAIL(e, "batch too large");
+    PrmeBatchIdx b;
+    b.N = (int)n; b.K = K;
+    if (on_host) {       // end-to-end path: the step's index arrays come from host memory inside the call
+        const void* hs[6] = {u, p, q, prev, dist, gap};
+        size_t bs[6] = {(size_t)n * 4, (size_t)n * 4, (size_t)n * K * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4};
+        void* dv[6];
+        POI_TRY(upload_many(e, hs, bs, 6, dv));
+        b.u = (const int32_t*)dv[0]; b.p = (const int32_t*)dv[1]; b.q = (const int32_t*)dv[2]; b.prev = (const int32_t*)dv[3];
+        b.dist = (const float*)dv[4]; b.gap = (const int32_t*)dv[5];
+    } else { b.u = u; b.p = p; b.q = q; b.prev = prev; b.dist = dist; b.gap = gap; }
+    const int R = K + 2, d4 = d / 4;
+    const int64_t n_occ = n * R;
+    uint32_t* keys = nullptr;
+    POI_TRY(arena_get(e, (size_t)n_occ, &keys));
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    POI_LAUNCH(e, k_prme_keys, (unsigned)poi_cdiv(n_occ, 256), 256, 0, b, keys);
+    SegList seg, seg_u;
+    POI_TRY(build_segments(e, keys, n_occ, (uint32_t)n_rows, false, &seg));
+    POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(b.u), n, (uint32_t)n_user, false, &seg_u));
+    float *KP = nullptr, *KS = nullptr, *SL = nullptr, *GU = nullptr, *GL = nullptr; double *part = nullptr, *out_dev = nullptr;
+    POI_TRY(arena_get(e, (size_t)n_occ, &KP));
+    POI_TRY(arena_get(e, (size_t)n_occ, &KS));
+    POI_TRY(arena_get(e, (size_t)n * d, &SL));
+    POI_TRY(arena_get(e, (size_t)n * d, &GU));
+    POI_TRY(arena_get(e, (size_t)n * d, &GL));
+    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * 8);
+    POI_TRY(arena_get(e, (size_t)blocks, &part));
+    POI_TRY(arena_get(e, 1, &out_dev));
+    const size_t smem = (size_t)8 * 2 * d4 * sizeof(float4);
+    // algorithmic bytes: every gathered row read once and written once + the index words; booked on the
+    // two kernels in proportion to what each moves (phase A: the reads, phase B: the read-modify-write of the unique rows)
+    const double algo = (double)n * ((2.0 * (2 * R + 1)) * d * 4 + 4.0 * (K + 5));
+    POI_CAT(e, CAT_MF, 0, 0.5 * algo);
+    int64_t awarps = std::min<int64_t>(n_occ, (int64_t)e->num_sms * 64);
+    unsigned agrid = (unsigned)std::max<int64_t>(poi_cdiv(awarps * 32, 256), 1);
+#define PRME_BK(NCH)                                                                                                        \
+    do {                                                                                                                    \
+        POI_CK(e, cudaFuncSetAttribute(k_prme_score<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        POI_LAUNCH(e, (k_prme_score<NCH>), blocks, 256, smem, du, dp, ds_, d4, b, (int)threshold, (float)cw, KP, KS, SL,    \
+                   GU, GL, part);                                                                                           \
+        POI_CAT(e, CAT_MF, 0, 0.5 * algo);                                                                                  \
+        POI_LAUNCH(e, (k_prme_apply<NCH>), agrid, 256, 0, seg, du, dp, ds_, d4, b, KP, KS, SL, GL, alpha, lambda);          \
+    } while (0)
+    if (d4 <= 32) PRME_BK(1); else if (d4 <= 64) PRME_BK(2); else if (d4 <= 128) PRME_BK(4); else PRME_BK(8);
+#undef PRME_BK
+    POI_CAT(e, CAT_REDUCE, 0, 0);
+    POI_LAUNCH(e, k_sum_partials_d, 1, 32, 0, part, blocks, out_dev, 1, 1);
+    // du[u]: one step per unique user, the check-ins of a user summed in fixed order (rows.cuh)
+    RowSrc src; memset(&src, 0, sizeof(src));
+    src.mode = SRC_DENSE_GRADS; src.dim = d; src.grads = GU;
+    POI_TRY(launch_rows_update(e, seg_u, du, d, alpha, lambda, src, ROW_LONG_THRESH));
+    POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    if (loss_sum_host) *loss_sum_host = e->h_out[0];
+    return 0;
+}

@@ -1020,7 +1020,7 @@ static int launch_bwd_cl(poi_engine* e, const float* DHl, const float* Z, const 
                          const uint8_t* wimg, float* DA, int B, int T, int H) {
     const size_t smem = fused_smem(H, CL, SPLIT3);
     POI_CK(e, cudaFuncSetAttribute(k_gru_bwd_fused<SPLIT3, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    POI_CAT(e, CAT_RECUR_FWD, 2.0 * (double)B * T * 3 * H * H, 0);
+    POI_CAT(e, CAT_RECUR_BWD, 2.0 * (double)B * T * 3 * H * H, 0);
     const unsigned grid = (unsigned)poi_cdiv(B, FM) * CL;
     if (CL == 1) { POI_LAUNCH(e, (k_gru_bwd_fused<SPLIT3, 1>), grid, F_THREADS, smem, DHl, Z, R, C, Hs, wimg, DA, B, T, H); return 0; }
     return launch_clustered(e, "k_gru_bwd_fused", k_gru_bwd_fused<SPLIT3, CL>, grid, F_THREADS, smem, CL, DHl, Z, R, C, Hs, wimg, DA, B, T, H);
@@ -1063,7 +1063,7 @@ static int launch_fwd_cl(poi_engine* e, const float* AX, const uint8_t* wimg, fl
                          int B, int T, int H) {
     const size_t smem = fused_smem(H, CL, SPLIT3);
     POI_CK(e, cudaFuncSetAttribute(k_gru_fwd_fused<SPLIT3, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    POI_CAT(e, CAT_RECUR_BWD, 2.0 * (double)B * T * 3 * H * H, 0);
+    POI_CAT(e, CAT_RECUR_FWD, 2.0 * (double)B * T * 3 * H * H, 0);
     const unsigned grid = (unsigned)poi_cdiv(B, FM) * CL;
     if (CL == 1) { POI_LAUNCH(e, (k_gru_fwd_fused<SPLIT3, 1>), grid, F_THREADS, smem, AX, wimg, Hs, Z, R, C, B, T, H); return 0; }
     return launch_clustered(e, "k_gru_fwd_fused", k_gru_fwd_fused<SPLIT3, CL>, grid, F_THREADS, smem, CL, AX, wimg, Hs, Z, R, C, B, T, H);

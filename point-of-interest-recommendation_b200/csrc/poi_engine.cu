@@ -9,6 +9,7 @@
 #include "gru.cuh"
 #include "mf.cuh"
 #include "geoie.cuh"
+#include "prme_k.cuh"
 #include "peer.cuh"
 #include "sampling.cuh"
 #include "eval.cuh"
@@ -352,6 +353,13 @@ static int upload_many(poi_engine* e, const void* const* hosts, const size_t* by
     size_t so = 0;
     for (int i = 0; i < k; ++i) {
         POI_TRY(arena_alloc(e, bytes[i], &devs[i]));
+        // page-locked caller memory goes to the device directly (every caller synchronises before it returns)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, hosts[i]) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+            POI_CK(e, cudaMemcpyAsync(devs[i], hosts[i], bytes[i], cudaMemcpyHostToDevice, e->stream));
+            continue;
+        }
+        cudaGetLastError();
         memcpy(e->h_stage + so, hosts[i], bytes[i]);
         POI_CK(e, cudaMemcpyAsync(devs[i], e->h_stage + so, bytes[i], cudaMemcpyHostToDevice, e->stream));
         so += poi_align_up(bytes[i], 256);

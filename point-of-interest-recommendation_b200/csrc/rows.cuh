@@ -128,6 +128,9 @@ struct RowSrc {
     // emit mode (multi-GPU sender side): instead of updating the table, write the duplicate-summed
     // gradient of segment sg to emit_rows[(emit_by_key ? key : sg) * dim] and its count to emit_cnt[.]
     float* emit_rows; float* emit_cnt; int emit_by_key;
+    // segments of ONE occurrence are left alone (their row was already updated in place by the kernel that produced the
+    // gradients: prme_k.cuh / geoie_k.cuh); only rows that occur several times in the batch are summed here
+    int skip_single;
 };
 
 __device__ __forceinline__ void row_finish(const RowSrc& src, float* table, int dim4, uint32_t key, uint32_t sg,
@@ -183,6 +186,7 @@ k_rows_update_warp(SegList seg, float* __restrict__ table, int dim4, float alpha
     for (int64_t sg = warp; sg < nu; sg += nwarps) {
         const uint32_t s0 = seg.seg_start[sg], s1 = seg.seg_start[sg + 1];
         const uint32_t cnt = s1 - s0;
+        if (src.skip_single && cnt == 1u) continue;
         if ((int)cnt > long_thresh) {
             if (lane == 0) { uint32_t pos = atomicAdd(long_count, 1u); long_list[pos] = (uint32_t)sg; }
             continue;

@@ -404,6 +404,40 @@ class Engine:
                                         loss.ctypes.data))
         return loss
 
+    def prme_train_seq_k(self, du, dp, ds, u, p, Q, prev, dist, gap, thd, cw, alpha, lam) -> np.ndarray:
+        """n sequential K-negative steps (parity mode); Q is [n, K]."""
+        u = _host_i32(u, "u").reshape(-1); p = _host_i32(p, "p").reshape(-1)
+        Q = _host_i32(Q, "Q").reshape(u.size, -1)
+        prev = _host_i32(prev, "prev").reshape(-1); gap = _host_i32(gap, "gap").reshape(-1)
+        dist = np.ascontiguousarray(dist, dtype=np.float64).reshape(-1)
+        loss = np.empty(u.size, dtype=np.float64)
+        self._ck(lib.poi_prme_train_seq_k(self._h, _dev_f32(du, "du"), _dev_f32(dp, "dp"), _dev_f32(ds, "ds"),
+                                          dp.shape[1], u.ctypes.data, p.ctypes.data, Q.ctypes.data, prev.ctypes.data,
+                                          dist.ctypes.data, gap.ctypes.data, u.size, Q.shape[1], int(thd), float(cw), alpha, lam,
+                                          loss.ctypes.data))
+        return loss
+
+    def prme_train_batch_k(self, du, dp, ds, u, p, Q, prev, dist, gap, thd, cw, alpha, lam) -> float:
+        """One K-negative mini-batch step (throughput mode).  The six index arrays are either all int32 / float32 CUDA
+        tensors (device resident) or all host arrays / pinned CPU tensors (copied inside the call: the e2e path)."""
+        on_dev = isinstance(u, torch.Tensor) and u.is_cuda
+        if on_dev:
+            n, K = int(u.numel()), int(Q.numel() // max(u.numel(), 1))
+            ptr = [_dev_i32(u, "u"), _dev_i32(p, "p"), _dev_i32(Q, "Q"), _dev_i32(prev, "prev"), _dev_f32(dist, "dist"),
+                   _dev_i32(gap, "gap")]
+            keep = None
+        else:
+            f = lambda x, dt: np.ascontiguousarray(x.numpy() if isinstance(x, torch.Tensor) else x, dtype=dt)
+            keep = [f(u, np.int32).reshape(-1), f(p, np.int32).reshape(-1), f(Q, np.int32), f(prev, np.int32).reshape(-1),
+                    f(dist, np.float32).reshape(-1), f(gap, np.int32).reshape(-1)]
+            n = keep[0].size; K = keep[2].size // max(n, 1)
+            ptr = [a.ctypes.data for a in keep]
+        out = c_double()
+        self._ck(lib.poi_prme_train_batch_k(self._h, _dev_f32(du, "du"), du.shape[0], _dev_f32(dp, "dp"), _dev_f32(ds, "ds"),
+                                            dp.shape[0], dp.shape[1], ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], ptr[5], n, K,
+                                            0 if on_dev else 1, int(thd), float(cw), alpha, lam, byref(out)))
+        return float(out.value)
+
     # ---- GeoIE ------------------------------------------------------------------------------
     def geoie_train(self, g, h, z, t, ab, uidx, p_row, q_row, dist_pos, dist_neg, msk, alpha, lam) -> float:
         prm = PoiGeoieParams()

@@ -107,4 +107,27 @@ class OboPrme(PrmeBasic):
                                           dists, gaps, self.thd, self.cw, self._alpha, self._lambda)
 
 
+    def train_k(self, u_idx, p_idx, q_idxs, prev_idx, ad_idx, t_idx):
+        """One check-in with K negatives `q_idxs` (BASELINE C3 "neg=20"): K = 1 is `train`."""
+        return float(self.engine.prme_train_seq_k(self.du.t, self.dp.t, self.ds.t, [u_idx], [p_idx], [list(q_idxs)], [prev_idx],
+                                                  [ad_idx], [t_idx], self.thd, self.cw, self._alpha, self._lambda)[0])
+
+    def train_sequence_k(self, u_idxs, p_idxs, Q_idxs, prev_idxs, dists, gaps):
+        """n back-to-back `train_k` calls in one launch (sequential SGD, last writer wins); Q_idxs is [n, K]."""
+        return self.engine.prme_train_seq_k(self.du.t, self.dp.t, self.ds.t, u_idxs, p_idxs, Q_idxs, prev_idxs, dists, gaps,
+                                            self.thd, self.cw, self._alpha, self._lambda)
+
+
+class Prme(OboPrme):
+    """Mini-batch PRME with K negatives per positive -- the throughput mode.  EXTENSION SEMANTICS (the reference trains PRME
+    one check-in at a time): `train(u, p, Q, prev, dist, gap)` takes N check-ins at once, evaluates every term from
+    pre-update values and applies the gradient summed over duplicate occurrences, one step per unique row -- the rule of the
+    reference's own mini-batch class (Bpr, BPR.py:351-397).  Returns the summed objective.  Index arrays may be CUDA
+    tensors (resident) or host arrays (copied inside the call)."""
+
+    def train(self, u_idxs, p_idxs, Q_idxs, prev_idxs, dists, gaps):
+        return self.engine.prme_train_batch_k(self.du.t, self.dp.t, self.ds.t, u_idxs, p_idxs, Q_idxs, prev_idxs, dists, gaps,
+                                              self.thd, self.cw, self._alpha, self._lambda)
+
+
 OboPRPRM = OboPrme

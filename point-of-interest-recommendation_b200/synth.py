@@ -14,6 +14,9 @@ CONFIGS = {
     # name: n_user, n_item, seq, d, UD(km), dd(m)
     "c1": dict(n_user=2321, n_item=5528, seq=64, d=32, UD=40, dd=200, model="gru"),
     "c2": dict(n_user=10000, n_item=40000, seq=32, d=128, UD=40, dd=200, model="distance2pre"),
+    # c3 / c4: BASELINE.json gives |POI|, d and the negatives per positive; |U| and seq are SURVEY.md 8d's assumptions
+    "c3": dict(n_user=10000, n_item=100000, seq=32, d=256, neg=20, UD=40, dd=200, model="prme"),
+    "c4": dict(n_user=100000, n_item=1000000, seq=32, d=256, neg=100, UD=40, dd=200, model="geoie"),
     "c5": dict(n_user=1000000, n_item=10000000, seq=256, d=512, UD=40, dd=200, model="distance2pre"),
 }
 
@@ -97,6 +100,50 @@ def make_dataset(n_user, n_item, seq, UD=40, dd=200, ragged=False, zipf=None, se
     tes = rs.randint(0, n_item, size=(n_user, 1)).astype(np.int32)
     return dict(P=P, Q=Q, M=M, DP=DP, DQ=DQ, lens=lens, coords=coords, tes=tes, dist_num=dist_num,
                 n_user=n_user, n_item=n_item, seq=seq, dd=dd, UD=UD)
+
+
+def prme_km(lat1, lon1, lat2, lon2):
+    """Vectorised `cal_dis` of the PRME loader (Load_Data_prme.py:27-36): equatorial radius, 2 asin form."""
+    rad = np.pi / 180.0
+    a = (lat1 - lat2) * rad
+    b = (lon1 - lon2) * rad
+    s = 2 * np.arcsin(np.sqrt(np.sin(a / 2) ** 2 + np.cos(lat1 * rad) * np.cos(lat2 * rad) * np.sin(b / 2) ** 2))
+    return s * 6378.137
+
+
+def make_mf_dataset(n_user, n_item, seq, K, seed=123):
+    """Check-in sequences for the pairwise models with K negatives per positive (C3 PRME, C4 GeoIE): P [U x seq] uniform
+    POIs, Q [U x seq x K] uniform negatives outside the user's own sequence (Load_Data_prme.py:120-140 draws one; here K
+    per position), coords [n_item+1 x 2] (pad row 0,0 like Load_Data_prme.py:108-112), PRME's per-position inputs: `dist`
+    = km between consecutive POIs (Load_Data_prme.py:60-75) and `gap` = integer minutes U{1..720} (threshold 360)."""
+    rs = np.random.RandomState(seed)
+    P = rs.randint(0, n_item, size=(n_user, seq)).astype(np.int32)
+    Q = rs.randint(0, n_item, size=(n_user, seq, K)).astype(np.int32)
+    own = np.sort(P, axis=1)
+    for _ in range(8):                                                   # rejection of the user's own POIs
+        pos = _rowwise_searchsorted(own, Q.reshape(n_user, -1)).reshape(Q.shape)
+        hit = np.take_along_axis(own, pos.reshape(n_user, -1), axis=1).reshape(Q.shape) == Q
+        n = int(hit.sum())
+        if n == 0:
+            break
+        Q[hit] = rs.randint(0, n_item, size=n)
+    coords = np.zeros((n_item + 1, 2), dtype=np.float64)
+    coords[:n_item, 0] = rs.uniform(1.22, 1.47, n_item); coords[:n_item, 1] = rs.uniform(103.60, 104.04, n_item)
+    a, b = coords[P[:, 1:]], coords[P[:, :-1]]
+    dist = np.zeros((n_user, seq), dtype=np.float32)
+    dist[:, 1:] = prme_km(a[..., 0], a[..., 1], b[..., 0], b[..., 1])
+    gap = rs.randint(1, 721, size=(n_user, seq)).astype(np.int32)
+    return dict(P=P, Q=Q, coords=coords, dist=dist, gap=gap, n_user=n_user, n_item=n_item, seq=seq, K=K)
+
+
+def init_mf_state(model, n_user, n_item, d, seed=123):
+    """U(-0.5, 0.5) fp32 tables (PRME.py:76-83, GeoIE.py:65-72); GeoIE's a, b drawn positive so that a d^b is finite."""
+    rs = np.random.RandomState(seed + 1)
+    u = lambda *shape: rs.uniform(-0.5, 0.5, shape).astype(np.float32)
+    if model == "prme":
+        return dict(ds=u(n_item + 1, d), dp=u(n_item + 1, d), du=u(n_user, d))
+    return dict(g=u(n_item + 1, d), h=u(n_item + 1, d), t=u(n_user, d), z=u(n_item + 1, d),
+                a=np.float64(rs.uniform(0.05, 0.5)), b=np.float64(rs.uniform(0.05, 0.5)))
 
 
 def init_state(n_item, d, H, dist_num=None, seed=123, n_user=None):

@@ -33,8 +33,13 @@ def test_distance2pre_d512_long_sequences(engine):
     (rl, rsur, rupq, rw), ref = E.gru_family_train_batch(ref, P, Q, M, A, L, DP, DQ)
     assert_close(out[:3], [rl, rsur, rupq], 1e-4, "losses")
     got = state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
-    for k in got:
-        assert_close(got[k], ref[k], 1e-4, k)
+    for k in ("lt", "di", "bi", "bs"):
+        assert_close(got[k], ref[k], 1e-4, k, floor=1.0 if k in ("bi", "bs") else 1e-3)
+    # weights scaled down to 0.09: an entry at the 1e-3 floor (9e-5) moves by alpha * G with |G| ~ 1..10 accumulated over
+    # 4 560 rows -- fp32 rounding of G alone (6e-8 |G|) is 1e-4 of such an entry (measured 1.1e-4), so the small entries
+    # of the weights are measured against 1e-2 of the largest one
+    for k in ("ui", "wh", "vs"):
+        assert_close(got[k], ref[k], 1e-4, k, floor=1e-2)
 
 
 def test_prme_c3_shape(engine):

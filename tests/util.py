@@ -34,6 +34,15 @@ def assert_close_global(a, b, rtol, what=""):
     assert e <= rtol, "%s: relative error %.3e > %.1e" % (what, e, rtol)
 
 
+def assert_state_close(got, ref, rtol, names=None, zero_init=("bi", "bs"), what=""):
+    """Parameter arrays after a step, element-wise (assert_close).  `zero_init` names the arrays the reference initialises
+    to ZERO (bi GRU.py:64, bs GRU_Spatial.py:61): after a step such an entry IS -alpha x (a sum over every (t, b) row, with
+    cancellation), so its error scales with the summed terms -- the largest entries -- not with the entry itself; those
+    arrays are measured against max|b| (floor = 1).  Pass zero_init=() when the test starts from non-zero biases."""
+    for k in (names or got.keys()):
+        assert_close(got[k], ref[k], rtol, (what + " " + k).strip(), floor=1.0 if k in zero_init else 1e-3)
+
+
 def state_from_model(model, names):
     out = {}
     for k in names:
