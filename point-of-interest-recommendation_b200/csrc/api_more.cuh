@@ -522,28 +522,36 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
     POI_TRY(arena_get(e, (size_t)n * d, &SL));
     POI_TRY(arena_get(e, (size_t)n * d, &GU));
     POI_TRY(arena_get(e, (size_t)n * d, &GL));
-    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * 8);
+    size_t tma_smem = 0;
+    const bool use_tma = prme_score_tma_ok(d4, K, &tma_smem) && !getenv("POI_PRME_NO_TMA");
+    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * (use_tma ? 2 : 8));
     POI_TRY(arena_get(e, (size_t)blocks, &part));
     POI_TRY(arena_get(e, 1, &out_dev));
     const size_t smem = (size_t)8 * 2 * d4 * sizeof(float4);
-    // algorithmic bytes: every gathered row read once and written once + the index words; booked on the
-    // two kernels in proportion to what each moves (phase A: the reads, phase B: the read-modify-write of the unique rows)
+    // algorithmic bytes: every gathered row read once and written once + the index words.  Phase A is
+    // booked with the reads (category "mf"), phase B with the write-back (category "rows").
     const double algo = (double)n * ((2.0 * (2 * R + 1)) * d * 4 + 4.0 * (K + 5));
-    POI_CAT(e, CAT_MF, 0, 0.5 * algo);
     int64_t awarps = std::min<int64_t>(n_occ, (int64_t)e->num_sms * 64);
     unsigned agrid = (unsigned)std::max<int64_t>(poi_cdiv(awarps * 32, 256), 1);
+    POI_CAT(e, CAT_MF, 0, 0.5 * algo);
+    if (use_tma) {
+        POI_CK(e, cudaFuncSetAttribute(k_prme_score_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+        POI_LAUNCH(e, k_prme_score_tma, blocks, 256, tma_smem, du, dp, ds_, d4, b, (int)threshold, (float)cw, KP, KS, SL, GU, GL, part);
+    }
 #define PRME_BK(NCH)                                                                                                        \
     do {                                                                                                                    \
-        POI_CK(e, cudaFuncSetAttribute(k_prme_score<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        POI_LAUNCH(e, (k_prme_score<NCH>), blocks, 256, smem, du, dp, ds_, d4, b, (int)threshold, (float)cw, KP, KS, SL,    \
-                   GU, GL, part);                                                                                           \
-        POI_CAT(e, CAT_MF, 0, 0.5 * algo);                                                                                  \
+        if (!use_tma) {                                                                                                     \
+            POI_CK(e, cudaFuncSetAttribute(k_prme_score<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+            POI_LAUNCH(e, (k_prme_score<NCH>), blocks, 256, smem, du, dp, ds_, d4, b, (int)threshold, (float)cw, KP, KS,    \
+                       SL, GU, GL, part);                                                                                   \
+        }                                                                                                                   \
+        POI_CAT(e, CAT_ROWS, 0, 0.5 * algo);                                                                                \
         POI_LAUNCH(e, (k_prme_apply<NCH>), agrid, 256, 0, seg, du, dp, ds_, d4, b, KP, KS, SL, GL, alpha, lambda);          \
     } while (0)
     if (d4 <= 32) PRME_BK(1); else if (d4 <= 64) PRME_BK(2); else if (d4 <= 128) PRME_BK(4); else PRME_BK(8);
 #undef PRME_BK
     POI_CAT(e, CAT_REDUCE, 0, 0);
-    POI_LAUNCH(e, k_sum_partials_d, 1, 32, 0, part, blocks, out_dev, 1, 1);
+    POI_LAUNCH(e, k_sum_partials_warp, 1, 32, 0, part, blocks, out_dev);
     // du[u]: one step per unique user, the check-ins of a user summed in fixed order (rows.cuh)
     RowSrc src; memset(&src, 0, sizeof(src));
     src.mode = SRC_DENSE_GRADS; src.dim = d; src.grads = GU;

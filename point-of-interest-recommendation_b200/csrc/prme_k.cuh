@@ -286,3 +286,120 @@ k_prme_apply(SegList seg, const float* __restrict__ du, float* __restrict__ dp, 
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Phase A with the rows staged by TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): the
+// 2K + 4 rows of a check-in (du[u], ds[prev], dp[x_j], ds[x_j], j = 0..K) are one 1 KB-per-row burst into a shared-memory
+// stage; two stages per CTA, so the rows of check-in i+1 stream in while check-in i is scored out of shared memory --
+// no register holds an in-flight row, and every row is read from L2 / HBM exactly once (the register version re-reads
+// the rows in its second pass).  Persistent CTAs, two per SM.  Used when 256 % (d/4) == 0 and two stages fit.
+// Stage layout (rows of d floats): 0 du[u] | 1 ds[prev] | 2 .. K+2 dp[x_j] | K+3 .. 2K+3 ds[x_j].
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, const float* __restrict__ ds, int d4, PrmeBatchIdx b,
+                 int thd, float cw, float* __restrict__ KP, float* __restrict__ KS, float* __restrict__ SL,
+                 float* __restrict__ GU, float* __restrict__ GL, double* __restrict__ part) {
+    extern __shared__ __align__(128) unsigned char prme_tma_smem[];
+    __shared__ uint64_t bar[2];
+    __shared__ float sD[PRME_MAXK + 1], sg[PRME_MAXK + 1], sl_[PRME_MAXK + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = b.K, R = K + 2, NR = 2 * K + 4, d = d4 * 4;
+    const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = row_bytes * (uint32_t)NR;
+    float4* red = reinterpret_cast<float4*>(prme_tma_smem + 2 * (size_t)stage_bytes);     // [ngrp][2][d4]
+    const int ngrp = 256 / d4;
+    if (tid == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::fence_barrier_init(); }
+    __syncthreads();
+    // warp 0 issues the bulk copies of check-in i into stage s: lane 0 arms the barrier with the stage's byte count, then
+    // every lane sends the rows r = lane, lane + 32, ... (one instruction per row)
+    auto issue = [&](int i, int s) {
+        if (warp != 0) return;
+        tc::fence_async_smem();                        // generic-proxy reads of this stage (two iterations ago) before async writes
+        const uint32_t barp = tc::smem_u32(&bar[s]);
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barp), "r"(stage_bytes) : "memory");
+        __syncwarp();
+        const uint32_t base = tc::smem_u32(prme_tma_smem) + (uint32_t)s * stage_bytes;
+        for (int r = lane; r < NR; r += 32) {
+            const float* src;
+            if (r == 0) src = du + (size_t)b.u[i] * d;
+            else if (r == 1) src = ds + (size_t)b.prev[i] * d;
+            else {
+                const int j = r - 2 <= K ? r - 2 : r - 3 - K;
+                const size_t x = (size_t)(j == 0 ? b.p[i] : b.q[(size_t)i * K + j - 1]);
+                src = (r - 2 <= K ? dp : ds) + x * d;
+            }
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(base + (uint32_t)r * row_bytes), "l"(src), "r"(row_bytes), "r"(barp) : "memory");
+        }
+    };
+    double loss_acc = 0.0;
+    int it = 0;
+    if ((int)blockIdx.x < b.N) issue(blockIdx.x, 0);
+    for (int i = blockIdx.x; i < b.N; i += gridDim.x, ++it) {
+        const int s = it & 1;
+        if (i + (int)gridDim.x < b.N) issue(i + gridDim.x, s ^ 1);
+        const bool far = b.gap[i] > thd;
+        const float w = sqrtf(sqrtf(1.0f + b.dist[i]));
+        const float cp = far ? 1.f : w * cw, cs = far ? 0.f : w * (1.f - cw);
+        tc::mbar_wait(&bar[s], (uint32_t)(it >> 1) & 1u);
+        const float4* st = reinterpret_cast<const float4*>(prme_tma_smem + (size_t)s * stage_bytes);
+        const float4* U = st; const float4* SLr = st + d4;
+        const float4* DP = st + 2 * (size_t)d4; const float4* DS = st + (size_t)(K + 3) * d4;
+        // ---- pass 1: D(x_j), one warp per candidate ----
+        for (int j = warp; j <= K; j += 8) {
+            float acc = 0.f;
+            for (int c = lane; c < d4; c += 32) {
+                const float4 a = f4sub(U[c], DP[(size_t)j * d4 + c]);
+                const float4 q = f4sub(DS[(size_t)j * d4 + c], SLr[c]);
+                acc += cp * (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) + cs * (q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) sD[j] = acc;
+        }
+        __syncthreads();
+        if (tid >= 1 && tid <= K) { const float x = sD[tid] - sD[0]; sg[tid] = sigmoidf_(-x); sl_[tid] = logsigmoidf_(x); }
+        __syncthreads();
+        float G = 0.f;
+        for (int k = 1; k <= K; ++k) G += sg[k];
+        if (tid == 0) { double ls = 0.0; for (int k = 1; k <= K; ++k) ls += (double)sl_[k]; loss_acc += ls; }
+        if (tid <= K + 1) {
+            const float cj = tid == 0 ? -G : (tid <= K ? sg[tid] : 0.f);
+            KP[(size_t)i * R + tid] = cj * 2.f * cp; KS[(size_t)i * R + tid] = cj * 2.f * cs;
+        }
+        // ---- pass 2: thread = (float4 column c, candidate group g): d/d du and d/d ds[prev] partial sums ----
+        {
+            const int c = tid % d4, g = tid / d4;
+            float4 au = f4zero(), as = f4zero();
+            const float4 u = U[c], sl = SLr[c];
+            for (int j = g; j <= K; j += ngrp) {
+                const float cj = j == 0 ? -G : sg[j];
+                au = f4fma(cj * 2.f * cp, f4sub(u, DP[(size_t)j * d4 + c]), au);
+                as = f4fma(cj * 2.f * cs, f4sub(sl, DS[(size_t)j * d4 + c]), as);
+            }
+            red[(g * 2 + 0) * d4 + c] = au; red[(g * 2 + 1) * d4 + c] = as;
+        }
+        __syncthreads();
+        if (tid < 2 * d4) {
+            const int c = tid % d4, which = tid / d4;
+            float4 t = red[which * d4 + c];
+            for (int g = 1; g < ngrp; ++g) t = f4add(t, red[(g * 2 + which) * d4 + c]);      // group order: fixed
+            if (which == 0) st4(GU + ((size_t)i * d4 + c) * 4, make_float4(-t.x, -t.y, -t.z, -t.w));
+            else { st4(GL + ((size_t)i * d4 + c) * 4, t); st4(SL + ((size_t)i * d4 + c) * 4, SLr[c]); }
+        }
+        __syncthreads();          // stage s, red, sD, sg are free again
+    }
+    if (tid == 0) part[blockIdx.x] = loss_acc;
+}
+
+static bool prme_score_tma_ok(int d4, int K, size_t* smem) {
+    const size_t stage = (size_t)(2 * K + 4) * d4 * 16;
+    *smem = 2 * stage + (size_t)2 * 256 * 16 + 128;
+    return d4 >= 1 && d4 <= 256 && 256 % d4 == 0 && 2 * d4 <= 256 && *smem <= 110 * 1024;
+}
+
+// fixed-order sum of n doubles by one warp: lane l adds part[l], part[l + 32], ... in order, then a fixed shuffle tree
+__global__ void k_sum_partials_warp(const double* __restrict__ part, int n, double* __restrict__ out) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) t += part[i];
+    t = warp_sum_d(t);
+    if (threadIdx.x == 0) *out = t;
+}

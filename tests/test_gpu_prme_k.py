@@ -10,6 +10,12 @@ from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
 A, L, THD, CW = 0.01, 0.001, 360, 0.2
+# Table entries are compared element-wise at 1e-4; entries below FLOOR x the largest one are measured against that floor.
+# At d = 256 the score x = D(q) - D(p) is the difference of two sums of ~256 squares (|D| ~ 40): float32 resolves it to
+# ~1e-5 absolute, so g = sigmoid(-x) and with it every gradient entry carries ~1e-5 relative error, i.e. alpha * 1e-5 * |u - p|
+# ~ 1e-7 absolute on a table whose entries are ~0.5 -- the float32 arithmetic the reference itself runs (floatX = float32)
+# has the same granularity.  Measured: whole-array error 2e-7 .. 5e-7, element-wise 1.0e-4 .. 1.8e-4 at a 1e-3 floor.
+FLOOR = 1e-2
 
 
 def _model(cls, st, n_user, n_item, d):
@@ -48,7 +54,7 @@ def test_sequential_k_matches_oracle(engine, K, d):
         want.append(l)
     assert_close(got, want, 1e-4, "losses")
     for k in ("du", "dp", "ds"):
-        assert_close(getattr(m, k).get_value(), ref[k], 1e-4, k)
+        assert_close(getattr(m, k).get_value(), ref[k], 1e-4, k, floor=FLOOR)
 
 
 def test_sequential_k1_is_the_reference_step(engine):
@@ -69,7 +75,7 @@ def test_sequential_k1_is_the_reference_step(engine):
         want.append(l)
     assert_close(la, want, 1e-4, "losses vs reference step"); assert_close(la, lb, 1e-5, "losses vs K = 1 kernel")
     for k in ("du", "dp", "ds"):
-        assert_close(getattr(a, k).get_value(), ref[k], 1e-4, k)
+        assert_close(getattr(a, k).get_value(), ref[k], 1e-4, k, floor=FLOOR)
         assert_close(getattr(a, k).get_value(), getattr(b, k).get_value(), 1e-5, k + " vs K = 1 kernel")
 
 
@@ -97,7 +103,7 @@ def test_batch_k_matches_oracle(engine, K, d, n, host):
     keys = np.concatenate((p, Q.ravel(), pr))
     assert len(np.unique(keys)) < len(keys)                # duplicates were present
     for k in ("du", "dp", "ds"):
-        assert_close(getattr(m, k).get_value(), ref[k], 1e-4, k)
+        assert_close(getattr(m, k).get_value(), ref[k], 1e-4, k, floor=FLOOR)
 
 
 def test_batch_k_is_deterministic_and_leaves_other_rows_alone(engine):
@@ -131,5 +137,6 @@ def test_batch_k_is_deterministic_and_leaves_other_rows_alone(engine):
     want, ref = OM.prme_train_batch_k(ref, u[:n1], p[:n1], Q[:n1], pr[:n1], dist[:n1], gap[:n1], A, L, THD, CW)
     assert_close(got, want, 1e-4, "summed objective")
     rows = np.unique(np.concatenate((p[:n1], pr[:n1], Q[:n1].ravel())))
-    assert_close(m.dp.get_value()[rows], ref["dp"][rows], 1e-4, "dp rows"); assert_close(m.ds.get_value()[rows], ref["ds"][rows], 1e-4, "ds rows")
-    assert_close(m.du.get_value()[u[:n1]], ref["du"][u[:n1]], 1e-4, "du rows")
+    assert_close(m.dp.get_value()[rows], ref["dp"][rows], 1e-4, "dp rows", floor=FLOOR)
+    assert_close(m.ds.get_value()[rows], ref["ds"][rows], 1e-4, "ds rows", floor=FLOOR)
+    assert_close(m.du.get_value()[u[:n1]], ref["du"][u[:n1]], 1e-4, "du rows", floor=FLOOR)
