@@ -231,6 +231,41 @@ int poi_pull_segments(poi_engine* e, int world, int dim, const int32_t* const* p
                       const float* const* cnts_host, const int64_t* src_off_host, const int64_t* n_host,
                       int32_t* recv_local_ids_dev, float* recv_grads_dev, float* recv_cnts_dev);
 
+/* ---- the whole multi-GPU step as ONE call: no collective library on its path, no host synchronisation before the final
+ * read-back (csrc/mg_step.cuh).  Every rank owns peer-visible buffers (poi_peer_alloc, mapped by all ranks with
+ * poi_peer_open) and passes the table of everybody's pointers; entry [rank] is the rank's own (writable) memory:
+ *   shard     [rows_r x d]  item-table shard (owner = row % world, local row = row / world)
+ *   ob_ids    [cap] int32, ob_grads [cap x d], ob_cnts [cap], ob_perm [cap] int32: the gradient outbox of the rank's batch
+ *             (sorted unique global row ids, duplicate-summed gradient rows, occurrence counts, record numbers grouped by owner)
+ *   ob_meta   int32 [world + 2]: records per owner, then n_unique and B
+ *   dense     float [poi_gru_mg_dense_size], sums double[4]: dense gradients and loss sums of the rank's batch
+ *   flags     uint32 [2 * world], ZERO before the first step: [r] = last step whose outbox rank r published, [world + r] = last
+ *             step rank r applied -- written by rank r into every peer's array
+ *   slot_tab  own memory, int32 [n_local_rows x world], all -1 (the step leaves it so)
+ * cap >= 2 * B * lmax.  Steps are numbered 1, 2, ... and every rank must make the same sequence of calls with the same B.
+ * Dense gradients are summed in rank order by every rank itself (identical weights everywhere); a rank that waits longer
+ * than POI_MG_TIMEOUT_MS (default 20 000) for a peer fails the call instead of hanging.  out_host as poi_gru_train
+ * (GLOBAL sums). */
+#define POI_MG_MAX_RANKS 16
+typedef struct {
+    int32_t   world, rank;
+    int64_t   cap;
+    int64_t   n_local_rows;
+    float*    shard[POI_MG_MAX_RANKS];
+    int32_t*  ob_ids[POI_MG_MAX_RANKS];
+    float*    ob_grads[POI_MG_MAX_RANKS];
+    float*    ob_cnts[POI_MG_MAX_RANKS];
+    int32_t*  ob_perm[POI_MG_MAX_RANKS];
+    int32_t*  ob_meta[POI_MG_MAX_RANKS];
+    float*    dense[POI_MG_MAX_RANKS];
+    double*   sums[POI_MG_MAX_RANKS];
+    uint32_t* flags[POI_MG_MAX_RANKS];
+    int32_t*  slot_tab;
+} poi_mg_peers;
+int poi_gru_step_mg(poi_engine* e, const poi_gru_params* params, const poi_seq_index* index, const int32_t* uidx_host,
+                    int32_t B, int32_t max_len_host, const poi_mg_peers* peers, int64_t step, float alpha, float lambda,
+                    double* out_host);
+
 /* ---- the reference's per-epoch host loops on the device (csrc/sampling.cuh).
  * poi_sample_negatives = fun_random_neg_masks_tra / _tes (Load_Data_by_length.py:127-162): out[u][t] = a uniform
  * draw from [0, n_item) redrawn while it occurs in the user's forbidden rows (sorted_a [n_user x la], optionally

@@ -59,6 +59,12 @@ class PoiGeoieParams(Structure):
                 ("n_rows", c_int64), ("H", c_int32)]
 
 
+class PoiMgPeers(Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("cap", c_int64), ("n_local_rows", c_int64)] + \
+               [(k, c_void_p * 16) for k in ("shard", "ob_ids", "ob_grads", "ob_cnts", "ob_perm", "ob_meta", "dense", "sums", "flags")] + \
+               [("slot_tab", c_void_p)]
+
+
 _E = c_void_p
 _PROTOS = {
     "poi_engine_create": (c_int, [c_int, POINTER(_E)]),
@@ -122,6 +128,8 @@ _PROTOS = {
     "poi_prme_train_batch_k": (c_int, [_E, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_double,
                                        c_float, c_float, POINTER(c_double)]),
+    "poi_gru_step_mg": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32, POINTER(PoiMgPeers),
+                                c_int64, c_float, c_float, POINTER(c_double)]),
     "poi_geoie_train": (c_int, [_E, POINTER(PoiGeoieParams), c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_void_p, c_int32, c_float, c_float, POINTER(c_double)]),
     "poi_score_topk": (c_int, [_E, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_float, c_int32,

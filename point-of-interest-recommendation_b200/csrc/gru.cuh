@@ -430,6 +430,7 @@ struct MgCtx {
     float* row_grads;        // [n_unique x d] duplicate-summed loss gradient per unique row
     float* row_cnt;          // [n_unique] occurrences (L2 multiplicity)
     double* loss_sums;       // device double[3]: sur, bpr, gwd
+    bool no_sync = false;    // poi_gru_step_mg: the caller continues on the stream, nothing is read back here
 };
 struct MgLayout { int64_t ui, wh, bi, vs, bs, di, dicnt, total; };
 struct GruIdx;
@@ -686,6 +687,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
     POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     phase_mark(e, 8);
     if (e->capturing) return 0;          // graph capture (poi_gru_train): the caller launches the graph and synchronises
+    if (mg && mg->no_sync) return 0;
     POI_CK(e, cudaStreamSynchronize(e->stream));
     if (e->kprof) prof_harvest(e);
     if (out_host) for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];

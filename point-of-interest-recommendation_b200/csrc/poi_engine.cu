@@ -412,3 +412,4 @@ int poi_prme_train_seq(poi_engine* e, float* du, float* dp, float* ds_, int32_t 
 }  // extern "C"
 
 #include "api_more.cuh"
+#include "mg_step.cuh"

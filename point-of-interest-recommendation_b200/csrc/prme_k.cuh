@@ -301,7 +301,8 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
                  float* __restrict__ GU, float* __restrict__ GL, double* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char prme_tma_smem[];
     __shared__ uint64_t bar[2];
-    __shared__ float sD[PRME_MAXK + 1], sg[PRME_MAXK + 1], sl_[PRME_MAXK + 1];
+    __shared__ float sD[PRME_MAXK + 1], sg[PRME_MAXK + 1];
+    __shared__ double sloss[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = b.K, R = K + 2, NR = 2 * K + 4, d = d4 * 4;
     const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = row_bytes * (uint32_t)NR;
@@ -309,34 +310,50 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
     const int ngrp = 256 / d4;
     if (tid == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::fence_barrier_init(); }
     __syncthreads();
-    // warp 0 issues the bulk copies of check-in i into stage s: lane 0 arms the barrier with the stage's byte count, then
-    // every lane sends the rows r = lane, lane + 32, ... (one instruction per row)
-    auto issue = [&](int i, int s) {
+    // Warp 0 issues the bulk copies: lane 0 arms the stage's barrier with the byte count, then lane l sends rows l, l + 32,
+    // ... (one instruction per row).  The source pointers of a check-in are looked up one iteration AHEAD of their use
+    // (src_next), so that the index loads are off the critical path.
+    constexpr int MAXRPL = (2 * PRME_MAXK + 4 + 31) / 32;       // rows per lane, upper bound
+    const int rpl = (NR + 31) / 32;
+    const float* src_next[MAXRPL];
+    auto lookup = [&](int i) {
+        if (warp != 0) return;
+#pragma unroll
+        for (int q = 0; q < MAXRPL; ++q) {
+            const int r = lane + 32 * q;
+            if (q < rpl && r < NR && i < b.N) {
+                if (r == 0) src_next[q] = du + (size_t)b.u[i] * d;
+                else if (r == 1) src_next[q] = ds + (size_t)b.prev[i] * d;
+                else {
+                    const int jj = r - 2 <= K ? r - 2 : r - 3 - K;
+                    const size_t x = (size_t)(jj == 0 ? b.p[i] : b.q[(size_t)i * K + jj - 1]);
+                    src_next[q] = (r - 2 <= K ? dp : ds) + x * d;
+                }
+            }
+        }
+    };
+    auto issue = [&](int s) {
         if (warp != 0) return;
         tc::fence_async_smem();                        // generic-proxy reads of this stage (two iterations ago) before async writes
         const uint32_t barp = tc::smem_u32(&bar[s]);
         if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barp), "r"(stage_bytes) : "memory");
         __syncwarp();
         const uint32_t base = tc::smem_u32(prme_tma_smem) + (uint32_t)s * stage_bytes;
-        for (int r = lane; r < NR; r += 32) {
-            const float* src;
-            if (r == 0) src = du + (size_t)b.u[i] * d;
-            else if (r == 1) src = ds + (size_t)b.prev[i] * d;
-            else {
-                const int j = r - 2 <= K ? r - 2 : r - 3 - K;
-                const size_t x = (size_t)(j == 0 ? b.p[i] : b.q[(size_t)i * K + j - 1]);
-                src = (r - 2 <= K ? dp : ds) + x * d;
-            }
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(base + (uint32_t)r * row_bytes), "l"(src), "r"(row_bytes), "r"(barp) : "memory");
+#pragma unroll
+        for (int q = 0; q < MAXRPL; ++q) {
+            const int r = lane + 32 * q;
+            if (q < rpl && r < NR)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(base + (uint32_t)r * row_bytes), "l"(src_next[q]), "r"(row_bytes), "r"(barp) : "memory");
         }
     };
-    double loss_acc = 0.0;
+    double loss_acc = 0.0;                              // thread k (1 <= k <= K) accumulates its own negative's terms
     int it = 0;
-    if ((int)blockIdx.x < b.N) issue(blockIdx.x, 0);
-    for (int i = blockIdx.x; i < b.N; i += gridDim.x, ++it) {
+    const int G0 = (int)gridDim.x;
+    if ((int)blockIdx.x < b.N) { lookup(blockIdx.x); issue(0); lookup(blockIdx.x + G0); }
+    for (int i = blockIdx.x; i < b.N; i += G0, ++it) {
         const int s = it & 1;
-        if (i + (int)gridDim.x < b.N) issue(i + gridDim.x, s ^ 1);
+        if (i + G0 < b.N) { issue(s ^ 1); lookup(i + 2 * G0); }
         const bool far = b.gap[i] > thd;
         const float w = sqrtf(sqrtf(1.0f + b.dist[i]));
         const float cp = far ? 1.f : w * cw, cs = far ? 0.f : w * (1.f - cw);
@@ -356,11 +373,12 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
             if (lane == 0) sD[j] = acc;
         }
         __syncthreads();
-        if (tid >= 1 && tid <= K) { const float x = sD[tid] - sD[0]; sg[tid] = sigmoidf_(-x); sl_[tid] = logsigmoidf_(x); }
+        if (tid >= 1 && tid <= K) { const float x = sD[tid] - sD[0]; sg[tid] = sigmoidf_(-x); loss_acc += (double)logsigmoidf_(x); }
         __syncthreads();
+        // G = sum_k g_k: every warp adds the same values in the same order (lane partial sums, fixed shuffle tree)
         float G = 0.f;
-        for (int k = 1; k <= K; ++k) G += sg[k];
-        if (tid == 0) { double ls = 0.0; for (int k = 1; k <= K; ++k) ls += (double)sl_[k]; loss_acc += ls; }
+        for (int k = 1 + lane; k <= K; k += 32) G += sg[k];
+        G = warp_sum(G);
         if (tid <= K + 1) {
             const float cj = tid == 0 ? -G : (tid <= K ? sg[tid] : 0.f);
             KP[(size_t)i * R + tid] = cj * 2.f * cp; KS[(size_t)i * R + tid] = cj * 2.f * cs;
@@ -387,7 +405,11 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
         }
         __syncthreads();          // stage s, red, sD, sg are free again
     }
-    if (tid == 0) part[blockIdx.x] = loss_acc;
+    // block loss: lanes in a fixed tree, then the 8 warps in order
+    loss_acc = warp_sum_d(loss_acc);
+    if (lane == 0) sloss[warp] = loss_acc;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int ww = 0; ww < 8; ++ww) t += sloss[ww]; part[blockIdx.x] = t; }
 }
 
 static bool prme_score_tma_ok(int d4, int K, size_t* smem) {

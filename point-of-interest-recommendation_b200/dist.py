@@ -22,14 +22,15 @@ G ranks x batch B is the same update as 1 rank x batch G*B up to floating-point 
 `RowExchange` is device-agnostic (CPU tensors + gloo work too) so the routing logic is testable
 without GPUs.
 
-Peer-memory path (default on GPUs, `peer=True`): steps 2 and 4 lose their all-to-alls.  Every rank's shard and
-gradient outbox live in IPC-exported device memory that all ranks of the box map once (csrc/peer.cuh); the rows
-are then gathered by a kernel reading the OWNERS' shards through NVLink (`poi_gather_rows_sharded`), and each owner
-pulls the (id, gradient row, count) records addressed to it out of every rank's outbox (`poi_pull_segments`), in
-rank order, so the duplicate sum keeps its fixed order.  What remains on NCCL: the step-start all-reduce (batch
-sizes; also the barrier that orders "owners have applied step k" before "anyone gathers for step k+1"), and the
-all-reduce of the dense gradients / loss sums / per-owner record counts (also the barrier between "outboxes
-written" and "owners pull").
+Peer-memory path (default on GPUs, `peer=True`): the whole step is ONE engine call (`poi_gru_step_mg`,
+csrc/mg_step.cuh) with no collective library on its path and no host synchronisation before the final read-back.
+Every rank's shard, gradient outbox, dense-gradient buffer and flag array live in IPC-exported device memory that all
+ranks of the box map once.  Rows are gathered by a kernel reading the OWNERS' shards through NVLink; ranks tell each
+other "my outbox is written" / "I have applied the step" by storing step counters into each other's flag arrays
+(waiting kernels time out into an error instead of hanging); the dense gradients are summed in rank order by every
+rank itself reading every peer's buffer (bit-identical weights everywhere); each owner finds the records addressed to
+it through a direct-address table and sums them, sources in rank order, straight out of the peers' outboxes.  NCCL is
+used at construction only (exchange of the IPC handles, one barrier).
 """
 from __future__ import annotations
 
@@ -181,33 +182,45 @@ class ShardedSpatialGru:
             self._setup_peer(int(max_batch) if max_batch else min(int(self.P.t.shape[0]), 4096))
 
     def _setup_peer(self, max_batch):
-        """Allocate the gradient outbox, exchange the IPC handles once, map every peer's shard and outbox."""
-        eng, W, d = self.engine, self.world, self.d
+        """Allocate this rank's peer-visible buffers, exchange the IPC handles once, map every peer's buffers and fill the
+        pointer table `poi_gru_step_mg` takes."""
+        from ._lib import PoiMgPeers
+        from .engine import Engine
+        eng, W, d, dev = self.engine, self.world, self.d, self.engine.torch_device
         self._cap = 2 * max_batch * int(self.P.t.shape[1])       # unique row ids of a step: at most 2 * B * lmax
-        ob_ids, h_ids = eng.peer_alloc((self._cap,), torch.int32)
-        ob_grads, h_gr = eng.peer_alloc((self._cap, d), torch.float32)
-        ob_cnts, h_cn = eng.peer_alloc((self._cap,), torch.float32)
-        ob_perm, h_pm = eng.peer_alloc((self._cap,), torch.int32)
-        mine = dict(lt=self._h_lt, lt_shape=tuple(self.lt_local.t.shape), ids=h_ids, grads=h_gr, cnts=h_cn, perm=h_pm,
-                    cap=self._cap)
+        n_dense = Engine.gru_mg_dense_size(self._params())
+        spec = dict(ob_ids=((self._cap,), torch.int32), ob_grads=((self._cap, d), torch.float32), ob_cnts=((self._cap,), torch.float32),
+                    ob_perm=((self._cap,), torch.int32), ob_meta=((W + 2,), torch.int32), dense=((n_dense,), torch.float32),
+                    sums=((4,), torch.float64), flags=((2 * W,), torch.int32))
+        own, handles = {}, {}
+        for k, (shape, dt) in spec.items():
+            own[k], handles[k] = eng.peer_alloc(shape, dt)
+            own[k].zero_()
+        own["shard"], handles["shard"] = self.lt_local.t, self._h_lt
+        self._own = own
+        self._slot_tab = torch.full((int(self.lt_local.t.shape[0]) * W,), -1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        mine = dict(h=handles, lt_shape=tuple(self.lt_local.t.shape), cap=self._cap)
         every = [None] * W
         dist.all_gather_object(every, mine, group=self.group)
         if any(x["cap"] != self._cap for x in every):
             raise ValueError("all ranks must use the same max_batch / lmax")
-        self._shards, self._ob_ids, self._ob_grads, self._ob_cnts, self._ob_perm = [], [], [], [], []
+        pt = PoiMgPeers()
+        pt.world, pt.rank, pt.cap, pt.n_local_rows = W, self.rank, self._cap, int(self.lt_local.t.shape[0])
+        self._mapped = []
         for r, x in enumerate(every):
-            if r == self.rank:
-                self._shards.append(self.lt_local.t); self._ob_ids.append(ob_ids)
-                self._ob_grads.append(ob_grads); self._ob_cnts.append(ob_cnts); self._ob_perm.append(ob_perm)
-            else:
-                self._shards.append(eng.peer_open(x["lt"], x["lt_shape"], torch.float32))
-                self._ob_ids.append(eng.peer_open(x["ids"], (self._cap,), torch.int32))
-                self._ob_grads.append(eng.peer_open(x["grads"], (self._cap, d), torch.float32))
-                self._ob_cnts.append(eng.peer_open(x["cnts"], (self._cap,), torch.float32))
-                self._ob_perm.append(eng.peer_open(x["perm"], (self._cap,), torch.int32))
-        # loss sums (3) + the world x world matrix "records rank p sends to owner o", all-reduced together
-        self._sums = torch.zeros(3 + W * W, dtype=torch.float64, device=self.engine.torch_device)
-        self._owners = torch.arange(W, dtype=torch.int64, device=self.engine.torch_device).unsqueeze(1)
+            for k in list(spec) + ["shard"]:
+                if r == self.rank:
+                    ptr = own[k].data_ptr()
+                else:
+                    shape, dt = (x["lt_shape"], torch.float32) if k == "shard" else spec[k]
+                    m = eng.peer_open(x["h"][k], shape, dt)
+                    self._mapped.append(m)
+                    ptr = m.data_ptr()
+                getattr(pt, k)[r] = ptr
+        pt.slot_tab = self._slot_tab.data_ptr()
+        self._peers = pt
+        self._step_no = 0
         dist.barrier(group=self.group)
 
     def _params(self):
@@ -245,82 +258,46 @@ class ShardedSpatialGru:
     def _step(self, uidx, index, Pt, Qt, lens_host):
         eng, dev = self.engine, self.engine.torch_device
         B = uidx.size
+        if self.peer:
+            # one engine call: slice + sort, sharded gather over NVLink, forward + backward, flag exchange, rank-order
+            # dense all-reduce, owner-side sparse SGD straight out of the peers' outboxes
+            if not self.uniform_batch:
+                raise ValueError("the peer-memory step needs the same batch size on every rank (construct with peer=False otherwise)")
+            if 2 * B * int(Pt.shape[1]) > self._cap:
+                raise ValueError("batch of %d users needs up to %d outbox records, capacity is %d: construct with a larger max_batch"
+                                 % (B, 2 * B * int(Pt.shape[1]), self._cap))
+            self._step_no += 1
+            out = eng.gru_step_mg(self._params(), index, uidx, int(lens_host[uidx].max()), self._peers, self._step_no,
+                                  self._alpha, self._lambda)
+            return [out[0], out[1], out[2], np.array([out[3], out[4]])]
         if self.trace: self.trace.mark('start')
         meta = torch.tensor([B, int((lens_host[uidx] >= 1).sum())], dtype=torch.int64, device=dev)
         if self.world > 1:
             dist.all_reduce(meta, group=self.group)
-        # the all-reduce is also the barrier "every owner has applied the previous step" -> shards may be read
-        check_later = self.head and self.uniform_batch and self.world > 1
-        if check_later:
-            global_batch, n_nonempty = B * self.world, 0           # no host wait; verified after the step's final sync
-        else:
-            global_batch, n_nonempty = int(meta[0].item()), int(meta[1].item())
+        global_batch, n_nonempty = int(meta[0].item()), int(meta[1].item())
         if self.trace: self.trace.mark('meta_allreduce')
         uniq = eng.gru_mg_prepare(self._params(), index, uidx, Pt.shape[1])     # slice + sort once, reused below
         if self.trace: self.trace.mark('prepare(slice+sort)')
         n_u = uniq.numel()
         max_len = int(lens_host[uidx].max())
-        if self.peer:
-            recv_local, recv_grads, recv_cnts = self._exchange_peer(uniq, index, uidx, max_len, global_batch)
-        else:
-            ex = RowExchange(uniq, self.world, self.group)
-            rows = ex.fetch(lambda loc: eng.gather_rows(self.lt_local.t, loc))
-            if self.trace: self.trace.mark('a2a_fetch_rows')
-            row_grads = torch.empty((n_u, self.d), dtype=torch.float32, device=dev)
-            row_cnt = torch.empty(n_u, dtype=torch.float32, device=dev)
-            eng.gru_train_mg(self._params(), index, uidx, max_len, global_batch, rows,
-                             self._dense, row_grads, row_cnt, self._sums)
-            if self.trace: self.trace.mark('train_mg(fwd+bwd)')
-            if self.world > 1:
-                dist.all_reduce(self._dense, group=self.group)
-                dist.all_reduce(self._sums, group=self.group)
-            recv_grads = ex.push(row_grads)
-
-            recv_cnts = ex.push(row_cnt)
-            recv_local = ex.recv_local
+        ex = RowExchange(uniq, self.world, self.group)
+        rows = ex.fetch(lambda loc: eng.gather_rows(self.lt_local.t, loc))
+        if self.trace: self.trace.mark('a2a_fetch_rows')
+        row_grads = torch.empty((n_u, self.d), dtype=torch.float32, device=dev)
+        row_cnt = torch.empty(n_u, dtype=torch.float32, device=dev)
+        eng.gru_train_mg(self._params(), index, uidx, max_len, global_batch, rows,
+                         self._dense, row_grads, row_cnt, self._sums)
+        if self.trace: self.trace.mark('train_mg(fwd+bwd)')
+        if self.world > 1:
+            dist.all_reduce(self._dense, group=self.group)
+            dist.all_reduce(self._sums, group=self.group)
+        recv_grads = ex.push(row_grads)
+        recv_cnts = ex.push(row_cnt)
+        recv_local = ex.recv_local
         self.last_exchange_rows = n_u
         if self.trace: self.trace.mark('exchange_back')
         out = eng.gru_apply_mg(self._params(), self._dense, self._sums, global_batch, 0 if self.head else n_nonempty,
                                self.lt_local.t, recv_local, recv_grads, recv_cnts, self._alpha, self._lambda)
         if self.trace: self.trace.mark('apply')
         if self.trace: self.trace.end_step()
-        if check_later and int(meta[0].item()) != global_batch:
-            raise ValueError("uniform_batch=True but the ranks passed different batch sizes (sum %d, expected %d): "
-                             "this step's update is wrong; construct with uniform_batch=False" % (int(meta[0].item()), global_batch))
         return [out[0], out[1], out[2], np.array([out[3], out[4]])]
-
-    def _exchange_peer(self, uniq, index, uidx, max_len, global_batch):
-        """Steps 2-4 over NVLink peer memory: gather from the owners' shards, compute, publish the gradient rows
-        grouped by owner in this rank's outbox, all-reduce the dense part (and the record counts), pull what this
-        rank owns out of every outbox."""
-        eng, dev, W, d = self.engine, self.engine.torch_device, self.world, self.d
-        n_u = uniq.numel()
-        if n_u > self._cap:
-            raise ValueError("batch needs %d unique rows, outbox holds %d: construct with a larger max_batch" % (n_u, self._cap))
-        rows = torch.empty((n_u, d), dtype=torch.float32, device=dev)
-        eng.gather_rows_sharded(self._shards, uniq, rows)
-        if self.trace: self.trace.mark('gather_sharded')
-        # the backward pass writes its per-row results straight into this rank's outbox (peer-visible memory)
-        me = self.rank
-        self._ob_ids[me][:n_u].copy_(uniq)
-        row_grads, row_cnt = self._ob_grads[me][:n_u], self._ob_cnts[me][:n_u]
-        eng.gru_train_mg(self._params(), index, uidx, max_len, global_batch, rows, self._dense, row_grads, row_cnt, self._sums)
-        if self.trace: self.trace.mark('train_mg(fwd+bwd)')
-        # perm: record numbers grouped by owner, ascending id inside a group (one stable radix pass on id % world);
-        # the group sizes go into this rank's row of the world x world count matrix that rides on the all-reduce
-        self._sums[3:].zero_()
-        eng.group_by_owner(uniq, W, self._ob_perm[me][:max(n_u, 1)], self._sums[3 + me * W: 3 + (me + 1) * W])
-        if self.trace: self.trace.mark('outbox(perm list)')
-        dist.all_reduce(self._dense, group=self.group)
-        dist.all_reduce(self._sums, group=self.group)         # completes => every outbox of this step is written
-        if self.trace: self.trace.mark('allreduce(dense+sums)')
-        cm = self._sums[3:].cpu().numpy().reshape(W, W).astype(np.int64)       # cm[p, o]: records p -> o (one host sync)
-        if self.trace: self.trace.mark('counts_to_host')
-        src_off, n = pull_plan(cm, me)
-        n_recv = int(sum(n))
-        recv_local = torch.empty(n_recv, dtype=torch.int32, device=dev)
-        recv_grads = torch.empty((n_recv, d), dtype=torch.float32, device=dev)
-        recv_cnts = torch.empty(n_recv, dtype=torch.float32, device=dev)
-        eng.pull_segments(self._ob_perm, self._ob_ids, self._ob_grads, self._ob_cnts, src_off, n, recv_local, recv_grads, recv_cnts)
-        if self.trace: self.trace.mark('pull_segments')
-        return recv_local, recv_grads, recv_cnts

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import PoiGeoieParams, PoiGruParams, PoiSeqIndex, lib
+from ._lib import PoiGeoieParams, PoiGruParams, PoiMgPeers, PoiSeqIndex, lib
 
 
 
@@ -373,6 +373,14 @@ class Engine:
                                       lt_local.shape[0], _dev_i32(recv_ids, "recv_ids") if n_recv else 0,
                                       _dev_f32(recv_grads, "recv_grads") if n_recv else 0,
                                       _dev_f32(recv_cnts, "recv_cnts") if n_recv else 0, n_recv, alpha, lam, out))
+        return list(out)
+
+    def gru_step_mg(self, params, index, uidx, max_len, peers, step, alpha, lam):
+        """The whole multi-GPU step in one call (csrc/mg_step.cuh); `peers` is a filled PoiMgPeers."""
+        uidx = _host_i32(uidx, "uidx").reshape(-1)
+        out = (c_double * 5)()
+        self._ck(lib.poi_gru_step_mg(self._h, byref(params), byref(index), uidx.ctypes.data, uidx.size, int(max_len),
+                                     byref(peers), int(step), alpha, lam, out))
         return list(out)
 
     # ---- BPR / PRME -------------------------------------------------------------------------
