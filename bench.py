@@ -582,6 +582,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch users per GPU per step; strong: --batch users per step split over the GPUs")
     ap.add_argument("--batch", type=int, default=4096, help="users per step per GPU (weak) / per step (strong)")
+    ap.add_argument("--c5-items", type=int, default=0, help="c5 smoke runs: catalogue size override (0 = the config's 10M)")
+    ap.add_argument("--c5-seq", type=int, default=0, help="c5 smoke runs: sequence length override (0 = the config's 256)")
     ap.add_argument("--positions", type=int, default=4, help="c3 / c4: consecutive positions of every user in one mini-batch step")
     ap.add_argument("--cpu-batch", type=int, default=512, help="users per CPU-oracle step")
     ap.add_argument("--gemm-mode", type=int, default=1,
@@ -598,6 +600,8 @@ def main():
     ap.add_argument("--no-micro", action="store_true", help="skip the stand-alone gather / scatter HBM micro-benchmark")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
+    if args.config == "c5" and "--batch" not in " ".join(sys.argv):
+        args.batch = 8192 if args.scaling == "strong" else 2048
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -265,6 +265,11 @@ typedef struct {
 int poi_gru_step_mg(poi_engine* e, const poi_gru_params* params, const poi_seq_index* index, const int32_t* uidx_host,
                     int32_t B, int32_t max_len_host, const poi_mg_peers* peers, int64_t step, float alpha, float lambda,
                     double* out_host);
+/* the same step with the batch's index ROWS supplied from host memory ([B x lmax] each; the copies are part of the call):
+ * the end-to-end entry, as poi_gru_train_host_rows is for one GPU */
+int poi_gru_step_mg_host_rows(poi_engine* e, const poi_gru_params* params, const int32_t* p_host, const int32_t* q_host,
+                              const int32_t* dp_host, const int32_t* dq_host, const int32_t* lens_host, int32_t B, int32_t lmax,
+                              const poi_mg_peers* peers, int64_t step, float alpha, float lambda, double* out_host);
 
 /* ---- the reference's per-epoch host loops on the device (csrc/sampling.cuh).
  * poi_sample_negatives = fun_random_neg_masks_tra / _tes (Load_Data_by_length.py:127-162): out[u][t] = a uniform

@@ -130,6 +130,8 @@ _PROTOS = {
                                        c_float, c_float, POINTER(c_double)]),
     "poi_gru_step_mg": (c_int, [_E, POINTER(PoiGruParams), POINTER(PoiSeqIndex), c_void_p, c_int32, c_int32, POINTER(PoiMgPeers),
                                 c_int64, c_float, c_float, POINTER(c_double)]),
+    "poi_gru_step_mg_host_rows": (c_int, [_E, POINTER(PoiGruParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                          POINTER(PoiMgPeers), c_int64, c_float, c_float, POINTER(c_double)]),
     "poi_geoie_train": (c_int, [_E, POINTER(PoiGeoieParams), c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_void_p, c_int32, c_float, c_float, POINTER(c_double)]),
     "poi_score_topk": (c_int, [_E, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_float, c_int32,

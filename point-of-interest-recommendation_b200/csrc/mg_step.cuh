@@ -202,19 +202,24 @@ __global__ void k_finalize_from_sums4(const double* __restrict__ sums, float* sc
 }
 __global__ void k_mg_set_extra(double* sums, double v) { if (threadIdx.x == 0 && blockIdx.x == 0) sums[3] = v; }
 
-extern "C" int poi_gru_step_mg(poi_engine* e, const poi_gru_params* p, const poi_seq_index* index, const int32_t* uidx_host,
-                               int32_t B, int32_t max_len, const poi_mg_peers* pr, int64_t step, float alpha, float lambda,
-                               double* out_host) {
+// index rows either resident on the device (uidx_host = the B row numbers) or supplied from host memory (rows_host != NULL:
+// [B x lmax] each, copied inside the call -- the end-to-end path)
+struct MgHostRows { const int32_t* p; const int32_t* q; const int32_t* dp; const int32_t* dq; const int32_t* lens; };
+
+static int gru_step_mg_body(poi_engine* e, const poi_gru_params* p, const poi_seq_index* index, const int32_t* uidx_host,
+                            const MgHostRows* rows_host, int32_t B, int32_t lmax, int32_t max_len, const poi_mg_peers* pr,
+                            int64_t step, float alpha, float lambda, double* out_host) {
     e->prep_valid = false;
     POI_TRY(begin_call(e));
     if (!p || !p->ui || !p->wh || !p->bi) POI_FAIL(e, "gru params: null pointer");
     if (p->d <= 0 || p->d % 4 || p->H != p->d) POI_FAIL(e, "n_in must equal n_hidden and be a multiple of 4");
     const bool head = p->di != nullptr;
-    if (!index || !index->p || !index->q || !index->lens || (head && (!index->dp || !index->dq))) POI_FAIL(e, "index matrices missing");
+    if (!rows_host && (!index || !index->p || !index->q || !index->lens || (head && (!index->dp || !index->dq)))) POI_FAIL(e, "index matrices missing");
+    if (rows_host && (!rows_host->p || !rows_host->q || !rows_host->lens || (head && (!rows_host->dp || !rows_host->dq)))) POI_FAIL(e, "host index rows missing");
     if (!pr || pr->world < 1 || pr->world > POI_MAX_PEERS || pr->rank < 0 || pr->rank >= pr->world) POI_FAIL(e, "bad peer table");
-    if (B <= 0 || step < 1) POI_FAIL(e, "bad batch size / step number");
+    if (B <= 0 || lmax <= 0 || step < 1) POI_FAIL(e, "bad batch size / step number");
     const int W = pr->world, me = pr->rank, d = p->d, H = p->H, din = head ? 2 * d : d, nD = head ? p->n_rows_di : 0;
-    const int64_t LB = (int64_t)index->lmax * B;
+    const int64_t LB = (int64_t)lmax * B;
     if (2 * LB > pr->cap) POI_FAIL(e, "batch needs up to %lld outbox records, capacity is %lld", (long long)(2 * LB), (long long)pr->cap);
     const MgLayout ML = mg_layout(H, din, nD, d);
     unsigned long long timeout_ns = 20000ull * 1000000ull;
@@ -224,15 +229,34 @@ extern "C" int poi_gru_step_mg(poi_engine* e, const poi_gru_params* p, const poi
     POI_TRY(arena_get(e, 4, &err));
     POI_CK(e, cudaMemsetAsync(err, 0, 4, e->stream));
     phase_mark(e, 0);
-    POI_TRY(stage_reserve(e, (size_t)B * 4 + 256));
-    size_t so = 0;
-    int32_t* uidx_dev = nullptr;
-    POI_TRY(gru_upload_i32(e, uidx_host, (size_t)B, &uidx_dev, &so));
     GruIdx ix;
-    POI_TRY(gru_alloc_idx(e, B, index->lmax, head, &ix));
-    POI_CAT(e, CAT_INDEX, 0, 0);
-    POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv(LB, 256), 256, 0, index->p, index->q, head ? index->dp : nullptr,
-               head ? index->dq : nullptr, index->lens, index->lmax, uidx_dev, B, ix.PQt, ix.DPt, ix.DQt, ix.lensB);
+    int64_t n_nonempty = 0;
+    if (rows_host) {
+        POI_TRY(stage_reserve(e, (head ? 4 : 2) * ((size_t)LB * 4 + 256) + (size_t)B * 4 + 256));
+        size_t so = 0;
+        int32_t *P = nullptr, *Q = nullptr, *DP = nullptr, *DQ = nullptr, *lens = nullptr;
+        POI_TRY(gru_upload_i32(e, rows_host->p, (size_t)LB, &P, &so));
+        POI_TRY(gru_upload_i32(e, rows_host->q, (size_t)LB, &Q, &so));
+        if (head) { POI_TRY(gru_upload_i32(e, rows_host->dp, (size_t)LB, &DP, &so)); POI_TRY(gru_upload_i32(e, rows_host->dq, (size_t)LB, &DQ, &so)); }
+        POI_TRY(gru_upload_i32(e, rows_host->lens, (size_t)B, &lens, &so));
+        max_len = 0;
+        for (int b = 0; b < B; ++b) { max_len = std::max(max_len, rows_host->lens[b]); n_nonempty += rows_host->lens[b] >= 1; }
+        POI_TRY(gru_alloc_idx(e, B, lmax, head, &ix));
+        POI_CAT(e, CAT_INDEX, 0, 0);
+        POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv(LB, 256), 256, 0, P, Q, DP, DQ, lens, lmax, (const int32_t*)nullptr, B,
+                   ix.PQt, ix.DPt, ix.DQt, ix.lensB);
+    } else {
+        POI_TRY(stage_reserve(e, (size_t)B * 4 + 256));
+        size_t so = 0;
+        int32_t* uidx_dev = nullptr;
+        POI_TRY(gru_upload_i32(e, uidx_host, (size_t)B, &uidx_dev, &so));
+        POI_TRY(gru_alloc_idx(e, B, lmax, head, &ix));
+        POI_CAT(e, CAT_INDEX, 0, 0);
+        POI_LAUNCH(e, k_slice_indices, (unsigned)poi_cdiv(LB, 256), 256, 0, index->p, index->q, head ? index->dp : nullptr,
+                   head ? index->dq : nullptr, index->lens, lmax, uidx_dev, B, ix.PQt, ix.DPt, ix.DQt, ix.lensB);
+        n_nonempty = B;                                  // reference data: every user has L >= 1 (GRU.py:352)
+    }
+    if (head) n_nonempty = 0;
     SegList seg_lt, seg_di;
     POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.PQt), 2 * LB, (uint32_t)p->n_rows_lt, true, &seg_lt));
     if (head) POI_TRY(build_segments(e, reinterpret_cast<const uint32_t*>(ix.DPt), LB, (uint32_t)nD, false, &seg_di));
@@ -259,9 +283,7 @@ extern "C" int poi_gru_step_mg(poi_engine* e, const poi_gru_params* p, const poi
     MgCtx mg; mg.rows = rows; mg.global_batch = B * W; mg.dense_grads = pr->dense[me];
     mg.row_grads = pr->ob_grads[me]; mg.row_cnt = pr->ob_cnts[me]; mg.loss_sums = pr->sums[me]; mg.no_sync = true;
     PreSeg pre{&seg_lt, &seg_di};
-    int64_t n_nonempty = 0;
-    if (!head) { for (int b = 0; b < B; ++b) n_nonempty += 1; }      // reference data: every user has L >= 1 (GRU.py:352)
-    POI_TRY(gru_train_core(e, p, ix, B, index->lmax, max_len, 0, 0.f, 0.f, nullptr, &mg, &pre));
+    POI_TRY(gru_train_core(e, p, ix, B, lmax, max_len, 0, 0.f, 0.f, nullptr, &mg, &pre));
     POI_CAT(e, CAT_REDUCE, 0, 0);
     POI_LAUNCH(e, k_mg_set_extra, 1, 32, 0, pr->sums[me], (double)n_nonempty * 0.6931471805599453);
     // ---- outbox: ids, permutation grouped by owner, group sizes ----
@@ -333,4 +355,19 @@ extern "C" int poi_gru_step_mg(poi_engine* e, const poi_gru_params* p, const poi
     if (ec == 900) POI_FAIL(e, "multi-GPU step %lld: the ranks passed different batch sizes; this step's update is wrong", (long long)step);
     for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];
     return 0;
+}
+
+extern "C" int poi_gru_step_mg(poi_engine* e, const poi_gru_params* p, const poi_seq_index* index, const int32_t* uidx_host,
+                               int32_t B, int32_t max_len, const poi_mg_peers* pr, int64_t step, float alpha, float lambda,
+                               double* out_host) {
+    if (!index) POI_FAIL(e, "index matrices missing");
+    return gru_step_mg_body(e, p, index, uidx_host, nullptr, B, index->lmax, max_len, pr, step, alpha, lambda, out_host);
+}
+
+extern "C" int poi_gru_step_mg_host_rows(poi_engine* e, const poi_gru_params* p, const int32_t* p_host, const int32_t* q_host,
+                                         const int32_t* dp_host, const int32_t* dq_host, const int32_t* lens_host, int32_t B,
+                                         int32_t lmax, const poi_mg_peers* pr, int64_t step, float alpha, float lambda,
+                                         double* out_host) {
+    MgHostRows hr{p_host, q_host, dp_host, dq_host, lens_host};
+    return gru_step_mg_body(e, p, nullptr, nullptr, &hr, B, lmax, 0, pr, step, alpha, lambda, out_host);
 }

@@ -242,6 +242,13 @@ class ShardedSpatialGru:
         from .engine import Engine
         dev = self.engine.torch_device
         B = p.shape[0]
+        if self.peer:
+            if 2 * B * int(p.shape[1]) > self._cap:
+                raise ValueError("batch of %d users exceeds the outbox capacity: construct with a larger max_batch" % B)
+            self._step_no += 1
+            out = self.engine.gru_step_mg_host_rows(self._params(), p, q, dp if self.head else None, dq if self.head else None, lens,
+                                                    self._peers, self._step_no, self._alpha, self._lambda)
+            return [out[0], out[1], out[2], np.array([out[3], out[4]])]
         idx_p = p.to(dev, non_blocking=True); idx_q = q.to(dev, non_blocking=True)
         idx_dp = dp.to(dev, non_blocking=True) if self.head else None
         idx_dq = dq.to(dev, non_blocking=True) if self.head else None

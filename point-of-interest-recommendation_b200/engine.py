@@ -383,6 +383,16 @@ class Engine:
                                      byref(peers), int(step), alpha, lam, out))
         return list(out)
 
+    def gru_step_mg_host_rows(self, params, p, q, dp, dq, lens, peers, step, alpha, lam):
+        """Same step, index rows from (pinned) host tensors / arrays [B x lmax]: copied inside the call."""
+        f = lambda x: None if x is None else np.ascontiguousarray(x.numpy() if isinstance(x, torch.Tensor) else x, dtype=np.int32)
+        p, q, dp, dq, lens = f(p), f(q), f(dp), f(dq), f(lens)
+        out = (c_double * 5)()
+        self._ck(lib.poi_gru_step_mg_host_rows(self._h, byref(params), p.ctypes.data, q.ctypes.data,
+                                               dp.ctypes.data if dp is not None else None, dq.ctypes.data if dq is not None else None,
+                                               lens.ctypes.data, p.shape[0], p.shape[1], byref(peers), int(step), alpha, lam, out))
+        return list(out)
+
     # ---- BPR / PRME -------------------------------------------------------------------------
     def bpr_train_seq(self, ux, lt, u, p, q, alpha, lam) -> np.ndarray:
         u = _host_i32(u, "u").reshape(-1); p = _host_i32(p, "p").reshape(-1); q = _host_i32(q, "q").reshape(-1)

@@ -15,6 +15,15 @@ from ..shared import L2Expr, Shared, init_uniform
 
 
 def _lens_from_masks(masks, what):
+    if isinstance(masks, torch.Tensor):
+        # device-generated data (C5 scale): a 1-D tensor is taken as the lengths themselves, a 2-D one is checked on its device
+        if masks.dim() == 1:
+            return masks.to(torch.int32).cpu().numpy()
+        lens = masks.sum(dim=1).to(torch.int32)
+        ar = torch.arange(masks.shape[1], device=masks.device)[None, :]
+        if not torch.equal(masks.to(torch.int32), (ar < lens[:, None]).to(torch.int32)):
+            raise ValueError("%s is not a prefix mask" % what)
+        return lens.cpu().numpy()
     m = np.asarray(masks, dtype=np.int32)
     lens = m.sum(axis=1).astype(np.int32)
     # the loader only ever builds prefix masks [1]*L + [0]*(Lmax-L) (Load_Data_by_length.py:123)

@@ -197,3 +197,64 @@ def write_sequence_file(path, n_user, n_item, min_len=6, max_len=20, seed=123):
         for r in rows:
             f.write(' '.join(str(x) for x in r) + '\n')
     return path
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C5 scale (|POI| = 10M, |U| = 1M, seq = 256, d = 512): generated on the DEVICE -- the item table alone is 20.5 GB
+# ----------------------------------------------------------------------------------------------------------------------
+def hashed_uniform_rows(rows, d, seed, device, scale=1.0, chunk=1 << 20):
+    """Table rows whose values depend only on (global row id, column, seed): the same table whatever the sharding.
+    value = ((row * 2654435761 + col * 40503 + seed * 97) mod 2^24) / 2^24 - 0.5, times `scale`; fp32 [len(rows) x d]."""
+    import torch
+    rows = torch.as_tensor(rows, dtype=torch.int64, device=device)
+    out = torch.empty((rows.numel(), d), dtype=torch.float32, device=device)
+    cols = torch.arange(d, dtype=torch.int64, device=device) * 40503 + int(seed) * 97
+    for s in range(0, rows.numel(), chunk):
+        r = rows[s:s + chunk, None] * 2654435761 + cols[None, :]
+        out[s:s + chunk] = ((r & 0xFFFFFF).to(torch.float32) * (1.0 / (1 << 24)) - 0.5) * scale
+    return out
+
+
+def make_dataset_device(engine, n_user, n_item, seq, users=None, UD=40, dd=200, seed=123):
+    """`make_dataset` at C5 scale, every array built on the engine's device: uniform POI sequences (no padding), negatives
+    by the engine's device sampler (csrc/sampling.cuh: uniform, rejecting the user's own POIs -- the rule of
+    Load_Data_by_length.py:127-143 on a counter-based stream), coordinates in the Singapore-sized box and both interval
+    matrices by `poi_neg_intervals` (fp64 haversine of Load_Data_by_length.py:24-42).  `users` (int64 tensor / array of
+    global user ids, default all) selects the rows to keep; a user's rows do not depend on which other users are kept.
+    Returns int32 device tensors P, Q, DP, DQ [len(users) x seq], lens, float64 coords [n_item+1 x 2], dist_num."""
+    import torch
+    dev = engine.torch_device
+    dist_num = int(UD * 1000 / dd)
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    P = torch.randint(0, n_item, (n_user, seq), dtype=torch.int32, device=dev, generator=g)
+    coords = torch.zeros((n_item + 1, 2), dtype=torch.float64, device=dev)
+    coords[:n_item, 0] = torch.rand(n_item, dtype=torch.float64, device=dev, generator=g) * 0.25 + 1.22
+    coords[:n_item, 1] = torch.rand(n_item, dtype=torch.float64, device=dev, generator=g) * 0.44 + 103.60
+    if users is not None:
+        P = P[torch.as_tensor(users, dtype=torch.int64, device=dev)].contiguous()
+    lens = torch.full((P.shape[0],), seq, dtype=torch.int32, device=dev)
+    srt = torch.sort(P, dim=1).values.contiguous()
+    Q = engine.sample_negatives(P, srt, n_item, seed, 0)
+    del srt
+    DP = engine.neg_intervals(P, P, lens, coords, float(dd), dist_num)          # interval(p[t-1], p[t]); D at t = 0
+    DQ = engine.neg_intervals(P, Q, lens, coords, float(dd), dist_num)          # interval(p[t-1], q[t])
+    engine.sync()
+    return dict(P=P, Q=Q, DP=DP, DQ=DQ, lens=lens, coords=coords, dist_num=dist_num, n_user=int(P.shape[0]), n_item=n_item, seq=seq)
+
+
+def init_state_device(n_item, d, dist_num, device, rows=None, seed=123):
+    """Distance2Pre parameters at C5 scale on the device.  `rows` = the global item rows this rank holds (default all
+    n_item + 1).  Tables U(-0.5, 0.5) like the reference (GRU.py:60, GRU_Spatial.py:57); the GRU / head weights are
+    U(-0.5, 0.5) * 4 / sqrt(d): at d = 512 the reference's unscaled init saturates every gate (pre-activations of order
+    sqrt(d) * 0.15 ~ 3.4 per term), which makes the gradients vanish and the run numerically meaningless; the scaling keeps
+    the recurrence in the regime the d = 128 configuration has with the reference's init (tests use the same scaling)."""
+    import torch
+    rs = np.random.RandomState(seed + 1)
+    sc = 4.0 / np.sqrt(d)
+    u = lambda *shape: torch.from_numpy((rs.uniform(-0.5, 0.5, shape) * sc).astype(np.float32)).to(device)
+    rows = torch.arange(n_item + 1, device=device) if rows is None else rows
+    return dict(lt=hashed_uniform_rows(rows, d, seed, device), ui=u(3, d, 2 * d), wh=u(3, d, d),
+                bi=torch.zeros((3, d), dtype=torch.float32, device=device),
+                di=torch.from_numpy(rs.uniform(-0.5, 0.5, (dist_num + 1, d)).astype(np.float32)).to(device),
+                vs=u(dist_num + 1, d), bs=torch.zeros((dist_num + 1,), dtype=torch.float32, device=device),
+                wd=np.float64(rs.uniform(0, 0.5)), loss_weight=rs.uniform(-0.5, 0.5, 2).astype(np.float32))

@@ -347,7 +347,9 @@ def test_small_batch_simt_path_matches_tensor_core_path(engine, B, d):
                 assert_close([los, sur, upq], [rl, rs_, ru], RTOL, "losses (small=%s)" % small)
             got = state_from_model(m, ["lt", "di", "ui", "wh", "bi", "vs", "bs"])
             for k in got:
-                assert_close(got[k], ref[k], RTOL, "%s (small=%s)" % (k, small))
+                # 16 sequential B = 1 steps at d = 128: an item row's small entries collect alpha * g with g a float32 sum of
+                # 128..256 products (measured 1.5e-4 of such an entry at a 1e-3 floor, 5e-7 of the largest entry)
+                assert_close(got[k], ref[k], RTOL, "%s (small=%s)" % (k, small), floor=1e-2 if d >= 64 else 1e-3)
             outs[small] = got
     finally:
         engine.set_small_batch_path(True)
