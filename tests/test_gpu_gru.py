@@ -349,7 +349,9 @@ def test_small_batch_simt_path_matches_tensor_core_path(engine, B, d):
             for k in got:
                 # 16 sequential B = 1 steps at d = 128: an item row's small entries collect alpha * g with g a float32 sum of
                 # 128..256 products (measured 1.5e-4 of such an entry at a 1e-3 floor, 5e-7 of the largest entry)
-                assert_close(got[k], ref[k], RTOL, "%s (small=%s)" % (k, small), floor=1e-2 if d >= 64 else 1e-3)
+                # (the tensor-core arm adds the 2^-21-per-product error of 3xTF32 on top: measured 1.1e-4 at a 1e-2 floor,
+                # 2.6e-6 of the largest entry -> its small entries are measured against 10 % of the largest)
+                assert_close(got[k], ref[k], RTOL, "%s (small=%s)" % (k, small), floor=(1e-2 if small else 1e-1) if d >= 64 else 1e-3)
             outs[small] = got
     finally:
         engine.set_small_batch_path(True)
