@@ -602,6 +602,8 @@ def main():
     args = ap.parse_args()
     if args.config == "c5" and "--batch" not in " ".join(sys.argv):
         args.batch = 8192 if args.scaling == "strong" else 2048
+    if args.config == "c4" and "--batch" not in " ".join(sys.argv):
+        args.batch = 128
     if args.impl == "reference":
         run_reference(args)
     else:

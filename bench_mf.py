@@ -50,7 +50,10 @@ def _plan(ds, batch, npos, n_steps):
 
 
 def run_reference(args):
-    cfg, ds, st = _workload(args.config, n_user_cap=2048 if args.config == "c4" else None)
+    if args.config == "c4":
+        import bench_geoie
+        return bench_geoie.run_reference(args)
+    cfg, ds, st = _workload(args.config)
     from oracle import models as OM
     import torch
     cores = os.cpu_count() or 1

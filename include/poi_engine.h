@@ -347,6 +347,17 @@ int poi_geoie_train(poi_engine* e, const poi_geoie_params* params, int32_t uidx,
                     const int32_t* msk_host, int32_t n, float alpha, float lambda,
                     double* out_host);
 
+/* K negatives per target, ONE mini-batch step over Bu users (BASELINE.json C4 "GeoIE ... neg=100"; throughput mode,
+ * EXTENSION semantics -- the reference trains one user per call with one negative; mini-batch rule as Bpr, BPR.py:351-397):
+ * every term from pre-update values, g / h / z rows duplicate-summed over the batch, a and b dense SGD, t untouched (its
+ * gradient is exactly zero).  P [Bu x L] POI sequences WITHOUT padding (2 <= L <= 33), Q [Bu x L x K] negatives (position 0
+ * unused), device resident (on_host = 0) or host memory copied inside the call (on_host = 1); coords_dev float
+ * [n_rows x 2] = lat, lon: the pairwise distances the reference's driver precomputes (Load_Data_GeoIE.py:143-156) are
+ * recomputed on the fly.  *loss_host = sum log sigmoid(sp - sq). */
+int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* params, const int32_t* P, const int32_t* Q,
+                            const float* coords_dev, int32_t Bu, int32_t L, int32_t K, int32_t on_host,
+                            float alpha, float lambda, double* loss_host);
+
 /* ---- evaluation helpers (scoring + top-K) ---------------------------- */
 /* scores[b, i] = users[b,:] . items[i,:] (+ wd * prob[b, i] if prob_dev != NULL), then the
  * indices of the top_k largest scores per row in descending order -- the product of

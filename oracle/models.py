@@ -482,3 +482,57 @@ def prme_train_batch_k(state, us, ps, Q, prevs, dists, gaps, alpha, lam, thd, cw
     new["dp"], _ = _unique_rows_update(state["dp"], idx.reshape(-1), -dp.grad.reshape(-1, d_), alpha)
     new["ds"], _ = _unique_rows_update(state["ds"], idx.reshape(-1), -g_ds.reshape(-1, d_), alpha)
     return float(upq.detach()), new
+
+
+def geoie_dist_km(lat1, lon1, lat2, lon2):
+    """`cal_dis` of the GeoIE loader (Load_Data_GeoIE.py:28-42): mean earth diameter 12742 km, (1 - cos)/2 form, float64."""
+    p = 0.017453292519943295
+    a = (lat1 - lat2) * p
+    b = (lon1 - lon2) * p
+    c = (1.0 - np.cos(a)) / 2 + np.cos(lat1 * p) * np.cos(lat2 * p) * (1.0 - np.cos(b)) / 2
+    return 12742 * np.arcsin(np.sqrt(c))
+
+
+def geoie_train_batch_k(state, users, P, Q, coords, alpha, lam, dtype=F64):
+    """GeoIE with K negatives per target, a mini-batch of users (BASELINE.json C4 "GeoIE ... neg=100"; EXTENSION semantics,
+    see the block comment above).  users [Bu]; P [Bu, L] POI sequences without padding; Q [Bu, L, K] negatives (position 0
+    unused); coords [n_item+1, 2] lat/lon.  Per user, target i = 0..L-2 (position i+1), history j <= i
+    (GeoIE.py:155-159 with the driver's triangular mask, Load_Data_GeoIE.py:143-156):
+        s(c)  = sum_{j<=i} (g[p_j] . h[c]) a dist(p_j, c)^b / (i+1)          (the t.z[p] term is the same in sp and sq: it cancels)
+        loss  = sum_i sum_k log sigmoid(s(p_{i+1}) - s(q_{i+1,k}))
+        cost  = -loss + lam/2 (|G|^2 + |Hp|^2 + sum_k |Hq_k|^2 + |Zp|^2 + sum_k |Zq_k|^2)
+    distances recomputed from the coordinates (the reference passes them in as n x n float matrices).  Updates: g, h, z rows
+    duplicate-summed over the batch (GeoIE.py:174-181), a and b dense SGD without L2 (:91,172-173), t untouched (zero
+    gradient).  At K = 1 and one user this is `geoie_train`.  Returns (loss, new_state)."""
+    users = np.asarray(users, dtype=np.int64); P = np.asarray(P, dtype=np.int64); Q = np.asarray(Q, dtype=np.int64)
+    Bu, L = P.shape
+    K = Q.shape[2]
+    n = L - 1
+    co = np.asarray(coords, dtype=np.float64)
+    a = _t(state["a"], F64, True); b = _t(state["b"], F64, True)
+    ig = P[:, :n]                                                        # [Bu, n]      rows of g
+    ih = np.concatenate((P[:, 1:, None], Q[:, 1:, :]), axis=2)          # [Bu, n, K+1] rows of h and z: candidate 0 = the positive
+    G = _t(state["g"][ig], dtype, True)
+    Hc = _t(state["h"][ih], dtype, True)
+    Zc = _t(state["z"][ih], dtype, True)
+    # dist[u, i, c, j] = km between history POI p_j and candidate c of target i
+    lat_h, lon_h = co[ig][..., 0], co[ig][..., 1]                        # [Bu, n]
+    lat_c, lon_c = co[ih][..., 0], co[ih][..., 1]                        # [Bu, n, K+1]
+    dist = geoie_dist_km(lat_h[:, None, None, :], lon_h[:, None, None, :], lat_c[..., None], lon_c[..., None])
+    msk = (np.arange(n)[None, :] <= np.arange(n)[:, None])               # [i, j]
+    mt = _t(msk.astype(np.float64), dtype)[None, :, None, :]
+    dt_ = _t(np.where(msk[None, :, None, :], dist, 1.0), dtype)
+    f_d = a * (dt_ ** b) * mt                                            # GeoIE.py:100-102 on the unmasked entries
+    dots = torch.einsum("ujh,uich->uicj", G, Hc)                         # g[p_j] . h[c]
+    n_h = _t(np.arange(1, n + 1, dtype=np.float64), dtype)[None, :, None]
+    s = (dots * f_d).sum(3) / n_h                                        # [Bu, n, K+1]
+    loss = _logsig(s[:, :, :1] - s[:, :, 1:]).sum()
+    cost = -loss + 0.5 * lam * ((G ** 2).sum() + (Hc ** 2).sum() + (Zc ** 2).sum())
+    cost.backward()
+    H_ = G.shape[2]
+    new = dict(state)
+    new["a"] = np.float64(_np(a - alpha * a.grad)); new["b"] = np.float64(_np(b - alpha * b.grad))
+    new["g"], _ = _unique_rows_update(state["g"], ig.reshape(-1), G.grad.reshape(-1, H_), alpha)
+    new["h"], _ = _unique_rows_update(state["h"], ih.reshape(-1), Hc.grad.reshape(-1, H_), alpha)
+    new["z"], _ = _unique_rows_update(state["z"], ih.reshape(-1), Zc.grad.reshape(-1, H_), alpha)
+    return float(loss.detach()), new

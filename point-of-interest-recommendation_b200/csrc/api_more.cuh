@@ -562,3 +562,64 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
     if (loss_sum_host) *loss_sum_host = e->h_out[0];
     return 0;
 }
+
+// ---- K-negative GeoIE mini-batch (geoie_k.cuh) ------------------------------------------------------
+extern "C" int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* prm, const int32_t* P, const int32_t* Q,
+                                       const float* coords_dev, int32_t Bu, int32_t L, int32_t K, int32_t on_host,
+                                       float alpha, float lambda, double* loss_host) {
+    POI_TRY(begin_call(e));
+    if (!prm || !prm->g || !prm->h || !prm->z || !prm->ab) POI_FAIL(e, "geoie params: null pointer");
+    const int H = prm->H;
+    if (H <= 0 || H % 4 || H > 512) POI_FAIL(e, "n_hidden must be a multiple of 4, <= 512");
+    if (L < 2 || L - 1 > GEO_MAXN) POI_FAIL(e, "sequence length must be in [2, %d] for the mini-batch kernel", GEO_MAXN + 1);
+    if (K < 1 || !coords_dev) POI_FAIL(e, "K >= 1 and a coordinate table are required");
+    if (Bu <= 0) { if (loss_host) *loss_host = 0.0; return 0; }
+    const int n = L - 1, C = K + 1;
+    const int64_t n_occ = (int64_t)Bu * n * C, n_g = (int64_t)Bu * n;
+    if (n_occ >= (int64_t)1 << 31) POI_FAIL(e, "batch too large");
+    GeoBatch gb; gb.Bu = Bu; gb.L = L; gb.K = K; gb.coords = reinterpret_cast<const float2*>(coords_dev);
+    if (on_host) {
+        const void* hs[2] = {P, Q}; size_t bs[2] = {(size_t)Bu * L * 4, (size_t)Bu * L * K * 4}; void* dv[2];
+        POI_TRY(upload_many(e, hs, bs, 2, dv));
+        gb.P = (const int32_t*)dv[0]; gb.Q = (const int32_t*)dv[1];
+    } else { gb.P = P; gb.Q = Q; }
+    uint32_t *keys_h = nullptr, *keys_g = nullptr;
+    POI_TRY(arena_get(e, (size_t)n_occ, &keys_h));
+    POI_TRY(arena_get(e, (size_t)n_g, &keys_g));
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    POI_LAUNCH(e, k_geoie_keys, (unsigned)poi_cdiv(n_occ, 256), 256, 0, gb, keys_h, keys_g);
+    SegList seg_h, seg_g;
+    POI_TRY(build_segments(e, keys_h, n_occ, (uint32_t)prm->n_rows, true, &seg_h));
+    POI_TRY(build_segments(e, keys_g, n_g, (uint32_t)prm->n_rows, true, &seg_g));
+    float *GH = nullptr, *GG = nullptr; double *part = nullptr, *out_dev = nullptr;
+    POI_TRY(arena_get(e, (size_t)n_occ * H, &GH));
+    POI_TRY(arena_get(e, (size_t)n_g * H, &GG));
+    const int blocks = (int)std::min<int64_t>(Bu, (int64_t)e->num_sms * 2);
+    POI_TRY(arena_get(e, (size_t)blocks * 3, &part));
+    POI_TRY(arena_get(e, 1, &out_dev));
+    const size_t smem = geoie_k_smem(H);
+    // algorithmic bytes: per target 1 g row + (h, z) x (1 + K) rows, each read once and written once
+    POI_CAT(e, CAT_GEOIE, 0, (double)Bu * n * (2.0 * (1 + 2 * C) * H * 4 + 4.0 * C));
+    if (H <= 256) {
+        POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        POI_LAUNCH(e, (k_geoie_batch_k<1>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, seg_h.seg_of_occ, seg_h.seg_start,
+                   seg_g.seg_of_occ, seg_g.seg_start, alpha, lambda, GH, GG, part);
+    } else {
+        POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        POI_LAUNCH(e, (k_geoie_batch_k<2>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, seg_h.seg_of_occ, seg_h.seg_start,
+                   seg_g.seg_of_occ, seg_g.seg_start, alpha, lambda, GH, GG, part);
+    }
+    POI_CAT(e, CAT_REDUCE, 0, 0);
+    POI_LAUNCH(e, k_geoie_k_finalize, 1, 32, 0, part, blocks, prm->ab, alpha, out_dev);
+    // rows that occur several times in the batch: duplicate-summed, L2 once per occurrence
+    RowSrc src; memset(&src, 0, sizeof(src));
+    src.mode = SRC_DENSE_GRADS; src.dim = H; src.skip_single = 1;
+    src.grads = GH; POI_TRY(launch_rows_update(e, seg_h, prm->h, H, alpha, lambda, src, ROW_LONG_THRESH));
+    src.grads = nullptr; POI_TRY(launch_rows_update(e, seg_h, prm->z, H, alpha, lambda, src, ROW_LONG_THRESH));   // z: L2 decay only
+    src.grads = GG; POI_TRY(launch_rows_update(e, seg_g, prm->g, H, alpha, lambda, src, ROW_LONG_THRESH));
+    POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    POI_CK(e, cudaStreamSynchronize(e->stream));
+    if (e->kprof) prof_harvest(e);
+    if (loss_host) *loss_host = e->h_out[0];
+    return 0;
+}

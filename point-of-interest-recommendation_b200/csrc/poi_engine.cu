@@ -10,6 +10,7 @@
 #include "mf.cuh"
 #include "geoie.cuh"
 #include "prme_k.cuh"
+#include "geoie_k.cuh"
 #include "peer.cuh"
 #include "sampling.cuh"
 #include "eval.cuh"

@@ -457,6 +457,27 @@ class Engine:
         return float(out.value)
 
     # ---- GeoIE ------------------------------------------------------------------------------
+    def geoie_train_batch_k(self, g, h, z, t, ab, P, Q, coords, alpha, lam) -> float:
+        """One K-negative GeoIE mini-batch step.  P [Bu, L], Q [Bu, L, K]: int32 CUDA tensors (resident) or host arrays /
+        pinned CPU tensors (copied inside the call); coords float32 CUDA [n_rows, 2]."""
+        prm = PoiGeoieParams()
+        prm.g = _dev_f32(g, "g"); prm.h = _dev_f32(h, "h"); prm.z = _dev_f32(z, "z"); prm.t = _dev_f32(t, "t")
+        prm.ab = ab.data_ptr(); prm.n_rows = g.shape[0]; prm.H = g.shape[1]
+        on_dev = isinstance(P, torch.Tensor) and P.is_cuda
+        if on_dev:
+            Bu, L = int(P.shape[0]), int(P.shape[1]); K = int(Q.shape[2])
+            pp, qp = _dev_i32(P, "P"), _dev_i32(Q, "Q")
+            keep = None
+        else:
+            f = lambda x: np.ascontiguousarray(x.numpy() if isinstance(x, torch.Tensor) else x, dtype=np.int32)
+            keep = (f(P), f(Q))
+            Bu, L = keep[0].shape; K = keep[1].shape[2]
+            pp, qp = keep[0].ctypes.data, keep[1].ctypes.data
+        out = c_double()
+        self._ck(lib.poi_geoie_train_batch_k(self._h, byref(prm), pp, qp, _dev_f32(coords, "coords"), Bu, L, K, 0 if on_dev else 1,
+                                             alpha, lam, byref(out)))
+        return float(out.value)
+
     def geoie_train(self, g, h, z, t, ab, uidx, p_row, q_row, dist_pos, dist_neg, msk, alpha, lam) -> float:
         prm = PoiGeoieParams()
         prm.g = _dev_f32(g, "g"); prm.h = _dev_f32(h, "h"); prm.z = _dev_f32(z, "z"); prm.t = _dev_f32(t, "t")

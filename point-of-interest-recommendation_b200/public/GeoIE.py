@@ -92,3 +92,22 @@ class GeoIE:
         return self.engine.geoie_train(self.g.t, self.h.t, self.z.t, self.t.t, self._ab, int(uidx),
                                        self._p_host[int(uidx)], self._q_host[int(uidx)],
                                        dist_pos, dist_neg, msk, self._alpha, self._lambda)
+
+
+class GeoIEBatch(GeoIE):
+    """Mini-batch GeoIE with K negatives per target -- the throughput mode (BASELINE.json C4).  EXTENSION SEMANTICS (the
+    reference trains one user per call with one negative): `train_batch(P, Q)` takes the POI sequences of a batch of users
+    (P [Bu, L], no padding) and K negatives per position (Q [Bu, L, K]), evaluates every term from pre-update values and
+    applies the gradient summed over duplicate occurrences, one step per unique row (Bpr, BPR.py:351-397).  The pairwise
+    distances come from `coords` ([n_item + 1, 2] lat / lon) instead of host-built n x n matrices."""
+
+    def __init__(self, *args, coords=None, **kw):
+        super(GeoIEBatch, self).__init__(*args, **kw)
+        c = np.zeros((self.g.t.shape[0], 2), dtype=np.float32)
+        cc = np.asarray(coords, dtype=np.float32)
+        c[:cc.shape[0]] = cc[:c.shape[0]]
+        self.coords = Shared(c, "float32", self.engine.torch_device)
+
+    def train_batch(self, P, Q):
+        return self.engine.geoie_train_batch_k(self.g.t, self.h.t, self.z.t, self.t.t, self._ab, P, Q, self.coords.t,
+                                               self._alpha, self._lambda)
