@@ -367,6 +367,15 @@ int poi_score_topk(poi_engine* e, const float* users_dev, int32_t B, const float
                    int64_t n_item, int32_t H, const float* prob_dev, float wd,
                    int32_t top_k, int32_t* topk_dev);
 
+/* Distance2Pre scoring + top-K WITHOUT the U x I `prob` / `ulptai` matrices (GRU_Spatial.py:77-78,117-125,
+ * Load_Data_by_length.py:183-235, Valuate.py:133-146): score[b, i] = users[b].items[i] + wd * sts[b, iv] * [iv < dist_num]
+ * where iv = cal_dis interval (Load_Data_by_length.py:24-42, fp64) between user b's last training POI (user_coords
+ * [B x 2] = lat, lon) and item i (item_coords [n_item x 2]) is computed on the fly; sts [B x n_dist_rows] are the
+ * interval distributions `predict` returns. */
+int poi_score_topk_geo(poi_engine* e, const float* users_dev, int32_t B, const float* items_dev, int64_t n_item, int32_t H,
+                       const float* sts_dev, int32_t n_dist_rows, const double* user_coords_dev, const double* item_coords_dev,
+                       double dd, int32_t dist_num, float wd, int32_t top_k, int32_t* topk_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,8 @@ _PROTOS = {
                                 c_void_p, c_void_p, c_int32, c_float, c_float, POINTER(c_double)]),
     "poi_geoie_train_batch_k": (c_int, [_E, POINTER(PoiGeoieParams), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                         c_float, c_float, POINTER(c_double)]),
+    "poi_score_topk_geo": (c_int, [_E, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_double,
+                                   c_int32, c_float, c_int32, c_void_p]),
     "poi_score_topk": (c_int, [_E, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_float, c_int32,
                                c_void_p]),
 }

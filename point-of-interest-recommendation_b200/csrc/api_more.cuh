@@ -307,8 +307,9 @@ int poi_gemm_atb(poi_engine* e, const float* A, int lda, const float* B, int ldb
     return 0;
 }
 
-int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* items, int64_t n_item, int32_t H,
-                   const float* prob, float wd, int32_t top_k, int32_t* topk_dev) {
+static int score_topk_body(poi_engine* e, const float* users, int32_t B, const float* items, int64_t n_item, int32_t H,
+                           const float* prob, const float* sts, int32_t nD, const double* ucoord, const double* icoord,
+                           double dd, int32_t dist_num, float wd, int32_t top_k, int32_t* topk_dev) {
     POI_TRY(begin_call(e));
     if (B <= 0 || n_item <= 0) return 0;
     if (H % 4) POI_FAIL(e, "H must be a multiple of 4");
@@ -323,13 +324,28 @@ int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* it
         POI_CK(e, cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t i0 = 0; i0 < n_item; i0 += chunk) {
         int cur = (int)std::min<int64_t>(chunk, n_item - i0);
-        POI_TRY(launch_gemm_tn(e, users, H, items + (size_t)i0 * H, H, B, cur, H, EpiScore{S, lds, prob, n_item, i0, wd, cur}));
+        // users . items^T on the tensor cores (3xTF32, fp32-faithful) when the shape allows, scores finished in the epilogue
+        if (sts) POI_TRY(gemm_tn(e, users, H, items + (size_t)i0 * H, H, B, cur, H,
+                                 EpiScoreGeo{S, lds, sts, nD, ucoord, icoord, dd, dist_num, i0, wd, cur}));
+        else POI_TRY(gemm_tn(e, users, H, items + (size_t)i0 * H, H, B, cur, H, EpiScore{S, lds, prob, n_item, i0, wd, cur}));
         POI_CAT(e, CAT_EVAL, 0, 0);
         POI_LAUNCH(e, k_topk_merge, B, 256, smem, S, lds, cur, i0, top_k, best_val, topk_dev, i0 == 0 ? 1 : 0);
     }
     POI_CK(e, cudaStreamSynchronize(e->stream));
     if (e->kprof) prof_harvest(e);
     return 0;
+}
+
+int poi_score_topk(poi_engine* e, const float* users, int32_t B, const float* items, int64_t n_item, int32_t H,
+                   const float* prob, float wd, int32_t top_k, int32_t* topk_dev) {
+    return score_topk_body(e, users, B, items, n_item, H, prob, nullptr, 0, nullptr, nullptr, 1.0, 0, wd, top_k, topk_dev);
+}
+
+int poi_score_topk_geo(poi_engine* e, const float* users, int32_t B, const float* items, int64_t n_item, int32_t H,
+                       const float* sts, int32_t n_dist_rows, const double* user_coords, const double* item_coords, double dd,
+                       int32_t dist_num, float wd, int32_t top_k, int32_t* topk_dev) {
+    if (!sts || !user_coords || !item_coords || !(dd > 0) || n_dist_rows <= dist_num - 1) POI_FAIL(e, "poi_score_topk_geo: bad arguments");
+    return score_topk_body(e, users, B, items, n_item, H, nullptr, sts, n_dist_rows, user_coords, item_coords, dd, dist_num, wd, top_k, topk_dev);
 }
 
 }  // extern "C"
@@ -572,7 +588,7 @@ extern "C" int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* pr
     const int H = prm->H;
     if (H <= 0 || H % 4 || H > 512) POI_FAIL(e, "n_hidden must be a multiple of 4, <= 512");
     if (L < 2 || L - 1 > GEO_MAXN) POI_FAIL(e, "sequence length must be in [2, %d] for the mini-batch kernel", GEO_MAXN + 1);
-    if (K < 1 || !coords_dev) POI_FAIL(e, "K >= 1 and a coordinate table are required");
+    if (K < 1 || K > 128 || !coords_dev) POI_FAIL(e, "1 <= K <= 128 and a coordinate table are required");
     if (Bu <= 0) { if (loss_host) *loss_host = 0.0; return 0; }
     const int n = L - 1, C = K + 1;
     const int64_t n_occ = (int64_t)Bu * n * C, n_g = (int64_t)Bu * n;
@@ -591,6 +607,11 @@ extern "C" int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* pr
     SegList seg_h, seg_g;
     POI_TRY(build_segments(e, keys_h, n_occ, (uint32_t)prm->n_rows, true, &seg_h));
     POI_TRY(build_segments(e, keys_g, n_g, (uint32_t)prm->n_rows, true, &seg_g));
+    uint8_t *single_h = nullptr, *single_g = nullptr;
+    POI_TRY(arena_get(e, (size_t)n_occ, &single_h));
+    POI_TRY(arena_get(e, (size_t)n_g, &single_g));
+    POI_LAUNCH(e, k_mark_single, (unsigned)poi_cdiv(n_occ, 256), 256, 0, seg_h, single_h);
+    POI_LAUNCH(e, k_mark_single, (unsigned)poi_cdiv(n_g, 256), 256, 0, seg_g, single_g);
     float *GH = nullptr, *GG = nullptr; double *part = nullptr, *out_dev = nullptr;
     POI_TRY(arena_get(e, (size_t)n_occ * H, &GH));
     POI_TRY(arena_get(e, (size_t)n_g * H, &GG));
@@ -602,12 +623,12 @@ extern "C" int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* pr
     POI_CAT(e, CAT_GEOIE, 0, (double)Bu * n * (2.0 * (1 + 2 * C) * H * 4 + 4.0 * C));
     if (H <= 256) {
         POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        POI_LAUNCH(e, (k_geoie_batch_k<1>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, seg_h.seg_of_occ, seg_h.seg_start,
-                   seg_g.seg_of_occ, seg_g.seg_start, alpha, lambda, GH, GG, part);
+        POI_LAUNCH(e, (k_geoie_batch_k<1>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, single_h, single_g,
+                   alpha, lambda, GH, GG, part);
     } else {
         POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        POI_LAUNCH(e, (k_geoie_batch_k<2>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, seg_h.seg_of_occ, seg_h.seg_start,
-                   seg_g.seg_of_occ, seg_g.seg_start, alpha, lambda, GH, GG, part);
+        POI_LAUNCH(e, (k_geoie_batch_k<2>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, single_h, single_g,
+                   alpha, lambda, GH, GG, part);
     }
     POI_CAT(e, CAT_REDUCE, 0, 0);
     POI_LAUNCH(e, k_geoie_k_finalize, 1, 32, 0, part, blocks, prm->ab, alpha, out_dev);

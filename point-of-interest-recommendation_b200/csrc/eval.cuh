@@ -5,6 +5,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "sampling.cuh"
 
 struct EpiScore {       // S[b, i] = acc + wd * prob[b, i0 + i]
     float* S; int lds; const float* prob; int64_t n_item; int64_t i0; float wd; int N;
@@ -12,6 +13,25 @@ struct EpiScore {       // S[b, i] = acc + wd * prob[b, i0 + i]
         for (int k = 0; k < 4 && n + k < N; ++k) {
             float s = v[k];
             if (prob) s += wd * prob[(size_t)m * n_item + i0 + n + k];
+            S[(size_t)m * lds + n + k] = s;
+        }
+    }
+};
+
+// Distance2Pre scoring without the U x I `prob` / `ulptai` matrices (GRU_Spatial.py:77-78,117-125,
+// Load_Data_by_length.py:183-235): prob[b, i] = sts[b, iv] * [iv < dist_num] with iv = the distance interval between user
+// b's last training POI and item i, computed here from the coordinates (fp64 haversine of cal_dis, the same device
+// function the negative-distance binning uses) instead of being read from a precomputed matrix.
+struct EpiScoreGeo {
+    float* S; int lds; const float* sts; int nD; const double* ucoord; const double* icoord; double dd; int dist_num;
+    int64_t i0; float wd; int N;
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
+        const double ulat = ucoord[2 * (size_t)m], ulon = ucoord[2 * (size_t)m + 1];
+        for (int k = 0; k < 4 && n + k < N; ++k) {
+            const size_t it = (size_t)(i0 + n + k);
+            const int iv = haversine_interval(ulat, ulon, icoord[2 * it], icoord[2 * it + 1], dd, dist_num);
+            float s = v[k];
+            if (iv < dist_num) s += wd * sts[(size_t)m * nD + iv];
             S[(size_t)m * lds + n + k] = s;
         }
     }

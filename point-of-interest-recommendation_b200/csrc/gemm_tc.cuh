@@ -676,7 +676,11 @@ static int launch_gemm_tn_tc(poi_engine* e, const float* A, int lda, const float
         if (split3) return launch_tc_persist<128, true>(e, A, lda, W, ldw, M, N, K, epi, 1, 0);
         return launch_tc_persist<128, false>(e, A, lda, W, ldw, M, N, K, epi, 1, 0);
     }
-    const bool wide = tiles128 >= e->num_sms;
+    // fewer tiles than two waves of 128-wide ones: take the width with fewer waves (a 64-wide tile costs ~0.8 of a 128-wide
+    // one: same MMA instruction count, half the W staging and epilogue)
+    const int64_t tiles64 = poi_cdiv(M, tc::BM) * poi_cdiv(N, 64);
+    const double cost128 = (double)poi_cdiv(tiles128, e->num_sms), cost64 = 0.8 * (double)poi_cdiv(tiles64, e->num_sms);
+    const bool wide = cost128 <= cost64;
     if (split3) {
         if (wide) return launch_tc_inst<128, true>(e, A, lda, W, ldw, M, N, K, epi);
         return launch_tc_inst<64, true>(e, A, lda, W, ldw, M, N, K, epi);

@@ -80,18 +80,20 @@ __device__ __forceinline__ void geo_weight(bool on, float hlat, float hlon, floa
 template <int NCOL>          // columns per thread: H <= 256 * NCOL
 __global__ void __launch_bounds__(256, NCOL == 1 ? 2 : 1)
 k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int H, GeoBatch gb,
-                const uint32_t* __restrict__ slot_h, const uint32_t* __restrict__ segstart_h,
-                const uint32_t* __restrict__ slot_g, const uint32_t* __restrict__ segstart_g,
+                const uint8_t* __restrict__ single_h, const uint8_t* __restrict__ single_g,
                 float alpha, float lambda, float* __restrict__ GH, float* __restrict__ GG,
                 double* __restrict__ part /* [grid][3]: loss, d/da, d/db */) {
     extern __shared__ __align__(16) float geo_sm[];
     const int n = gb.L - 1, K = gb.K, C = K + 1, HS = H + 4;
     float* Gs = geo_sm;                                   // [n][HS]
-    float* Ht = Gs + (size_t)GEO_MAXN * HS;               // [GEO_TILE][H]  candidate rows of the tile
-    float* Hp = Ht + (size_t)GEO_TILE * H;                // [H]            the positive's row
+    float* Ht2 = Gs + (size_t)GEO_MAXN * HS;              // [2][GEO_TILE][H] candidate rows: the tile in use + the one streaming in (cp.async)
+    float* Hp = Ht2 + (size_t)2 * GEO_TILE * H;           // [H]            the positive's row
     float* coef = Hp + H;                                 // [GEO_TILE][32] eps_c w_jc
     float* wP = coef + GEO_TILE * 32;                     // [32]           w_jp of the positive
     float* sc = wP + 32;                                  // [16] scalars: 0 s_p, 1 A_p, 2 B_p, 3 E ; [8..15] per-warp E partials
+    __shared__ int32_t sq[128];                           // the target's K negatives (row ids), staged once per target
+    __shared__ int32_t sx[GEO_TILE];                      // row ids of the tile's candidates
+    __shared__ uint8_t sfl[GEO_TILE];                     // 1 = the row occurs once in the batch (update in place)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float a = (float)ab[0], b = (float)ab[1];
     double loss_acc = 0.0, ga_acc = 0.0, gb_acc = 0.0;    // meaningful in lane 0 of each warp
@@ -118,6 +120,25 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
             const float inv = 1.0f / (float)(i + 1);
             const bool on = lane <= i;
             const size_t occ0 = ((size_t)u * n + i) * C;                 // occurrence id of the positive of this target
+            const int32_t* Qi = gb.Q + ((size_t)u * gb.L + i + 1) * K;
+            for (int k = tid; k < K; k += 256) sq[k] = Qi[k];
+            // this warp's rows of tile `t0` -> buffer `bf`, asynchronously (16 B per lane and request)
+            auto prefetch = [&](int t0, int bf) {
+                float* hb = Ht2 + ((size_t)bf * GEO_TILE + 2 * warp) * H;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int k = t0 + 2 * warp + r;
+                    if (k < K) {
+                        const float* src = h + (size_t)Qi[k] * H;
+                        for (int c4 = lane; c4 < (H >> 2); c4 += 32)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(hb + (size_t)r * H + 4 * c4)), "l"(src + 4 * c4) : "memory");
+                    } else {
+                        for (int c4 = lane; c4 < (H >> 2); c4 += 32) *reinterpret_cast<float4*>(hb + (size_t)r * H + 4 * c4) = f4zero();
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            prefetch(0, 0);
             // ---- the positive: warp 0 scores it; its row stays in Hp until the target's negatives are done ----
             if (warp == 0) {
                 const int32_t x = Pu[i + 1];
@@ -136,17 +157,15 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
             const float s_p = sc[0];
             float E_w = 0.f;                                              // this warp's sum of eps over its negatives
             // ---- negatives, GEO_TILE per pass ----
-            for (int t0 = 0; t0 < K; t0 += GEO_TILE) {
+            for (int t0 = 0, bf = 0; t0 < K; t0 += GEO_TILE, bf ^= 1) {
                 const int k0 = t0 + 2 * warp, k1 = k0 + 1;               // this warp's two candidates (negative numbers)
                 const bool v0 = k0 < K, v1 = k1 < K;
-                const int32_t* Qi = gb.Q + ((size_t)u * gb.L + i + 1) * K;
-                const int32_t x0 = v0 ? Qi[k0] : 0, x1 = v1 ? Qi[k1] : 0;
+                const int32_t x0 = v0 ? sq[k0] : 0, x1 = v1 ? sq[k1] : 0;
+                float* Ht = Ht2 + (size_t)bf * GEO_TILE * H;
                 float* h0 = Ht + (size_t)(2 * warp) * H; float* h1 = h0 + H;
-                for (int c4 = lane; c4 < (H >> 2); c4 += 32) {
-                    *reinterpret_cast<float4*>(h0 + 4 * c4) = v0 ? ld4(h + (size_t)x0 * H + 4 * c4) : f4zero();
-                    *reinterpret_cast<float4*>(h1 + 4 * c4) = v1 ? ld4(h + (size_t)x1 * H + 4 * c4) : f4zero();
-                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");       // this warp's two rows of the tile have landed
                 __syncwarp();
+                if (t0 + GEO_TILE < K) prefetch(t0 + GEO_TILE, bf ^ 1);     // next tile streams in behind the compute
                 float d0, d1;
                 geo_dots2(Gs, HS, H, lane, h0, h1, d0, d1);
                 float pw0, pwl0, pw1, pwl1;
@@ -159,6 +178,10 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
                 const float xk0 = s_p - s0, xk1 = s_p - s1;
                 const float e0 = v0 ? sigmoidf_(-xk0) : 0.f, e1 = v1 ? sigmoidf_(-xk1) : 0.f;   // d cost / d s(q_k)
                 coef[(2 * warp) * 32 + lane] = e0 * w0; coef[(2 * warp + 1) * 32 + lane] = e1 * w1;
+                if (lane == 0) {
+                    sx[2 * warp] = x0; sx[2 * warp + 1] = x1;
+                    sfl[2 * warp] = v0 ? single_h[occ0 + 1 + k0] : 0; sfl[2 * warp + 1] = v1 ? single_h[occ0 + 1 + k1] : 0;
+                }
                 E_w += e0 + e1;
                 if (lane == 0) {
                     if (v0) loss_acc += (double)logsigmoidf_(xk0);
@@ -185,9 +208,8 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
                                 dG[q][4 * j4 + 3] = fmaf(cf.w, hv, dG[q][4 * j4 + 3]); dh = fmaf(cf.w, Gcol[q][4 * j4 + 3], dh);
                             }
                             const size_t o = occ0 + 1 + t0 + cw;
-                            const uint32_t sl = slot_h[o];
-                            const size_t x = (size_t)Qi[t0 + cw];
-                            if (segstart_h[sl + 1] - segstart_h[sl] == 1u) {
+                            const size_t x = (size_t)sx[cw];
+                            if (sfl[cw]) {
                                 h[x * H + col] = hv - alpha * (dh + lambda * hv);
                                 const float zv = z[x * H + col];
                                 z[x * H + col] = zv - alpha * (lambda * zv);
@@ -204,8 +226,7 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
             for (int ww = 0; ww < 8; ++ww) E += sc[8 + ww];               // warp order: fixed
             if (tid == 0) { ga_acc -= (double)(E * sc[1]); gb_acc -= (double)(E * sc[2]); }
             {
-                const uint32_t sl = slot_h[occ0];
-                const bool single = segstart_h[sl + 1] - segstart_h[sl] == 1u;
+                const bool single = single_h[occ0] != 0;
                 const size_t x = (size_t)Pu[i + 1];
 #pragma unroll
                 for (int q = 0; q < NCOL; ++q) {
@@ -237,8 +258,7 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
                 for (int j = 0; j < GEO_MAXN; ++j) {
                     if (j < n) {
                         const size_t og = (size_t)u * n + j;
-                        const uint32_t sl = slot_g[og];
-                        if (segstart_g[sl + 1] - segstart_g[sl] == 1u)
+                        if (single_g[og])
                             g[(size_t)Pu[j] * H + col] = Gcol[q][j] - alpha * (dG[q][j] + lambda * Gcol[q][j]);
                         else GG[og * H + col] = dG[q][j];
                     }
@@ -252,8 +272,16 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
     if (tid < 3) { double t = 0.0; for (int ww = 0; ww < 8; ++ww) t += sred[ww][tid]; part[(size_t)blockIdx.x * 3 + tid] = t; }
 }
 
+// single[o] = 1 iff occurrence o is the only one of its row in the batch
+__global__ void k_mark_single(SegList seg, uint8_t* __restrict__ single) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= seg.n) return;
+    const uint32_t sl = seg.seg_of_occ[q];
+    single[q] = seg.seg_start[sl + 1] - seg.seg_start[sl] == 1u ? 1 : 0;
+}
+
 static size_t geoie_k_smem(int H) {
-    return ((size_t)GEO_MAXN * (H + 4) + (size_t)GEO_TILE * H + H + GEO_TILE * 32 + 32 + 16) * sizeof(float);
+    return ((size_t)GEO_MAXN * (H + 4) + (size_t)2 * GEO_TILE * H + H + GEO_TILE * 32 + 32 + 16) * sizeof(float);
 }
 
 // a, b <- a, b - alpha * (sum over CTAs of the partials), loss out; fixed order

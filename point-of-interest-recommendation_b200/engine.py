@@ -495,6 +495,17 @@ class Engine:
         return out.value
 
     # ---- evaluation -------------------------------------------------------------------------
+    def score_topk_geo(self, users, items, top_k, sts, user_coords, item_coords, dd, dist_num, wd):
+        """Distance2Pre scores + top-K with the interval probabilities looked up on the fly (no U x I matrices)."""
+        B = users.shape[0]
+        out = torch.empty((B, top_k), dtype=torch.int32, device=users.device)
+        if user_coords.dtype != torch.float64 or item_coords.dtype != torch.float64:
+            raise EngineError("coordinates must be float64")
+        self._ck(lib.poi_score_topk_geo(self._h, _dev_f32(users, "users"), B, _dev_f32(items, "items"), items.shape[0], items.shape[1],
+                                        _dev_f32(sts, "sts"), sts.shape[1], user_coords.contiguous().data_ptr(),
+                                        item_coords.contiguous().data_ptr(), float(dd), int(dist_num), float(wd), int(top_k), out.data_ptr()))
+        return out
+
     def score_topk(self, users, items, top_k, prob=None, wd=0.0):
         B = users.shape[0]
         out = torch.empty((B, top_k), dtype=torch.int32, device=users.device)

@@ -74,7 +74,16 @@ class Params(object):
         self.tra_buys_masks, self.tra_masks, self.tra_buys_neg_masks = tra_buys_masks, tra_masks, tra_buys_neg_masks
         self.tes_buys_masks, self.tes_masks, self.tes_buys_neg_masks = tes_buys_masks, tes_masks, tes_buys_neg_masks
         self.tra_dist_masks, self.tes_dist_masks, self.tra_dist_neg_masks = tra_dist_masks, tes_dist_masks, tra_dist_neg_masks
-        self.ulptai = fun_compute_distance(tra_buys_masks, tra_masks, pois_cordis, p['dd'], dist_num)
+        self._ulptai = None
+
+    @property
+    def ulptai(self):
+        """n_user x n_item interval table between each user's last training POI and every POI (the reference builds it in
+        `Params`, prog_bpr_gru_spatial.py:90).  Built on first use only: the default evaluation path (p['gpu_topk'] = 1) looks
+        the intervals up on the device from the coordinates and never needs it."""
+        if self._ulptai is None:
+            self._ulptai = fun_compute_distance(self.tra_buys_masks, self.tra_masks, self.pois_cordis, self.p['dd'], self.dist_num)
+        return self._ulptai
 
     def build_model_one_by_one(self, flag=0, init=None, device=None):
         print('Building the model one_by_one ...')
@@ -163,7 +172,10 @@ def compute_user_representations(p, model, starts_ends_tes, ulptai, dist_num):
         outs = [model.predict(se) for se in starts_ends_tes]
         all_hus = np.concatenate([o[0] for o in outs]); all_sus = np.concatenate([o[1] for o in outs])
         model.update_trained_users(all_hus)
-        model.update_prob(fun_acquire_prob(all_sus, ulptai, dist_num))
+        if p.get('gpu_topk', 1):
+            model.update_sts(all_sus)                  # fused scoring: intervals looked up on the fly, no U x I matrices
+        else:
+            model.update_prob(fun_acquire_prob(all_sus, ulptai() if callable(ulptai) else ulptai, dist_num))
 
 
 def train_valid_or_test(pas, init=None, device=None):
@@ -176,7 +188,10 @@ def train_valid_or_test(pas, init=None, device=None):
     user_num, item_num, dist_num = pas.user_num, pas.item_num, pas.dist_num
     tra_buys_masks, tra_masks, tra_buys_neg_masks = pas.tra_buys_masks, pas.tra_masks, pas.tra_buys_neg_masks
     tes_buys_masks, tes_masks = pas.tes_buys_masks, pas.tes_masks
-    dd, pois_cordis, ulptai = p['dd'], pas.pois_cordis, pas.ulptai
+    dd, pois_cordis = p['dd'], pas.pois_cordis
+    ulptai = lambda: pas.ulptai                          # only the host scoring path (p['gpu_topk'] = 0) evaluates it
+    if 2 == p['gru'] and p.get('gpu_topk', 1):
+        model.set_eval_geometry(pois_cordis, dd, dist_num)
 
     ini_epoch = 0
     if 2 == p['gru'] and p['load_epoch'] != 0:

@@ -39,6 +39,8 @@ class OboSpatialGru(GruBasic):
         # the reference allocates a dense n_user x n_item `prob` up front (GRU_Spatial.py:77-78); here it
         # is allocated when update_prob() supplies it
         self.prob = None
+        self._sts = None                 # interval distributions of every user (update_sts), for the fused scoring path
+        self._icoords = None             # item coordinates etc. (set_eval_geometry)
         self.params = [self.ui, self.wh, self.bi, self.vs, self.bs, self.wd, self.loss_weight]
         self.l2 = L2Expr(self.engine,
                          lambda: [self.lt.t, self.di.t, self.ui.t, self.wh.t, self.bi.t, self.vs.t, self.bs.t, self._scal.t],
@@ -67,6 +69,24 @@ class OboSpatialGru(GruBasic):
     def update_prob(self, prob):
         self.prob = Shared(np.asarray(prob, dtype=np.float32), "float32", self.engine.torch_device)
 
+    def update_sts(self, all_sus):
+        """Keep the users' interval distributions [n_user x (n_dist + 1)] (the `sts` output of `predict`) on the device: with
+        `set_eval_geometry` they replace the dense n_user x n_item `prob` matrix (GRU_Spatial.py:77-78,114-115) in scoring."""
+        self._sts = Shared(np.asarray(all_sus, dtype=np.float32), "float32", self.engine.torch_device)
+
+    def set_eval_geometry(self, pois_cordis, dd_m, dist_num):
+        """Coordinates of every POI (lat, lon) and the interval width in metres: lets `compute_sub_topk` look the interval
+        between a user's last training POI and every candidate up on the fly (the reference builds the n_user x n_item
+        table `ulptai` on the host, Load_Data_by_length.py:183-215)."""
+        dev = self.engine.torch_device
+        c = np.zeros((self.n_item + 1, 2), dtype=np.float64)
+        cc = np.asarray(pois_cordis, dtype=np.float64)
+        c[:min(len(cc), self.n_item)] = cc[:self.n_item]
+        self._icoords = torch.from_numpy(c).to(dev)
+        last = self.tra_buys_masks.t[torch.arange(self.n_user, device=dev), (self._lens - 1).long()].long()
+        self._ucoords = self._icoords[last].contiguous()
+        self._dd_m, self._dist_num = float(dd_m), int(dist_num)
+
     def compute_sub_all_scores(self, start_end):
         """users . items^T + wd * prob, raw trained wd (GRU_Spatial.py:117-125)."""
         se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
@@ -79,8 +99,12 @@ class OboSpatialGru(GruBasic):
         """Fused device scoring + top-K with the `wd * prob` term (GRU_Spatial.py:117-125)."""
         se = torch.as_tensor(np.asarray(start_end), dtype=torch.long, device=self.engine.torch_device)
         users = self.trained_users.t[se].contiguous()
-        prob = self.prob.t[se].contiguous() if self.prob is not None else None
         wd = float(self._scal.t[0].item())
+        if self._sts is not None and self._icoords is not None:
+            # fused path: no n_user x n_item matrix exists; intervals from the coordinates inside the GEMM epilogue
+            return self.engine.score_topk_geo(users, self.trained_items.t[:-1], top_k, self._sts.t[se].contiguous(),
+                                              self._ucoords[se].contiguous(), self._icoords, self._dd_m, self._dist_num, wd).cpu().numpy()
+        prob = self.prob.t[se].contiguous() if self.prob is not None else None
         return self.engine.score_topk(users, self.trained_items.t[:-1], top_k, prob, wd).cpu().numpy()
 
     def _params(self, trained=False):

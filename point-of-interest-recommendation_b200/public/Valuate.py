@@ -97,7 +97,8 @@ def fun_predict_auc_recall_map_ndcg(p, model, best, epoch, starts_ends_auc, star
     # ---- top-K ranks ------------------------------------------------------------------------
     at_nums = p['at_nums']
     top_k = at_nums[-1]
-    use_gpu_topk = bool(p.get('gpu_topk', 0)) and hasattr(model, 'compute_sub_topk')
+    # scoring + top-K fused on the device is the default (p['gpu_topk'] = 0 restores the host argpartition path)
+    use_gpu_topk = bool(p.get('gpu_topk', 1)) and hasattr(model, 'compute_sub_topk')
     ranks = []
     for se in starts_ends_tes:
         if use_gpu_topk:

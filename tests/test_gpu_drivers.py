@@ -258,8 +258,9 @@ def test_checkpoint_roundtrip(engine, tmp_path):
 
 
 def test_gpu_topk_gives_same_recall(engine, tmp_path):
-    """p['gpu_topk'] = 1 routes Valuate's ranking through the fused score + top-K kernel; the metrics
-    must equal the host argpartition path."""
+    """Valuate's ranking through the fused score + top-K kernel (the default, p['gpu_topk'] = 1: Distance2Pre looks the
+    distance intervals up from the coordinates inside the GEMM epilogue, no n_user x n_item `prob` / `ulptai`) must give
+    the same metrics as the reference's host path (p['gpu_topk'] = 0: dense prob matrix + argpartition)."""
     from poi_b200 import prog_bpr_gru_spatial as drv
     from poi_b200.public.Global_Best import GlobalBest
     from poi_b200.public.Valuate import fun_predict_auc_recall_map_ndcg
@@ -271,10 +272,52 @@ def test_gpu_topk_gives_same_recall(engine, tmp_path):
     for u in range(pas.user_num):
         model.train(u)
     _, ses = pas.compute_start_end('test'); _, ses_auc = pas.compute_start_end('test_auc')
-    drv.compute_user_representations(p, model, ses, pas.ulptai, pas.dist_num)
+    model.set_eval_geometry(pas.pois_cordis, p['dd'], pas.dist_num)
     res = {}
     for flag in (0, 1):
         p['gpu_topk'] = flag
+        drv.compute_user_representations(p, model, ses, pas.ulptai, pas.dist_num)
         res[flag] = fun_predict_auc_recall_map_ndcg(p, model, GlobalBest(p['at_nums']), 0, ses_auc, ses, pas.tes_buys_masks, pas.tes_masks)
+    assert model.prob is not None and model._sts is not None
     for k in ("recall", "map", "ndcg"):
         assert np.allclose(res[0][k], res[1][k], atol=1e-12), k
+
+
+def test_fused_scoring_at_one_million_items(engine):
+    """poi_score_topk_geo at |POI| = 1M: top-20 of users . items^T + wd * sts[interval(last POI, item)] with the intervals
+    computed on the fly, against a chunked float64 host evaluation of the reference's formula (GRU_Spatial.py:117-125 with
+    Load_Data_by_length.py:24-42,218-235).  Items whose scores are within 1e-5 of the 20th may swap; Recall@20 against a
+    planted test item must be identical."""
+    import torch
+    from poi_b200.public.Load_Data_by_length import cal_dis_np
+    rs = np.random.RandomState(21)
+    B, H, I, D, dd = 48, 32, 1000000, 200, 200.0
+    users = rs.uniform(-0.5, 0.5, (B, H)).astype(np.float32); items = rs.uniform(-0.5, 0.5, (I, H)).astype(np.float32)
+    sts = rs.dirichlet(np.ones(D + 1), size=B).astype(np.float32)
+    ic = np.stack([rs.uniform(1.22, 1.47, I), rs.uniform(103.60, 104.04, I)], axis=1)
+    uc = ic[rs.randint(0, I, B)]
+    wd = 37.5
+    dev = engine.torch_device
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    got = engine.score_topk_geo(t(users, torch.float32), t(items, torch.float32), 20, t(sts, torch.float32), t(uc, torch.float64),
+                                t(ic, torch.float64), dd, D, wd).cpu().numpy()
+    top = np.empty((B, 20), dtype=np.int64); kth = np.empty(B); sc_got = np.empty((B, 20))
+    best_v = np.full((B, 40), -np.inf); best_i = np.zeros((B, 40), dtype=np.int64)
+    for s in range(0, I, 100000):
+        e = min(I, s + 100000)
+        sc = users.astype(np.float64) @ items[s:e].astype(np.float64).T
+        iv = cal_dis_np(uc[:, 0:1], uc[:, 1:2], ic[None, s:e, 0], ic[None, s:e, 1], dd, D)
+        sc += wd * np.take_along_axis(sts.astype(np.float64), iv, axis=1) * (iv < D)
+        allv = np.concatenate((best_v, sc), axis=1); alli = np.concatenate((best_i, np.broadcast_to(np.arange(s, e), sc.shape)), axis=1)
+        sel = np.argsort(-allv, axis=1, kind="stable")[:, :40]
+        best_v = np.take_along_axis(allv, sel, axis=1); best_i = np.take_along_axis(alli, sel, axis=1)
+        for b in range(B):
+            m = (got[b] >= s) & (got[b] < e)
+            sc_got[b, m] = sc[b, got[b][m] - s]
+    for b in range(B):
+        assert len(set(got[b].tolist())) == 20
+        # every returned item scores at least the true 20th best (up to float32 rounding), in descending order
+        assert np.all(sc_got[b] >= best_v[b, 19] - 1e-5), b
+        assert np.all(np.diff(sc_got[b]) <= 1e-5), b
+        clear = best_v[b, :20] > best_v[b, 20] + 1e-5               # unambiguous members of the top 20
+        assert set(best_i[b, :20][clear].tolist()) <= set(got[b].tolist()), b
