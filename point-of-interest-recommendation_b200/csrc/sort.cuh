@@ -60,11 +60,43 @@ __global__ void k_scan_add(uint32_t* out, const uint32_t* block_off, int64_t n) 
     if (idx < n) out[idx] += block_off[idx / SCAN_TILE];
 }
 
+// up to SCAN_SINGLE_MAX elements in ONE launch: thread t owns the contiguous run [t * ipt, (t + 1) * ipt), sums it, the
+// 1024 run totals are scanned in the block, the run is rewritten with its exclusive prefixes (out may alias in)
+constexpr int SCAN_SINGLE_MAX = 65536;
+__global__ void __launch_bounds__(1024)
+k_scan_single(const uint32_t* in, uint32_t* out, int n, uint32_t* total_out) {
+    __shared__ uint32_t warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ipt = (n + 1023) / 1024;
+    const int b0 = tid * ipt, b1 = min(b0 + ipt, n);
+    uint32_t sum = 0;
+    for (int i = b0; i < b1; ++i) sum += in[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t s2 = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += s2; }
+        warp_tot[lane] = ti - t;
+        if (lane == 31 && total_out) *total_out = ti;
+    }
+    __syncthreads();
+    uint32_t excl = warp_tot[wid] + inc - sum;
+    for (int i = b0; i < b1; ++i) { const uint32_t v = in[i]; out[i] = excl; excl += v; }
+}
+
 // out may alias in.  total_dev (optional) receives the sum of all elements.
 static int exclusive_scan_u32(poi_engine* e, const uint32_t* in, uint32_t* out, int64_t n,
                               uint32_t* total_dev) {
     if (n <= 0) {
         if (total_dev) POI_CK(e, cudaMemsetAsync(total_dev, 0, 4, e->stream));
+        return 0;
+    }
+    if (n <= SCAN_SINGLE_MAX) {
+        POI_LAUNCH(e, k_scan_single, 1, 1024, 0, in, out, (int)n, total_dev);
         return 0;
     }
     int64_t nb = poi_cdiv(n, SCAN_TILE);
@@ -253,6 +285,55 @@ __global__ void k_seg_write(const uint32_t* keys, const uint32_t* vals, const ui
     if (i == n - 1) { uint32_t nu = sid + 1u; *n_unique = nu; seg_start[nu] = (uint32_t)n; }
 }
 
+// Segment heads and ranks in two kernels instead of flags -> 3-launch scan -> write: k_seg_rank_block scans the head flags
+// (computed from the sorted keys on the fly) inside each SCAN_TILE block and leaves the block totals; after the block
+// totals are scanned (one launch), k_seg_write2 adds the block offset while it writes the segment arrays.
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_seg_rank_block(const uint32_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ excl, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+    uint32_t prev = base > 0 && base - 1 < n ? keys[base - 1] : 0u;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const int64_t idx = base + i;
+        uint32_t k = idx < n ? keys[idx] : 0u;
+        v[i] = idx < n && (idx == 0 || k != prev) ? 1u : 0u;
+        prev = k;
+        sum += v[i];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0u, ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t s2 = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += s2; }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t;
+        if (lane == SCAN_THREADS / 32 - 1) block_sums[blockIdx.x] = ti;
+    }
+    __syncthreads();
+    uint32_t ex = warp_tot[wid] + inc - sum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { const int64_t idx = base + i; if (idx < n) excl[idx] = ex; ex += v[i]; }
+}
+
+__global__ void k_seg_write2(const uint32_t* keys, const uint32_t* vals, const uint32_t* excl, const uint32_t* block_off, int64_t n,
+                             uint32_t* seg_start, uint32_t* uniq, uint32_t* n_unique, uint32_t* seg_of_occ) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool head = (i == 0 || keys[i] != keys[i - 1]);
+    const uint32_t ex = excl[i] + block_off[i / SCAN_TILE];
+    const uint32_t sid = head ? ex : ex - 1u;
+    if (head) { seg_start[sid] = (uint32_t)i; uniq[sid] = keys[i]; }
+    if (seg_of_occ) seg_of_occ[vals[i]] = sid;
+    if (i == n - 1) { uint32_t nu = sid + 1u; *n_unique = nu; seg_start[nu] = (uint32_t)n; }
+}
+
 static int build_segments(poi_engine* e, const uint32_t* keys_dev, int64_t n, uint32_t bound,
                           bool want_inverse, SegList* out) {
     out->n = n;
@@ -268,9 +349,12 @@ static int build_segments(poi_engine* e, const uint32_t* keys_dev, int64_t n, ui
     if (want_inverse) POI_TRY(arena_get(e, nn, &out->seg_of_occ));
     if (n <= 0) { POI_CK(e, cudaMemsetAsync(out->n_unique, 0, 4, e->stream)); return 0; }
     unsigned g = (unsigned)poi_cdiv(n, 256);
-    POI_LAUNCH(e, k_seg_flags, g, 256, 0, out->keys, n, excl);
-    POI_TRY(exclusive_scan_u32(e, excl, excl, n, nullptr));
-    POI_LAUNCH(e, k_seg_write, g, 256, 0, out->keys, out->vals, excl, n, out->seg_start, out->uniq,
+    const int64_t nb = poi_cdiv(n, SCAN_TILE);
+    uint32_t* bs = nullptr;
+    POI_TRY(arena_get(e, (size_t)nb + 1, &bs));
+    POI_LAUNCH(e, k_seg_rank_block, (unsigned)nb, SCAN_THREADS, 0, out->keys, n, excl, bs);
+    POI_TRY(exclusive_scan_u32(e, bs, bs, nb, nullptr));
+    POI_LAUNCH(e, k_seg_write2, g, 256, 0, out->keys, out->vals, excl, bs, n, out->seg_start, out->uniq,
                out->n_unique, out->seg_of_occ);
     return 0;
 }
