@@ -54,7 +54,9 @@ struct poi_engine {
     void* prep_state = nullptr;      // MgPrep*, owned
     // CUDA-graph replay of small-batch train calls (the reference's one-by-one mode): one instantiated graph per
     // (parameter pointers, batch size, max length, modes); valid while the arena has not been re-allocated
-    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0; int warm = 0; int64_t n_launch = 0; };
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0; int warm = 0; int64_t n_launch = 0;
+                        std::vector<uint64_t> key; uint64_t last_use = 0; };
+    uint64_t graph_clock = 0;
     std::unordered_map<uint64_t, GraphEntry> graphs;
     cudaStream_t cap_stream = nullptr;
     bool capturing = false;

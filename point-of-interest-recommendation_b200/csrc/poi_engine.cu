@@ -203,13 +203,31 @@ int poi_gru_train(poi_engine* e, const poi_gru_params* p, const poi_seq_index* i
     const bool graphable = e->graph_mode && B <= 8 && !e->kprof && !e->timing;
     if (!graphable) return gru_train_body(e, p, index, uidx_host, B, max_len, alpha, lambda, out_host);
 
-    uint64_t key = 1469598103934665603ull;
-    key = fnv1a(key, p, sizeof(*p)); key = fnv1a(key, index, sizeof(*index));
-    const int32_t modes[6] = {B, max_len, e->gemm_mode, (int32_t)e->fuse_recurrence | ((int32_t)e->persistent_gemm << 1) | ((int32_t)e->wgrad_mn << 2) | ((int32_t)e->small_batch_path << 3),
-                              e->fused_cluster, 0};
-    key = fnv1a(key, modes, sizeof(modes)); key = fnv1a(key, &alpha, 4); key = fnv1a(key, &lambda, 4);
-    const void* strm = e->stream; key = fnv1a(key, &strm, sizeof(strm));
+    // cache key = every field the captured launches depend on, listed explicitly (no struct padding), stored in the entry
+    // and compared on lookup: a 64-bit hash collision can not replay a graph built for other pointers or another T
+    std::vector<uint64_t> kv = {(uint64_t)(uintptr_t)p->lt, (uint64_t)p->n_rows_lt, (uint64_t)p->d, (uint64_t)p->H, (uint64_t)(uintptr_t)p->ui,
+                                (uint64_t)(uintptr_t)p->wh, (uint64_t)(uintptr_t)p->bi, (uint64_t)(uintptr_t)p->di, (uint64_t)p->n_rows_di,
+                                (uint64_t)(uintptr_t)p->vs, (uint64_t)(uintptr_t)p->bs, (uint64_t)(uintptr_t)p->scal,
+                                (uint64_t)(uintptr_t)index->p, (uint64_t)(uintptr_t)index->q, (uint64_t)(uintptr_t)index->dp,
+                                (uint64_t)(uintptr_t)index->dq, (uint64_t)(uintptr_t)index->lens, (uint64_t)index->lmax, (uint64_t)index->n_user,
+                                (uint64_t)B, (uint64_t)max_len, (uint64_t)e->gemm_mode,
+                                (uint64_t)((int)e->fuse_recurrence | ((int)e->persistent_gemm << 1) | ((int)e->wgrad_mn << 2) | ((int)e->small_batch_path << 3)),
+                                (uint64_t)e->fused_cluster, 0, 0, (uint64_t)(uintptr_t)e->stream};
+    memcpy(&kv[24], &alpha, 4); memcpy(&kv[25], &lambda, 4);
+    uint64_t key = fnv1a(1469598103934665603ull, kv.data(), kv.size() * sizeof(uint64_t));
+    {
+        auto it = e->graphs.find(key);
+        while (it != e->graphs.end() && !it->second.key.empty() && it->second.key != kv) it = e->graphs.find(++key);   // collision: probe
+    }
+    if (e->graphs.size() >= 128 && e->graphs.find(key) == e->graphs.end()) {      // bounded: drop the least recently used entry
+        auto lru = e->graphs.begin();
+        for (auto it = e->graphs.begin(); it != e->graphs.end(); ++it) if (it->second.last_use < lru->second.last_use) lru = it;
+        if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+        e->graphs.erase(lru);
+    }
     poi_engine::GraphEntry& ge = e->graphs[key];
+    if (ge.key.empty()) ge.key = kv;
+    ge.last_use = ++e->graph_clock;
     auto finish = [&]() -> int {
         POI_CK(e, cudaStreamSynchronize(e->stream));
         if (out_host) for (int i = 0; i < 5; ++i) out_host[i] = e->h_out[i];

@@ -61,10 +61,11 @@ k_sample_negatives(const int32_t* __restrict__ rows, int lrow, const int32_t* __
 __device__ __forceinline__ int haversine_interval(double lat1, double lon1, double lat2, double lon2, double dd, int dist_num) {
     const double d = 12742.0, p = 0.017453292519943295;
     const double a = (lat1 - lat2) * p, b = (lon1 - lon2) * p;
-    const double c = (1.0 - cos(a)) / 2 + cos(lat1 * p) * cos(lat2 * p) * (1.0 - cos(b)) / 2;
+    double c = (1.0 - cos(a)) / 2 + cos(lat1 * p) * cos(lat2 * p) * (1.0 - cos(b)) / 2;
+    c = c < 0.0 ? 0.0 : (c > 1.0 ? 1.0 : c);       // rounding outside [0, 1] would make asin NaN and the interval id negative
     const double dist = d * asin(sqrt(c));
     const double iv = dist * 1000 / dd;
-    const int interval = iv >= 2147483647.0 ? 2147483647 : (int)iv;
+    const int interval = iv >= 2147483647.0 ? 2147483647 : (iv > 0.0 ? (int)iv : 0);
     return interval < dist_num ? interval : dist_num;
 }
 

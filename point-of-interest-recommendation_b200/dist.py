@@ -308,3 +308,58 @@ class ShardedSpatialGru:
         if self.trace: self.trace.mark('apply')
         if self.trace: self.trace.end_step()
         return [out[0], out[1], out[2], np.array([out[3], out[4]])]
+
+    # ---- checkpoint of the row-sharded model ("sharded save for C5") ----------------------------------
+    def save_checkpoint(self, directory, epoch=0):
+        """Every rank writes its shard of the item table as `lt.shard<r>of<W>.npy`; rank 0 adds `dense.pkl`: the reference's
+        9-array list (prog_bpr_gru_spatial.py:323-330, order fixed by GRU_Spatial.py:92-101) with the `lt` slot holding a
+        manifest {n_rows, d, world, pattern} instead of the 20 GB table.  `assemble_checkpoint` turns the directory back into
+        one reference-format file when the table fits the host."""
+        import os
+        import pickle
+        os.makedirs(directory, exist_ok=True)
+        np.save(os.path.join(directory, "lt.shard%dof%d.npy" % (self.rank, self.world)), self.lt_local.get_value())
+        if self.rank == 0:
+            sc = self._scal.get_value()
+            manifest = dict(n_rows=self.n_rows, d=self.d, world=self.world, pattern="lt.shard%dof%d.npy", epoch=int(epoch))
+            arrays = [np.asarray(sc[1:], dtype=np.float32), np.asarray(sc[0], dtype=np.float64), manifest, self.di.get_value(),
+                      self.ui.get_value(), self.wh.get_value(), self.bi.get_value(), self.vs.get_value(), self.bs.get_value()]
+            with open(os.path.join(directory, "dense.pkl"), "wb") as f:
+                pickle.dump(arrays, f, protocol=2)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def load_checkpoint(self, directory):
+        """Inverse of `save_checkpoint`; the directory may have been written with a different world size (rows are re-dealt:
+        global row = local * world_saved + rank_saved)."""
+        import os
+        import pickle
+        with open(os.path.join(directory, "dense.pkl"), "rb") as f:
+            arrays = pickle.load(f, encoding="latin1")
+        man = arrays[2]
+        if man["n_rows"] != self.n_rows or man["d"] != self.d:
+            raise ValueError("checkpoint is for a %d x %d table, this model has %d x %d" % (man["n_rows"], man["d"], self.n_rows, self.d))
+        mine = np.arange(self.rank, self.n_rows, self.world)
+        out = np.empty((len(mine), self.d), dtype=np.float32)
+        for r in range(man["world"]):
+            sh = np.load(os.path.join(directory, man["pattern"] % (r, man["world"])), mmap_mode="r")
+            sel = np.nonzero(mine % man["world"] == r)[0]
+            out[sel] = sh[mine[sel] // man["world"]]
+        self.lt_local.t.copy_(torch.from_numpy(out))
+        self._scal.set_value(np.array([float(arrays[1]), arrays[0][0], arrays[0][1]], dtype=np.float32))
+        for k, a in zip(("di", "ui", "wh", "bi", "vs", "bs"), arrays[3:]):
+            getattr(self, k).set_value(np.asarray(a, dtype=np.float32))
+
+
+def assemble_checkpoint(directory, out_path):
+    """Sharded checkpoint directory -> ONE file in the reference's 9-array format (loadable by `OboSpatialGru.load_params`
+    and by the reference itself)."""
+    import os
+    import pickle
+    with open(os.path.join(directory, "dense.pkl"), "rb") as f:
+        arrays = pickle.load(f, encoding="latin1")
+    man = arrays[2]
+    arrays[2] = unshard_rows([np.load(os.path.join(directory, man["pattern"] % (r, man["world"]))) for r in range(man["world"])], man["n_rows"])
+    with open(out_path, "wb") as f:
+        pickle.dump(arrays, f, protocol=2)
+    return out_path

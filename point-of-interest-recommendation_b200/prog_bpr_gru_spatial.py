@@ -125,9 +125,19 @@ def save_checkpoint(model, path):
         pickle.dump(arrays, f, protocol=pickle.HIGHEST_PROTOCOL)
 
 
-def load_checkpoint(model, path):
+def read_checkpoint(path):
+    """The 9 arrays of a Distance2Pre checkpoint, in the reference's order [loss_weight, wd, lt, di, ui, wh, bi, vs, bs].
+    Reads both this port's files and the reference's own (Python 2.7 `cPickle.dump(..., protocol=2)`,
+    prog_bpr_gru_spatial.py:323-330: byte strings are py2 `str`, hence encoding='latin1')."""
     with open(path, 'rb') as f:
-        model.load_params(pickle.load(f, encoding='latin1'))      # latin1: also reads py2 cPickle files
+        arrays = pickle.load(f, encoding='latin1')
+    if not isinstance(arrays, (list, tuple)) or len(arrays) != 9:
+        raise ValueError("%s: expected the 9-array list [loss_weight, wd, lt, di, ui, wh, bi, vs, bs]" % path)
+    return [np.asarray(a) for a in arrays]
+
+
+def load_checkpoint(model, path):
+    model.load_params(read_checkpoint(path))
 
 
 def train_one_epoch(p, model, epoch, user_num, tra_buys_masks, tra_masks, tra_buys_neg_masks, starts_ends_tra=None):

@@ -84,7 +84,12 @@ def epoch_call_list(user_idxs_tra, tra_pois_masks, tra_pois_neg_masks, tra_all_d
     lens = np.sum(np.asarray(tra_masks), axis=1)
     us = np.repeat(user_idxs_tra, np.maximum(lens[user_idxs_tra] - 1, 0))
     pos = np.concatenate([np.arange(1, lens[u]) for u in user_idxs_tra]) if len(user_idxs_tra) else np.zeros(0, int)
-    return us, P[us, pos], Q[us, pos], P[us, pos - 1], D[us, pos], G[us, pos].astype(np.int32)
+    gaps = G[us, pos]
+    # the reference declares the gap an int32 scalar (PRME.py:177, `iscalar`): Theano refuses a non-integral value, it does
+    # not truncate it -- 360.5 > 360 must not silently become 360 > 360
+    if gaps.size and (np.any(gaps != np.round(gaps)) or np.any(np.abs(gaps) >= 2 ** 31)):
+        raise TypeError("PRME time gaps must be integral minutes that fit int32 (PRME.py:177 declares an iscalar)")
+    return us, P[us, pos], Q[us, pos], P[us, pos - 1], D[us, pos], gaps.astype(np.int32)
 
 
 def train_valid_or_test(pas=None, init=None, device=None):

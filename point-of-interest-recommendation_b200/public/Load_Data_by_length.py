@@ -35,8 +35,10 @@ def cal_dis_np(lat1, lon1, lat2, lon2, dd, dist_num):
     a = (lat1 - lat2) * p
     b = (lon1 - lon2) * p
     c = (1.0 - np.cos(a)) / 2 + np.cos(lat1 * p) * np.cos(lat2 * p) * (1.0 - np.cos(b)) / 2
-    dist = d * np.arcsin(np.sqrt(c))
-    return np.minimum((dist * 1000 / dd).astype(np.int64), dist_num)
+    # rounding can push c a hair outside [0, 1] for (near-)antipodal or identical points: arcsin would return NaN and the
+    # integer cast a huge negative interval id (the reference's math.asin raises instead); clamp
+    dist = d * np.arcsin(np.sqrt(np.clip(c, 0.0, 1.0)))
+    return np.clip((dist * 1000 / dd).astype(np.int64), 0, dist_num)
 
 
 def read_sequences(dataset):
