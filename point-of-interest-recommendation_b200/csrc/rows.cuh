@@ -314,7 +314,9 @@ static int launch_rows_update(poi_engine* e, const SegList& seg, float* table, i
     else if (dim4 <= 128) POI_LAUNCH(e, (k_rows_update_warp<4>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
     else if (dim4 <= 256) POI_LAUNCH(e, (k_rows_update_warp<8>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
     else POI_FAIL(e, "row dim %d too large (max 1024)", dim);
-    // long segments: chunk partials, then ordered final sum
+    // long segments: chunk partials, then ordered final sum (none can exist when the whole list is shorter than the
+    // threshold -- the one-by-one calls of the reference's semantics -- so the three launches are skipped)
+    if (seg.n <= long_thresh) return 0;
     const size_t max_long = (size_t)seg.n / (size_t)std::max(long_thresh, 1) + 2;
     const size_t max_chunks = (size_t)seg.n / ROW_CHUNK + max_long + 2;
     uint32_t* chunk_off = nullptr; float4* partial = nullptr; float* partial_w = nullptr;
