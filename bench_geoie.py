@@ -73,31 +73,45 @@ def run_reference(args):
 def run_ours(args):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
-        raise SystemExit("bench.py --config c4: the row-sharded 2-GPU GeoIE step is not built; run with --gpus 1")
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import poi_b200  # noqa: F401
     from poi_b200 import synth
     from poi_b200.public.GeoIE import GeoIEBatch
     cfg = dict(synth.CONFIGS["c4"])
     I, d, L, K = cfg["n_item"], cfg["d"], cfg["seq"], cfg["neg"]
-    Bu = args.batch
+    weak = args.scaling == "weak"
+    Bu = args.batch if weak else max(1, args.batch // world)          # users per GPU per step
+    Bg = Bu * world
     W, Kst = max(args.warmup, 3), max(args.steps, 1)
     n_steps = 2 * (W + Kst) + 4
-    P, Q, coords = _data(cfg, Bu * n_steps)
-    n_user = Bu * n_steps
+    P, Q, coords = _data(cfg, Bg * n_steps)                              # same seed on every rank: identical data
+    n_user = Bg * n_steps
     dev = torch.device("cuda", local_rank)
-    st = synth.init_mf_state("geoie", n_user, I, d)
+    st = synth.init_mf_state("geoie", 8, I, d)
     tes = [[I]]
-    model = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [B0.ALPHA, B0.LAM], n_user, I, d, d, None, init=st, coords=coords, device=local_rank)
+    if world == 1:
+        model = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [B0.ALPHA, B0.LAM], 8, I, d, d, None, init=st, coords=coords, device=local_rank)
+    else:
+        from poi_b200.dist import ShardedGeoIE
+        model = ShardedGeoIE([B0.ALPHA, B0.LAM], I, d, st, coords, max_users=Bu, seq_len=L, n_neg=K, device=local_rank)
     eng = model.engine
-    res = [(torch.as_tensor(P[s * Bu:(s + 1) * Bu], device=dev), torch.as_tensor(Q[s * Bu:(s + 1) * Bu], device=dev)) for s in range(n_steps)]
-    pin = [(torch.from_numpy(P[s * Bu:(s + 1) * Bu]).pin_memory(), torch.from_numpy(Q[s * Bu:(s + 1) * Bu]).pin_memory()) for s in range(n_steps)]
+    mine = lambda s: slice(s * Bg + rank * Bu, s * Bg + (rank + 1) * Bu)  # this rank's users of step s
+    res = [(torch.as_tensor(P[mine(s)], device=dev), torch.as_tensor(Q[mine(s)], device=dev)) for s in range(n_steps)]
+    pin = [(torch.from_numpy(P[mine(s)]).pin_memory(), torch.from_numpy(Q[mine(s)]).pin_memory()) for s in range(n_steps)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def timed(arrs, n_warm, n, first):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for i in range(n_warm):
             model.train_batch(*arrs[first + i])
+        if dist is not None:
+            dist.barrier()
         torch.cuda.synchronize()
         l0 = eng.launch_count(); losses = []
         for i in range(n):
@@ -106,6 +120,8 @@ def run_ours(args):
             losses.append(model.train_batch(*arrs[first + n_warm + i]))
             ev[i][1].record()
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
         return sum(a.elapsed_time(b) for a, b in ev), eng.launch_count() - l0, losses
 
     sampler = B0.ClockSampler(local_rank); sampler.start()
@@ -117,24 +133,36 @@ def run_ours(args):
     for i in range(nprof):
         model.train_batch(*res[2 * (W + Kst) + i])
     prof = eng.kprof_get(); eng.kprof_enable(False)
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0].item()), float(t[1].item())
+        t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        launches = int(t.item())
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     peaks = B0.load_peaks()
-    N = Bu * (L - 1)
+    N = Bg * (L - 1)
     value = N * Kst / (ms * 1e-3)
     kern = {}
     for k, what in (("geoie", "k_geoie_batch_k: per user, G in shared memory / registers, candidates streamed, unique rows updated in place"),
-                    ("rows", "segment sums of the rows that occur several times in the batch"), ("index", "keys, radix sort, segments"),
+                    ("rows", "segment sums of the rows that occur several times in the batch (multi-GPU: + deltas, owner-side apply)"),
+                    ("gather", "multi-GPU: compact copies of the touched rows out of the owners' shards (NVLink)"),
+                    ("index", "keys, radix sort, segments"), ("other", "multi-GPU: flag signal / wait kernels"),
                     ("reduce", "loss / a, b finalisation")):
         r = prof[k]
         if r["ms"] > 0:
             kern[k] = {"what": what, "ms_per_step": r["ms"] / nprof, "launches_per_step": r["launches"] / nprof}
-    t_main = (prof["geoie"]["ms"] + prof["rows"]["ms"]) / nprof
-    ach = ALGO * N / (t_main * 1e-3) / 1e9
+    t_main = (prof["geoie"]["ms"] + prof["rows"]["ms"] + prof["gather"]["ms"]) / nprof
+    ach = ALGO * (N / world) / (t_main * 1e-3) / 1e9                     # per GPU
     tot_ms = sum(v["ms"] for v in prof.values()) / nprof
     roof = {"kernel": "k_geoie_batch_k + segment sums (the gather / scatter of the step)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
             "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_check_in": ALGO,
-            "share_of_step": t_main / tot_ms, "whole_step_frac": ALGO * N / (ms / Kst * 1e-3) / 1e9 / peaks["hbm"]}
+            "share_of_step": t_main / tot_ms, "whole_step_frac": ALGO * (N / world) / (ms / Kst * 1e-3) / 1e9 / peaks["hbm"]}
     parity = None
-    if not args.no_parity:
+    if not args.no_parity and world == 1:
         from oracle import models as OM
         nb = 4
         m2 = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [B0.ALPHA, B0.LAM], n_user, I, d, d, None, init=st, coords=coords, device=local_rank)
@@ -151,7 +179,7 @@ def run_ours(args):
                   "rel_err_ab": max(abs(m2.a.eval() - ref["a"]) / abs(ref["a"]), abs(m2.b.eval() - ref["b"]) / abs(ref["b"])), "tolerance": 1e-4,
                   "metric": "element-wise |a-b| / max(|b|, 1e-2 max|b|) on the touched rows"}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         from oracle import models as OM
         torch.set_num_threads(os.cpu_count() or 1)
         state = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
@@ -163,13 +191,18 @@ def run_ours(args):
             ts.append(time.perf_counter() - t_)
         cpu = {"value": n_ci * 2 / sum(ts[1:]), "unit": B0.UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "2 steps x 8 users of the %d-user step (torch-CPU oracle, float64, all cores)" % Bu}
-    line = {"metric": B0.METRIC, "value": value, "unit": B0.UNIT, "n_gpus": 1, "steps": Kst, "warmup": W, "ms_per_step": ms / Kst,
+    line = {"metric": B0.METRIC, "value": value, "unit": B0.UNIT, "n_gpus": world, "steps": Kst, "warmup": W, "ms_per_step": ms / Kst,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": B0.make_config("c4", cfg, args.batch, 1, args.scaling),
-            "engine": {"check_ins_per_step": N, "negatives": K, "note": "BASELINE.json quotes c4 on 2 x B200 row-sharded; this line is one GPU holding all three 1 GB tables"},
+            "config": B0.make_config("c4", cfg, args.batch, world, args.scaling),
+            "engine": {"check_ins_per_step": N, "negatives": K, "users_per_gpu": Bu,
+                       "parallelism": "1 GPU holding all three 1 GB tables" if world == 1 else
+                       "dp%d: users sharded, g / h / z row-sharded (row %% %d), compact copies gathered from the owners' shards and deltas applied by the "
+                       "owners over NVLink peer memory (csrc/mf_mg.cuh)" % (world, world)},
             "e2e": {"value": N * Kst / (ms_e2e * 1e-3), "unit": B0.UNIT, "h2d_bytes_per_step": Bu * L * (K + 1) * 4, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / Kst},
             "gpu_launches": int(launches), "roofline": roof, "kernels": kern,
             "kernel_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in prof.items() if v["ms"] > 0},
             "parity": parity, "cpu_baseline": cpu, "clocks": clocks, "final_loss": float(losses[-1])}
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()

@@ -358,6 +358,30 @@ int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* params, const
                             const float* coords_dev, int32_t Bu, int32_t L, int32_t K, int32_t on_host,
                             float alpha, float lambda, double* loss_host);
 
+/* ---- row-sharded multi-GPU step of the pairwise models (csrc/mf_mg.cuh; BASELINE.json C4 "GeoIE ... 2 x B200 row-sharded").
+ * Same peer-memory protocol as poi_gru_step_mg.  Key set 0 = the g occurrences (history), key set 1 = the h / z occurrences
+ * (candidates); table 0 = g (set 0), 1 = h, 2 = z (set 1).  Per rank, peer-visible (poi_peer_alloc): the three shards, per key
+ * set ob_ids / ob_perm [cap[set]] and ob_meta [world + 2], per table ob_grads [cap[set of the table] x H], sums double[4],
+ * flags uint32 [2 * world] (zero before step 1); slot_tab[set]: own int32 [n_local_rows x world], all -1.
+ * cap[0] >= Bu (L - 1), cap[1] >= Bu (L - 1)(K + 1).  params->g/h/z are ignored (the shards come from `peers`), params->n_rows
+ * is the GLOBAL row count, params->ab the replicated scalars.  P, Q hold GLOBAL row ids of this rank's users. */
+typedef struct {
+    int32_t   world, rank;
+    int64_t   cap[2];
+    int64_t   n_local_rows;
+    float*    shard[3][POI_MG_MAX_RANKS];
+    int32_t*  ob_ids[2][POI_MG_MAX_RANKS];
+    int32_t*  ob_perm[2][POI_MG_MAX_RANKS];
+    int32_t*  ob_meta[2][POI_MG_MAX_RANKS];
+    float*    ob_grads[3][POI_MG_MAX_RANKS];
+    double*   sums[POI_MG_MAX_RANKS];
+    uint32_t* flags[POI_MG_MAX_RANKS];
+    int32_t*  slot_tab[2];
+} poi_mf_peers;
+int poi_geoie_step_mg(poi_engine* e, const poi_geoie_params* params, const int32_t* P, const int32_t* Q, const float* coords_dev,
+                      int32_t Bu, int32_t L, int32_t K, int32_t on_host, const poi_mf_peers* peers, int64_t step,
+                      float alpha, float lambda, double* loss_host);
+
 /* ---- evaluation helpers (scoring + top-K) ---------------------------- */
 /* scores[b, i] = users[b,:] . items[i,:] (+ wd * prob[b, i] if prob_dev != NULL), then the
  * indices of the top_k largest scores per row in descending order -- the product of

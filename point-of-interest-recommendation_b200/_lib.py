@@ -65,6 +65,13 @@ class PoiMgPeers(Structure):
                [("slot_tab", c_void_p)]
 
 
+class PoiMfPeers(Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("cap", c_int64 * 2), ("n_local_rows", c_int64),
+                ("shard", (c_void_p * 16) * 3), ("ob_ids", (c_void_p * 16) * 2), ("ob_perm", (c_void_p * 16) * 2),
+                ("ob_meta", (c_void_p * 16) * 2), ("ob_grads", (c_void_p * 16) * 3), ("sums", c_void_p * 16),
+                ("flags", c_void_p * 16), ("slot_tab", c_void_p * 2)]
+
+
 _E = c_void_p
 _PROTOS = {
     "poi_engine_create": (c_int, [c_int, POINTER(_E)]),
@@ -132,6 +139,8 @@ _PROTOS = {
                                 c_int64, c_float, c_float, POINTER(c_double)]),
     "poi_gru_step_mg_host_rows": (c_int, [_E, POINTER(PoiGruParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                           POINTER(PoiMgPeers), c_int64, c_float, c_float, POINTER(c_double)]),
+    "poi_geoie_step_mg": (c_int, [_E, POINTER(PoiGeoieParams), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                  POINTER(PoiMfPeers), c_int64, c_float, c_float, POINTER(c_double)]),
     "poi_geoie_train": (c_int, [_E, POINTER(PoiGeoieParams), c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_void_p, c_int32, c_float, c_float, POINTER(c_double)]),
     "poi_geoie_train_batch_k": (c_int, [_E, POINTER(PoiGeoieParams), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,

@@ -580,25 +580,73 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
 }
 
 // ---- K-negative GeoIE mini-batch (geoie_k.cuh) ------------------------------------------------------
+// One GeoIE mini-batch step on the tables given (the real ones on one GPU; compact copies of the touched rows with slot
+// indices in `gb` under mf_mg.cuh).  seg_h / seg_g: segments of the h / z and g occurrences (inverse map included) whose
+// `uniq` entries are the row numbers IN THE TABLES PASSED.  ab_apply == NULL: a, b are left alone and out_dev[1..2] receive
+// this rank's d cost / d a, d cost / d b.
+static int geoie_batch_core(poi_engine* e, float* g, float* h, float* z, const double* ab_read, double* ab_apply, int H,
+                            const GeoBatch& gb, const SegList& seg_h, const SegList& seg_g, float alpha, float lambda,
+                            double* out_dev) {
+    const int Bu = gb.Bu, n = gb.L - 1, C = gb.K + 1;
+    const int64_t n_occ = (int64_t)Bu * n * C, n_g = (int64_t)Bu * n;
+    uint8_t *single_h = nullptr, *single_g = nullptr;
+    POI_TRY(arena_get(e, (size_t)n_occ, &single_h));
+    POI_TRY(arena_get(e, (size_t)n_g, &single_g));
+    POI_CAT(e, CAT_INDEX, 0, 0);
+    POI_LAUNCH(e, k_mark_single, (unsigned)poi_cdiv(n_occ, 256), 256, 0, seg_h, single_h);
+    POI_LAUNCH(e, k_mark_single, (unsigned)poi_cdiv(n_g, 256), 256, 0, seg_g, single_g);
+    float *GH = nullptr, *GG = nullptr; double* part = nullptr;
+    POI_TRY(arena_get(e, (size_t)n_occ * H, &GH));
+    POI_TRY(arena_get(e, (size_t)n_g * H, &GG));
+    const int blocks = (int)std::min<int64_t>(Bu, (int64_t)e->num_sms * 2);
+    POI_TRY(arena_get(e, (size_t)blocks * 3, &part));
+    const size_t smem = geoie_k_smem(H);
+    // algorithmic bytes (SURVEY.md 8d): per target 1 g row + (h, z) x (1 + K) rows, each read once and written once
+    POI_CAT(e, CAT_GEOIE, 0, (double)Bu * n * (2.0 * (1 + 2 * C) * H * 4 + 4.0 * C));
+    if (H <= 256) {
+        POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        POI_LAUNCH(e, (k_geoie_batch_k<1>), blocks, 256, smem, g, h, z, ab_read, H, gb, single_h, single_g, alpha, lambda, GH, GG, part);
+    } else {
+        POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        POI_LAUNCH(e, (k_geoie_batch_k<2>), blocks, 256, smem, g, h, z, ab_read, H, gb, single_h, single_g, alpha, lambda, GH, GG, part);
+    }
+    POI_CAT(e, CAT_REDUCE, 0, 0);
+    POI_LAUNCH(e, k_geoie_k_finalize, 1, 32, 0, part, blocks, ab_apply, alpha, out_dev);
+    // rows that occur several times in the batch: duplicate-summed, L2 once per occurrence
+    RowSrc src; memset(&src, 0, sizeof(src));
+    src.mode = SRC_DENSE_GRADS; src.dim = H; src.skip_single = 1;
+    src.grads = GH; POI_TRY(launch_rows_update(e, seg_h, h, H, alpha, lambda, src, ROW_LONG_THRESH));
+    src.grads = nullptr; POI_TRY(launch_rows_update(e, seg_h, z, H, alpha, lambda, src, ROW_LONG_THRESH));   // z: L2 decay only
+    src.grads = GG; POI_TRY(launch_rows_update(e, seg_g, g, H, alpha, lambda, src, ROW_LONG_THRESH));
+    return 0;
+}
+
+static int geoie_check(poi_engine* e, const poi_geoie_params* prm, int L, int K, const float* coords_dev) {
+    if (!prm || !prm->g || !prm->h || !prm->z || !prm->ab) POI_FAIL(e, "geoie params: null pointer");
+    if (prm->H <= 0 || prm->H % 4 || prm->H > 512) POI_FAIL(e, "n_hidden must be a multiple of 4, <= 512");
+    if (L < 2 || L - 1 > GEO_MAXN) POI_FAIL(e, "sequence length must be in [2, %d] for the mini-batch kernel", GEO_MAXN + 1);
+    if (K < 1 || K > 128 || !coords_dev) POI_FAIL(e, "1 <= K <= 128 and a coordinate table are required");
+    return 0;
+}
+
 extern "C" int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* prm, const int32_t* P, const int32_t* Q,
                                        const float* coords_dev, int32_t Bu, int32_t L, int32_t K, int32_t on_host,
                                        float alpha, float lambda, double* loss_host) {
     POI_TRY(begin_call(e));
-    if (!prm || !prm->g || !prm->h || !prm->z || !prm->ab) POI_FAIL(e, "geoie params: null pointer");
+    POI_TRY(geoie_check(e, prm, L, K, coords_dev));
     const int H = prm->H;
-    if (H <= 0 || H % 4 || H > 512) POI_FAIL(e, "n_hidden must be a multiple of 4, <= 512");
-    if (L < 2 || L - 1 > GEO_MAXN) POI_FAIL(e, "sequence length must be in [2, %d] for the mini-batch kernel", GEO_MAXN + 1);
-    if (K < 1 || K > 128 || !coords_dev) POI_FAIL(e, "1 <= K <= 128 and a coordinate table are required");
     if (Bu <= 0) { if (loss_host) *loss_host = 0.0; return 0; }
     const int n = L - 1, C = K + 1;
     const int64_t n_occ = (int64_t)Bu * n * C, n_g = (int64_t)Bu * n;
     if (n_occ >= (int64_t)1 << 31) POI_FAIL(e, "batch too large");
-    GeoBatch gb; gb.Bu = Bu; gb.L = L; gb.K = K; gb.coords = reinterpret_cast<const float2*>(coords_dev);
+    GeoBatch gb; gb.Bu = Bu; gb.L = L; gb.K = K;
+    gb.coords_g = gb.coords_h = reinterpret_cast<const float2*>(coords_dev);
     if (on_host) {
         const void* hs[2] = {P, Q}; size_t bs[2] = {(size_t)Bu * L * 4, (size_t)Bu * L * K * 4}; void* dv[2];
         POI_TRY(upload_many(e, hs, bs, 2, dv));
         gb.P = (const int32_t*)dv[0]; gb.Q = (const int32_t*)dv[1];
     } else { gb.P = P; gb.Q = Q; }
+    gb.Ph = gb.P;
     uint32_t *keys_h = nullptr, *keys_g = nullptr;
     POI_TRY(arena_get(e, (size_t)n_occ, &keys_h));
     POI_TRY(arena_get(e, (size_t)n_g, &keys_g));
@@ -607,37 +655,9 @@ extern "C" int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* pr
     SegList seg_h, seg_g;
     POI_TRY(build_segments(e, keys_h, n_occ, (uint32_t)prm->n_rows, true, &seg_h));
     POI_TRY(build_segments(e, keys_g, n_g, (uint32_t)prm->n_rows, true, &seg_g));
-    uint8_t *single_h = nullptr, *single_g = nullptr;
-    POI_TRY(arena_get(e, (size_t)n_occ, &single_h));
-    POI_TRY(arena_get(e, (size_t)n_g, &single_g));
-    POI_LAUNCH(e, k_mark_single, (unsigned)poi_cdiv(n_occ, 256), 256, 0, seg_h, single_h);
-    POI_LAUNCH(e, k_mark_single, (unsigned)poi_cdiv(n_g, 256), 256, 0, seg_g, single_g);
-    float *GH = nullptr, *GG = nullptr; double *part = nullptr, *out_dev = nullptr;
-    POI_TRY(arena_get(e, (size_t)n_occ * H, &GH));
-    POI_TRY(arena_get(e, (size_t)n_g * H, &GG));
-    const int blocks = (int)std::min<int64_t>(Bu, (int64_t)e->num_sms * 2);
-    POI_TRY(arena_get(e, (size_t)blocks * 3, &part));
-    POI_TRY(arena_get(e, 1, &out_dev));
-    const size_t smem = geoie_k_smem(H);
-    // algorithmic bytes (SURVEY.md 8d): per target 1 g row + (h, z) x (1 + K) rows, each read once and written once
-    POI_CAT(e, CAT_GEOIE, 0, (double)Bu * n * (2.0 * (1 + 2 * C) * H * 4 + 4.0 * C));
-    if (H <= 256) {
-        POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        POI_LAUNCH(e, (k_geoie_batch_k<1>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, single_h, single_g,
-                   alpha, lambda, GH, GG, part);
-    } else {
-        POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        POI_LAUNCH(e, (k_geoie_batch_k<2>), blocks, 256, smem, prm->g, prm->h, prm->z, prm->ab, H, gb, single_h, single_g,
-                   alpha, lambda, GH, GG, part);
-    }
-    POI_CAT(e, CAT_REDUCE, 0, 0);
-    POI_LAUNCH(e, k_geoie_k_finalize, 1, 32, 0, part, blocks, prm->ab, alpha, out_dev);
-    // rows that occur several times in the batch: duplicate-summed, L2 once per occurrence
-    RowSrc src; memset(&src, 0, sizeof(src));
-    src.mode = SRC_DENSE_GRADS; src.dim = H; src.skip_single = 1;
-    src.grads = GH; POI_TRY(launch_rows_update(e, seg_h, prm->h, H, alpha, lambda, src, ROW_LONG_THRESH));
-    src.grads = nullptr; POI_TRY(launch_rows_update(e, seg_h, prm->z, H, alpha, lambda, src, ROW_LONG_THRESH));   // z: L2 decay only
-    src.grads = GG; POI_TRY(launch_rows_update(e, seg_g, prm->g, H, alpha, lambda, src, ROW_LONG_THRESH));
+    double* out_dev = nullptr;
+    POI_TRY(arena_get(e, 4, &out_dev));
+    POI_TRY(geoie_batch_core(e, prm->g, prm->h, prm->z, prm->ab, prm->ab, H, gb, seg_h, seg_g, alpha, lambda, out_dev));
     POI_CK(e, cudaMemcpyAsync(e->h_out, out_dev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     POI_CK(e, cudaStreamSynchronize(e->stream));
     if (e->kprof) prof_harvest(e);

@@ -25,10 +25,13 @@ constexpr int GEO_TILE = 16;          // candidates per tile (2 per warp)
 constexpr int GEO_MAXN = 32;          // history length: one lane per history position
 
 struct GeoBatch {
-    const int32_t* P;                 // [Bu x L]
-    const int32_t* Q;                 // [Bu x L x K]   (position 0 unused)
-    const float2* coords;             // [n_rows] lat, lon (degrees)
+    const int32_t* P;                 // [Bu x L]       row of g (and of coords_g) for every position
+    const int32_t* Ph;                // [Bu x L]       row of h / z (and of coords_h) for every position; == P on one GPU
+    const int32_t* Q;                 // [Bu x L x K]   rows of h / z (and of coords_h) of the negatives (position 0 unused)
+    const float2* coords_g;           // lat, lon (degrees) indexed like P
+    const float2* coords_h;           // lat, lon indexed like Ph / Q; == coords_g on one GPU
     int Bu, L, K;
+    // (multi-GPU: the tables are compact copies of the rows the batch touches and P / Ph / Q hold SLOTS, mf_mg.cuh)
 };
 
 // keys of the h / z occurrences: o = (b n + i)(K + 1) + c, c = 0 the positive p_{i+1}, c >= 1 the negatives; then the
@@ -39,7 +42,7 @@ __global__ void k_geoie_keys(GeoBatch gb, uint32_t* __restrict__ keys_h, uint32_
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o < tot) {
         const int c = (int)(o % C); const int64_t bi = o / C; const int i = (int)(bi % n); const int b = (int)(bi / n);
-        keys_h[o] = (uint32_t)(c == 0 ? gb.P[(size_t)b * gb.L + i + 1] : gb.Q[((size_t)b * gb.L + i + 1) * gb.K + c - 1]);
+        keys_h[o] = (uint32_t)(c == 0 ? gb.Ph[(size_t)b * gb.L + i + 1] : gb.Q[((size_t)b * gb.L + i + 1) * gb.K + c - 1]);
     }
     if (o < (int64_t)gb.Bu * n) { const int j = (int)(o % n), b = (int)(o / n); keys_g[o] = (uint32_t)gb.P[(size_t)b * gb.L + j]; }
 }
@@ -107,7 +110,8 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
             *reinterpret_cast<float4*>(Gs + (size_t)j * HS + 4 * c4) = j < n ? ld4(g + (size_t)Pu[j] * H + 4 * c4) : f4zero();
         }
         float hlat = 0.f, hlon = 0.f, hcos = 1.f;
-        if (lane < n) { const float2 cc = gb.coords[Pu[lane]]; hlat = cc.x; hlon = cc.y; hcos = cosf(cc.x * 0.017453292519943295f); }
+        const int32_t* Phu = gb.Ph + (size_t)u * gb.L;
+        if (lane < n) { const float2 cc = gb.coords_g[Pu[lane]]; hlat = cc.x; hlon = cc.y; hcos = cosf(cc.x * 0.017453292519943295f); }
         __syncthreads();
         float Gcol[NCOL][GEO_MAXN], dG[NCOL][GEO_MAXN];
 #pragma unroll
@@ -141,13 +145,13 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
             prefetch(0, 0);
             // ---- the positive: warp 0 scores it; its row stays in Hp until the target's negatives are done ----
             if (warp == 0) {
-                const int32_t x = Pu[i + 1];
+                const int32_t x = Phu[i + 1];
                 for (int c4 = lane; c4 < (H >> 2); c4 += 32) *reinterpret_cast<float4*>(Hp + 4 * c4) = ld4(h + (size_t)x * H + 4 * c4);
                 __syncwarp();
                 float d0, d1;
                 geo_dots2(Gs, HS, H, lane, Hp, Hp, d0, d1);
                 float pw, pwl;
-                geo_weight(on, hlat, hlon, hcos, gb.coords[x], b, pw, pwl);
+                geo_weight(on, hlat, hlon, hcos, gb.coords_h[x], b, pw, pwl);
                 const float w = a * pw * inv;
                 wP[lane] = w;
                 const float s = warp_sum(on ? d0 * w : 0.f), A = warp_sum(on ? d0 * pw * inv : 0.f), Bv = warp_sum(on ? d0 * a * pwl * inv : 0.f);
@@ -169,8 +173,8 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
                 float d0, d1;
                 geo_dots2(Gs, HS, H, lane, h0, h1, d0, d1);
                 float pw0, pwl0, pw1, pwl1;
-                geo_weight(on && v0, hlat, hlon, hcos, gb.coords[x0], b, pw0, pwl0);
-                geo_weight(on && v1, hlat, hlon, hcos, gb.coords[x1], b, pw1, pwl1);
+                geo_weight(on && v0, hlat, hlon, hcos, gb.coords_h[x0], b, pw0, pwl0);
+                geo_weight(on && v1, hlat, hlon, hcos, gb.coords_h[x1], b, pw1, pwl1);
                 const float w0 = a * pw0 * inv, w1 = a * pw1 * inv;
                 const float s0 = warp_sum(d0 * w0), s1 = warp_sum(d1 * w1);          // masked lanes have w = 0
                 const float A0 = warp_sum(d0 * pw0 * inv), A1 = warp_sum(d1 * pw1 * inv);
@@ -227,7 +231,7 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
             if (tid == 0) { ga_acc -= (double)(E * sc[1]); gb_acc -= (double)(E * sc[2]); }
             {
                 const bool single = single_h[occ0] != 0;
-                const size_t x = (size_t)Pu[i + 1];
+                const size_t x = (size_t)Phu[i + 1];
 #pragma unroll
                 for (int q = 0; q < NCOL; ++q) {
                     const int col = tid + 256 * q;
@@ -290,6 +294,7 @@ __global__ void k_geoie_k_finalize(const double* __restrict__ part, int nblocks,
     double loss = 0.0, ga = 0.0, gb = 0.0;
     for (int i = 0; i < nblocks; ++i) { loss += part[(size_t)i * 3]; ga += part[(size_t)i * 3 + 1]; gb += part[(size_t)i * 3 + 2]; }
     out[0] = loss;
+    if (!ab) { out[1] = ga; out[2] = gb; return; }   // multi-GPU: the caller sums the ranks' partials first
     ab[0] -= (double)alpha * ga;                     // params = [a, b], no L2 on them (GeoIE.py:91,172-173)
     ab[1] -= (double)alpha * gb;
 }

@@ -171,7 +171,7 @@ k_mg_apply_rows(MgPull pl, const int32_t* __restrict__ slot_tab, float* __restri
             for (int q = p; q < W; ++q) {            // sources in rank order = the arrival order of the all-to-all formulation
                 const int s2 = q == p ? s : tab[q];
                 if (s2 < 0) continue;
-                cntf += pl.cnts[q][s2];
+                if (pl.cnts[q]) cntf += pl.cnts[q][s2];
                 const float* g = pl.grads[q] + (size_t)s2 * dim4 * 4;
 #pragma unroll
                 for (int k = 0; k < NCH; ++k) { const int c = lane + 32 * k; if (c < dim4) acc[k] = f4add(acc[k], ld4(g + 4 * c)); }

@@ -432,3 +432,4 @@ int poi_prme_train_seq(poi_engine* e, float* du, float* dp, float* ds_, int32_t 
 
 #include "api_more.cuh"
 #include "mg_step.cuh"
+#include "mf_mg.cuh"

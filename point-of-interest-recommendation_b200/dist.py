@@ -351,6 +351,103 @@ class ShardedSpatialGru:
             getattr(self, k).set_value(np.asarray(a, dtype=np.float32))
 
 
+class ShardedGeoIE:
+    """Mini-batch GeoIE with K negatives over `world` GPUs (BASELINE.json C4: "GeoIE ... 2 x B200 row-sharded"; EXTENSION
+    semantics as `GeoIEBatch`).  Users are split over the ranks; the item tables g, h, z are ROW-SHARDED (owner = row %
+    world), the scalars a, b replicated.  `train_batch(P, Q)` takes THIS rank's users (global POI ids) and runs the
+    peer-memory step of csrc/mf_mg.cuh; every rank must call it in lock-step with the same batch shape.  G ranks x Bu
+    users is the same update as one GPU x G Bu users up to float32 rounding."""
+
+    def __init__(self, alpha_lambda, n_item, n_hidden, init, coords, max_users, seq_len, n_neg, rank=None, world=None, device=None,
+                 tables_are_shards=False, group=None):
+        from ._lib import PoiMfPeers
+        from .engine import Engine
+        from .shared import Shared
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.group = group
+        self.engine = Engine.get(device)
+        eng, W, dev = self.engine, self.world, self.engine.torch_device
+        self.n_rows, self.H = n_item + 1, n_hidden
+        self._alpha, self._lambda = float(alpha_lambda[0]), float(alpha_lambda[1])
+        self._ab = torch.tensor([float(init["a"]), float(init["b"])], dtype=torch.float64, device=dev)
+        c = np.zeros((self.n_rows, 2), dtype=np.float32)
+        cc = np.asarray(coords, dtype=np.float32); c[:min(len(cc), self.n_rows)] = cc[:self.n_rows]
+        self.coords = Shared(c, "float32", dev)
+        n = seq_len - 1
+        cap = (max_users * n, max_users * n * (n_neg + 1))
+        own, handles = {}, {}
+        for k in ("g", "h", "z"):
+            t = init[k]
+            if not tables_are_shards:
+                t = t[self.rank::W] if isinstance(t, torch.Tensor) else shard_rows(np.asarray(t), self.rank, W)
+            t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+            own[k], handles[k] = eng.peer_alloc(tuple(t.shape), torch.float32)
+            own[k].copy_(t)
+        n_local = int(own["g"].shape[0])
+        spec = {}
+        for s_ in (0, 1):
+            spec["ob_ids%d" % s_] = ((cap[s_],), torch.int32); spec["ob_perm%d" % s_] = ((cap[s_],), torch.int32)
+            spec["ob_meta%d" % s_] = ((W + 2,), torch.int32)
+        for t_, s_ in ((0, 0), (1, 1), (2, 1)):
+            spec["ob_grads%d" % t_] = ((cap[s_], n_hidden), torch.float32)
+        spec["sums"] = ((4,), torch.float64); spec["flags"] = ((2 * W,), torch.int32)
+        for k, (shape, dt) in spec.items():
+            own[k], handles[k] = eng.peer_alloc(shape, dt)
+            if own[k].numel() <= 4096:
+                own[k].zero_()
+        self.g, self.h, self.z = (Shared(own[k], "float32", dev) for k in ("g", "h", "z"))
+        self._own = own
+        self._slot = [torch.full((n_local * W,), -1, dtype=torch.int32, device=dev) for _ in range(2)]
+        torch.cuda.synchronize(dev)
+        mine = dict(h=handles, shapes={k: tuple(own[k].shape) for k in own}, cap=cap)
+        every = [None] * W
+        if W > 1:
+            dist.all_gather_object(every, mine, group=group)
+        else:
+            every[0] = mine
+        if any(tuple(x["cap"]) != tuple(cap) for x in every):
+            raise ValueError("all ranks must use the same max_users / seq_len / n_neg")
+        pt = PoiMfPeers()
+        pt.world, pt.rank, pt.n_local_rows = W, self.rank, n_local
+        pt.cap[0], pt.cap[1] = cap
+        self._mapped = []
+        dts = {torch.float32: torch.float32, torch.int32: torch.int32, torch.float64: torch.float64}
+
+        def ptr_of(r, x, key):
+            if r == self.rank:
+                return own[key].data_ptr()
+            m = eng.peer_open(x["h"][key], x["shapes"][key], own[key].dtype)
+            self._mapped.append(m)
+            return m.data_ptr()
+        for r, x in enumerate(every):
+            for t_, k in enumerate(("g", "h", "z")):
+                pt.shard[t_][r] = ptr_of(r, x, k)
+                pt.ob_grads[t_][r] = ptr_of(r, x, "ob_grads%d" % t_)
+            for s_ in (0, 1):
+                pt.ob_ids[s_][r] = ptr_of(r, x, "ob_ids%d" % s_); pt.ob_perm[s_][r] = ptr_of(r, x, "ob_perm%d" % s_)
+                pt.ob_meta[s_][r] = ptr_of(r, x, "ob_meta%d" % s_)
+            pt.sums[r] = ptr_of(r, x, "sums"); pt.flags[r] = ptr_of(r, x, "flags")
+        pt.slot_tab[0], pt.slot_tab[1] = self._slot[0].data_ptr(), self._slot[1].data_ptr()
+        self._peers, self._cap, self._step_no = pt, cap, 0
+        if W > 1:
+            dist.barrier(group=group)
+
+    def train_batch(self, P, Q):
+        """P [Bu, L], Q [Bu, L, K] of THIS rank's users (global POI ids; CUDA tensors or host arrays).  Returns the GLOBAL
+        summed log-sigmoid loss."""
+        Bu, L = int(P.shape[0]), int(P.shape[1]); K = int(Q.shape[2])
+        if Bu * (L - 1) > self._cap[0] or Bu * (L - 1) * (K + 1) > self._cap[1]:
+            raise ValueError("batch exceeds the outbox capacity: construct with a larger max_users")
+        self._step_no += 1
+        return self.engine.geoie_step_mg(self._ab, self.n_rows, self.H, P, Q, self.coords.t, self._peers, self._step_no,
+                                         self._alpha, self._lambda)
+
+    def a_b(self):
+        v = self._ab.cpu().numpy()
+        return float(v[0]), float(v[1])
+
+
 def assemble_checkpoint(directory, out_path):
     """Sharded checkpoint directory -> ONE file in the reference's 9-array format (loadable by `OboSpatialGru.load_params`
     and by the reference itself)."""

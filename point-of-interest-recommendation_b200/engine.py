@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import PoiGeoieParams, PoiGruParams, PoiMgPeers, PoiSeqIndex, lib
+from ._lib import PoiGeoieParams, PoiGruParams, PoiMfPeers, PoiMgPeers, PoiSeqIndex, lib
 
 
 
@@ -392,6 +392,26 @@ class Engine:
                                                dp.ctypes.data if dp is not None else None, dq.ctypes.data if dq is not None else None,
                                                lens.ctypes.data, p.shape[0], p.shape[1], byref(peers), int(step), alpha, lam, out))
         return list(out)
+
+    def geoie_step_mg(self, ab, n_rows_global, H, P, Q, coords, peers, step, alpha, lam) -> float:
+        """One row-sharded multi-GPU GeoIE mini-batch step (csrc/mf_mg.cuh); P, Q: global row ids of this rank's users."""
+        prm = PoiGeoieParams()
+        prm.g = 0; prm.h = 0; prm.z = 0; prm.t = 0
+        prm.ab = ab.data_ptr(); prm.n_rows = int(n_rows_global); prm.H = int(H)
+        on_dev = isinstance(P, torch.Tensor) and P.is_cuda
+        if on_dev:
+            Bu, L = int(P.shape[0]), int(P.shape[1]); K = int(Q.shape[2])
+            pp, qp = _dev_i32(P, "P"), _dev_i32(Q, "Q")
+            keep = None
+        else:
+            f = lambda x: np.ascontiguousarray(x.numpy() if isinstance(x, torch.Tensor) else x, dtype=np.int32)
+            keep = (f(P), f(Q))
+            Bu, L = keep[0].shape; K = keep[1].shape[2]
+            pp, qp = keep[0].ctypes.data, keep[1].ctypes.data
+        out = c_double()
+        self._ck(lib.poi_geoie_step_mg(self._h, byref(prm), pp, qp, _dev_f32(coords, "coords"), Bu, L, K, 0 if on_dev else 1,
+                                       byref(peers), int(step), alpha, lam, byref(out)))
+        return float(out.value)
 
     # ---- BPR / PRME -------------------------------------------------------------------------
     def bpr_train_seq(self, ux, lt, u, p, q, alpha, lam) -> np.ndarray:

@@ -46,3 +46,11 @@ def test_all_visible_gpus_peer_exchange():
         pytest.skip("needs >= 4 GPUs")
     rc, out = _run("mg_check.py", n, {"POI_MG_PEER": "1"})
     assert rc == 0 and ("MG_CHECK PASS world %d" % n) in out, out[-3000:]
+
+
+def test_geoie_row_sharded_two_ranks_equal_one_rank_union_batch():
+    """csrc/mf_mg.cuh: 2 ranks x Bu users == 1 rank x 2 Bu users for the K-negative GeoIE mini-batch step."""
+    if _n_gpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rc, out = _run("mg_check_geoie.py", 2, {})
+    assert rc == 0 and "MG_CHECK_GEOIE PASS world 2" in out, out[-3000:]
