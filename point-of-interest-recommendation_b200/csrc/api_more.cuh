@@ -605,10 +605,10 @@ static int geoie_batch_core(poi_engine* e, float* g, float* h, float* z, const d
     POI_CAT(e, CAT_GEOIE, 0, (double)Bu * n * (2.0 * (1 + 2 * C) * H * 4 + 4.0 * C));
     if (H <= 256) {
         POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        POI_LAUNCH(e, (k_geoie_batch_k<1>), blocks, 256, smem, g, h, z, ab_read, H, gb, single_h, single_g, alpha, lambda, GH, GG, part);
+        POI_LAUNCH(e, (k_geoie_batch_k<1>), blocks, 256, smem, g, h, ab_read, H, gb, single_h, single_g, alpha, lambda, GH, GG, part);
     } else {
         POI_CK(e, cudaFuncSetAttribute(k_geoie_batch_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        POI_LAUNCH(e, (k_geoie_batch_k<2>), blocks, 256, smem, g, h, z, ab_read, H, gb, single_h, single_g, alpha, lambda, GH, GG, part);
+        POI_LAUNCH(e, (k_geoie_batch_k<2>), blocks, 256, smem, g, h, ab_read, H, gb, single_h, single_g, alpha, lambda, GH, GG, part);
     }
     POI_CAT(e, CAT_REDUCE, 0, 0);
     POI_LAUNCH(e, k_geoie_k_finalize, 1, 32, 0, part, blocks, ab_apply, alpha, out_dev);
@@ -616,7 +616,10 @@ static int geoie_batch_core(poi_engine* e, float* g, float* h, float* z, const d
     RowSrc src; memset(&src, 0, sizeof(src));
     src.mode = SRC_DENSE_GRADS; src.dim = H; src.skip_single = 1;
     src.grads = GH; POI_TRY(launch_rows_update(e, seg_h, h, H, alpha, lambda, src, ROW_LONG_THRESH));
-    src.grads = nullptr; POI_TRY(launch_rows_update(e, seg_h, z, H, alpha, lambda, src, ROW_LONG_THRESH));   // z: L2 decay only
+    // z: no loss gradient, L2 decay of every unique row (lambda x its occurrence count), single or not
+    src.grads = nullptr; src.skip_single = 0;
+    POI_TRY(launch_rows_update(e, seg_h, z, H, alpha, lambda, src, ROW_LONG_THRESH));
+    src.skip_single = 1;
     src.grads = GG; POI_TRY(launch_rows_update(e, seg_g, g, H, alpha, lambda, src, ROW_LONG_THRESH));
     return 0;
 }

@@ -14,9 +14,10 @@
 // haversine weight for ITS history POI), so no cross-lane reduction is needed per dot -- then all 256 threads turn the
 // tile's coefficients into d h[c] (written straight back) and dG (registers).  The distances are recomputed from an fp32
 // coordinate table (sin^2 form of the loader's haversine; the reference precomputes n x n matrices on the host).
-// A row that occurs ONCE in the batch is updated in place by the thread block that read it (read once + written once =
-// the algorithmic traffic); occurrences of rows that occur several times emit their gradient row and are summed in
-// fixed order by rows.cuh (skip_single).  No atomics; same bits on a re-run.
+// A row of g / h that occurs ONCE in the batch is updated in place by the thread block that read it (read once + written
+// once = the algorithmic traffic); occurrences of rows that occur several times emit their gradient row and are summed in
+// fixed order by rows.cuh (skip_single).  The z rows receive no loss gradient (t.z cancels): their update is the L2 decay
+// z -= alpha lambda cnt z, one streaming read-modify-write per unique row by rows.cuh.  No atomics; same bits on a re-run.
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
@@ -82,7 +83,7 @@ __device__ __forceinline__ void geo_weight(bool on, float hlat, float hlon, floa
 
 template <int NCOL>          // columns per thread: H <= 256 * NCOL
 __global__ void __launch_bounds__(256, NCOL == 1 ? 2 : 1)
-k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int H, GeoBatch gb,
+k_geoie_batch_k(float* __restrict__ g, float* __restrict__ h, const double* __restrict__ ab, int H, GeoBatch gb,
                 const uint8_t* __restrict__ single_h, const uint8_t* __restrict__ single_g,
                 float alpha, float lambda, float* __restrict__ GH, float* __restrict__ GG,
                 double* __restrict__ part /* [grid][3]: loss, d/da, d/db */) {
@@ -213,11 +214,8 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
                             }
                             const size_t o = occ0 + 1 + t0 + cw;
                             const size_t x = (size_t)sx[cw];
-                            if (sfl[cw]) {
-                                h[x * H + col] = hv - alpha * (dh + lambda * hv);
-                                const float zv = z[x * H + col];
-                                z[x * H + col] = zv - alpha * (lambda * zv);
-                            } else GH[o * H + col] = dh;          // z of a shared row: L2 only, the segment pass needs no gradient row
+                            if (sfl[cw]) h[x * H + col] = hv - alpha * (dh + lambda * hv);
+                            else GH[o * H + col] = dh;
                         }
                     }
                 }
@@ -243,11 +241,8 @@ k_geoie_batch_k(float* g, float* h, float* z, const double* __restrict__ ab, int
                             const float cf = -E * wP[j] * (j <= i ? 1.f : 0.f);
                             dG[q][j] = fmaf(cf, hv, dG[q][j]); dh = fmaf(cf, Gcol[q][j], dh);
                         }
-                        if (single) {
-                            h[x * H + col] = hv - alpha * (dh + lambda * hv);
-                            const float zv = z[x * H + col];
-                            z[x * H + col] = zv - alpha * (lambda * zv);
-                        } else GH[occ0 * H + col] = dh;
+                        if (single) h[x * H + col] = hv - alpha * (dh + lambda * hv);
+                        else GH[occ0 * H + col] = dh;
                     }
                 }
             }

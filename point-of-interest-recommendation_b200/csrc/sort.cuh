@@ -60,21 +60,21 @@ __global__ void k_scan_add(uint32_t* out, const uint32_t* block_off, int64_t n) 
     if (idx < n) out[idx] += block_off[idx / SCAN_TILE];
 }
 
-// up to SCAN_SINGLE_MAX elements in ONE launch: thread t owns the contiguous run [t * ipt, (t + 1) * ipt), sums it, the
-// 1024 run totals are scanned in the block, the run is rewritten with its exclusive prefixes (out may alias in)
+// up to SCAN_SINGLE_MAX elements in ONE launch.  Warp w owns the contiguous run [w * rpw * 32, (w + 1) * rpw * 32) and walks
+// it in rows of 32 (coalesced): pass 1 adds the rows up to the warp's total, the 32 warp totals are scanned in the block,
+// pass 2 walks the rows again (L1 / L2 hits) writing exclusive prefixes with a running carry.  out may alias in.
 constexpr int SCAN_SINGLE_MAX = 65536;
 __global__ void __launch_bounds__(1024)
 k_scan_single(const uint32_t* in, uint32_t* out, int n, uint32_t* total_out) {
     __shared__ uint32_t warp_tot[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ipt = (n + 1023) / 1024;
-    const int b0 = tid * ipt, b1 = min(b0 + ipt, n);
+    const int rpw = (n + 1023) / 1024;                     // rows of 32 per warp
+    const int b0 = wid * rpw * 32;
     uint32_t sum = 0;
-    for (int i = b0; i < b1; ++i) sum += in[i];
-    uint32_t inc = sum;
+    for (int r = 0; r < rpw; ++r) { const int i = b0 + r * 32 + lane; if (i < n) sum += in[i]; }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) warp_tot[wid] = inc;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) warp_tot[wid] = sum;
     __syncthreads();
     if (wid == 0) {
         uint32_t t = warp_tot[lane], ti = t;
@@ -84,8 +84,16 @@ k_scan_single(const uint32_t* in, uint32_t* out, int n, uint32_t* total_out) {
         if (lane == 31 && total_out) *total_out = ti;
     }
     __syncthreads();
-    uint32_t excl = warp_tot[wid] + inc - sum;
-    for (int i = b0; i < b1; ++i) { const uint32_t v = in[i]; out[i] = excl; excl += v; }
+    uint32_t carry = warp_tot[wid];
+    for (int r = 0; r < rpw; ++r) {
+        const int i = b0 + r * 32 + lane;
+        const uint32_t v = i < n ? in[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (i < n) out[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
 }
 
 // out may alias in.  total_dev (optional) receives the sum of all elements.

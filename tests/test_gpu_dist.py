@@ -69,7 +69,8 @@ def test_sharded_checkpoint_roundtrip_and_py2_file(engine, tmp_path):
     arrays = read_checkpoint(os.path.join(G, "ref_ckpt_py2_protocol2.pkl"))
     n_item2, d2, D2 = arrays[2].shape[0] - 1, arrays[2].shape[1], arrays[3].shape[0] - 1
     tes = [[n_item2]] * 2
-    m2 = OboSpatialGru([[[0, n_item2]] * 2][0], [tes, [[0]] * 2, tes], [[[D2, D2]] * 2, [[D2]] * 2, [[D2, D2]] * 2], [0.01, 0.001], 2, n_item2,
+    tra = [[0, n_item2]] * 2
+    m2 = OboSpatialGru([tra, [[1, 0]] * 2, tra], [tes, [[0]] * 2, tes], [[[D2, D2]] * 2, [[D2]] * 2, [[D2, D2]] * 2], [0.01, 0.001], 2, n_item2,
                        [D2, 0.2], d2, d2)
     load_checkpoint(m2, os.path.join(G, "ref_ckpt_py2_protocol2.pkl"))
     for k, a_ in zip(("loss_weight", "wd", "lt", "di", "ui", "wh", "bi", "vs", "bs"), arrays):
