@@ -26,7 +26,7 @@ st = dict(g=rs.uniform(-0.5, 0.5, (I + 1, H)).astype(np.float32), h=rs.uniform(-
 coords = np.zeros((I + 1, 2), dtype=np.float32)
 coords[:I, 0] = rs.uniform(1.22, 1.47, I); coords[:I, 1] = rs.uniform(103.60, 104.04, I)
 P = rs.randint(0, I, (steps, world * Bu, L)).astype(np.int32); Q = rs.randint(0, I, (steps, world * Bu, L, K)).astype(np.int32)
-A, LAM = 0.01, 0.001
+A, LAM = 0.001, 0.001          # small step: the summed a, b gradient of a batch is large (no normalisation, as Bpr)
 m = ShardedGeoIE([A, LAM], I, H, st, coords, max_users=Bu, seq_len=L, n_neg=K, device=lr)
 dev = torch.device("cuda", lr)
 losses = []
@@ -44,7 +44,7 @@ if rank == 0:
         want = ref.train_batch(torch.as_tensor(P[s], device=dev), torch.as_tensor(Q[s], device=dev))
         e = abs(losses[s] - want) / abs(want)
         print("step %d loss mg=%.6f ref=%.6f rel.err=%.2e" % (s, losses[s], want, e))
-        ok &= e < 1e-5
+        ok &= e < 1e-5 and np.isfinite(want)
     def rel(a, b): return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
     errs = {k: rel(unshard_rows(shards[k], I + 1), getattr(ref, k).get_value()) for k in "ghz"}
     a, b = m.a_b()
