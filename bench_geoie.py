@@ -10,6 +10,9 @@ import numpy as np
 import bench as B0
 
 ALGO = 416148.0
+# The reference's alpha = 0.01 is a per-user step; a mini-batch sums the users' gradients into the two shared scalars a, b
+# without normalisation (Bpr's rule), so the batch runs use alpha / 128 (with 0.01 a 128-user step overshoots into NaN).
+ALPHA_C4 = B0.ALPHA / 128.0
 
 
 def _data(cfg, n_users, seed=123):
@@ -56,7 +59,7 @@ def run_reference(args):
     for s in range(warm + steps):
         users = np.arange(s * cb, (s + 1) * cb)
         t_ = time.perf_counter()
-        state, n_ci = cpu_step(OM, state, ds, users, B0.ALPHA, B0.LAM)
+        state, n_ci = cpu_step(OM, state, ds, users, ALPHA_C4, B0.LAM)
         dt = time.perf_counter() - t_
         if s >= warm:
             ts.append(dt); done += n_ci
@@ -96,10 +99,10 @@ def run_ours(args):
     st = synth.init_mf_state("geoie", 8, I, d)
     tes = [[I]]
     if world == 1:
-        model = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [B0.ALPHA, B0.LAM], 8, I, d, d, None, init=st, coords=coords, device=local_rank)
+        model = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [ALPHA_C4, B0.LAM], 8, I, d, d, None, init=st, coords=coords, device=local_rank)
     else:
         from poi_b200.dist import ShardedGeoIE
-        model = ShardedGeoIE([B0.ALPHA, B0.LAM], I, d, st, coords, max_users=Bu, seq_len=L, n_neg=K, device=local_rank)
+        model = ShardedGeoIE([ALPHA_C4, B0.LAM], I, d, st, coords, max_users=Bu, seq_len=L, n_neg=K, device=local_rank)
     eng = model.engine
     mine = lambda s: slice(s * Bg + rank * Bu, s * Bg + (rank + 1) * Bu)  # this rank's users of step s
     res = [(torch.as_tensor(P[mine(s)], device=dev), torch.as_tensor(Q[mine(s)], device=dev)) for s in range(n_steps)]
@@ -165,10 +168,10 @@ def run_ours(args):
     if not args.no_parity and world == 1:
         from oracle import models as OM
         nb = 4
-        m2 = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [B0.ALPHA, B0.LAM], n_user, I, d, d, None, init=st, coords=coords, device=local_rank)
+        m2 = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [ALPHA_C4, B0.LAM], n_user, I, d, d, None, init=st, coords=coords, device=local_rank)
         got = m2.train_batch(res[0][0][:nb].contiguous(), res[0][1][:nb].contiguous())
         ref = {k: np.asarray(v, dtype=np.float64) for k, v in st.items()}
-        want, ref = OM.geoie_train_batch_k(ref, np.arange(nb), P[:nb], Q[:nb], coords.astype(np.float64), B0.ALPHA, B0.LAM)
+        want, ref = OM.geoie_train_batch_k(ref, np.arange(nb), P[:nb], Q[:nb], coords.astype(np.float64), ALPHA_C4, B0.LAM)
         rows = np.unique(np.concatenate((P[:nb].ravel(), Q[:nb, 1:].ravel())))
 
         def el(a, b):
@@ -187,7 +190,7 @@ def run_ours(args):
         ts = []
         for s in range(3):
             t_ = time.perf_counter()
-            state, n_ci = cpu_step(OM, state, ds, np.arange(s * 8, s * 8 + 8), B0.ALPHA, B0.LAM)
+            state, n_ci = cpu_step(OM, state, ds, np.arange(s * 8, s * 8 + 8), ALPHA_C4, B0.LAM)
             ts.append(time.perf_counter() - t_)
         cpu = {"value": n_ci * 2 / sum(ts[1:]), "unit": B0.UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "2 steps x 8 users of the %d-user step (torch-CPU oracle, float64, all cores)" % Bu}

@@ -352,8 +352,8 @@ int poi_geoie_train(poi_engine* e, const poi_geoie_params* params, int32_t uidx,
  * every term from pre-update values, g / h / z rows duplicate-summed over the batch, a and b dense SGD, t untouched (its
  * gradient is exactly zero).  P [Bu x L] POI sequences WITHOUT padding (2 <= L <= 33), Q [Bu x L x K] negatives (position 0
  * unused), device resident (on_host = 0) or host memory copied inside the call (on_host = 1); coords_dev float
- * [n_rows x 2] = lat, lon: the pairwise distances the reference's driver precomputes (Load_Data_GeoIE.py:143-156) are
- * recomputed on the fly.  *loss_host = sum log sigmoid(sp - sq). */
+ * [n_rows x 4] = lat, lon (degrees), cos(lat), 0: the pairwise distances the reference's driver precomputes
+ * (Load_Data_GeoIE.py:143-156) are recomputed on the fly.  *loss_host = sum log sigmoid(sp - sq). */
 int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* params, const int32_t* P, const int32_t* Q,
                             const float* coords_dev, int32_t Bu, int32_t L, int32_t K, int32_t on_host,
                             float alpha, float lambda, double* loss_host);

@@ -538,9 +538,9 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
     POI_TRY(arena_get(e, (size_t)n * d, &SL));
     POI_TRY(arena_get(e, (size_t)n * d, &GU));
     POI_TRY(arena_get(e, (size_t)n * d, &GL));
-    size_t tma_smem = 0;
-    const bool use_tma = prme_score_tma_ok(d4, K, &tma_smem) && !getenv("POI_PRME_NO_TMA");
-    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * (use_tma ? 2 : 8));
+    size_t tma_smem = 0; int tma_nst = 0;
+    const bool use_tma = prme_score_tma_ok(d4, K, &tma_smem, &tma_nst) && !getenv("POI_PRME_NO_TMA");
+    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * (use_tma ? 1 : 8));
     POI_TRY(arena_get(e, (size_t)blocks, &part));
     POI_TRY(arena_get(e, 1, &out_dev));
     const size_t smem = (size_t)8 * 2 * d4 * sizeof(float4);
@@ -552,7 +552,7 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
     POI_CAT(e, CAT_MF, 0, 0.5 * algo);
     if (use_tma) {
         POI_CK(e, cudaFuncSetAttribute(k_prme_score_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
-        POI_LAUNCH(e, k_prme_score_tma, blocks, 256, tma_smem, du, dp, ds_, d4, b, (int)threshold, (float)cw, KP, KS, SL, GU, GL, part);
+        POI_LAUNCH(e, k_prme_score_tma, blocks, PRME_TMA_THREADS, tma_smem, du, dp, ds_, d4, b, tma_nst, (int)threshold, (float)cw, KP, KS, SL, GU, GL, part);
     }
 #define PRME_BK(NCH)                                                                                                        \
     do {                                                                                                                    \
@@ -643,7 +643,7 @@ extern "C" int poi_geoie_train_batch_k(poi_engine* e, const poi_geoie_params* pr
     const int64_t n_occ = (int64_t)Bu * n * C, n_g = (int64_t)Bu * n;
     if (n_occ >= (int64_t)1 << 31) POI_FAIL(e, "batch too large");
     GeoBatch gb; gb.Bu = Bu; gb.L = L; gb.K = K;
-    gb.coords_g = gb.coords_h = reinterpret_cast<const float2*>(coords_dev);
+    gb.coords_g = gb.coords_h = reinterpret_cast<const float4*>(coords_dev);
     if (on_host) {
         const void* hs[2] = {P, Q}; size_t bs[2] = {(size_t)Bu * L * 4, (size_t)Bu * L * K * 4}; void* dv[2];
         POI_TRY(upload_many(e, hs, bs, 2, dv));

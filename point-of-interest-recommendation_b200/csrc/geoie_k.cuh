@@ -29,8 +29,8 @@ struct GeoBatch {
     const int32_t* P;                 // [Bu x L]       row of g (and of coords_g) for every position
     const int32_t* Ph;                // [Bu x L]       row of h / z (and of coords_h) for every position; == P on one GPU
     const int32_t* Q;                 // [Bu x L x K]   rows of h / z (and of coords_h) of the negatives (position 0 unused)
-    const float2* coords_g;           // lat, lon (degrees) indexed like P
-    const float2* coords_h;           // lat, lon indexed like Ph / Q; == coords_g on one GPU
+    const float4* coords_g;           // (lat, lon, cos(lat), 0) in degrees, indexed like P
+    const float4* coords_h;           // the same, indexed like Ph / Q; == coords_g on one GPU
     int Bu, L, K;
     // (multi-GPU: the tables are compact copies of the rows the batch touches and P / Ph / Q hold SLOTS, mf_mg.cuh)
 };
@@ -48,13 +48,27 @@ __global__ void k_geoie_keys(GeoBatch gb, uint32_t* __restrict__ keys_h, uint32_
     if (o < (int64_t)gb.Bu * n) { const int j = (int)(o % n), b = (int)(o / n); keys_g[o] = (uint32_t)gb.P[(size_t)b * gb.L + j]; }
 }
 
-__device__ __forceinline__ float geo_dist_km(float lat1, float lon1, float coslat1, float lat2, float lon2) {
+// sin x: odd polynomial to x^9 for |x| < 0.5 (relative error < 2e-9: the half-angles of POIs a few km -- or a few thousand
+// km -- apart), the library routine beyond.  The hardware approximation (__sinf, absolute error 2^-21) is useless here: the
+// angles are ~1e-3 rad and it is their RELATIVE error that sets the distance.
+__device__ __forceinline__ float geo_sin(float x) {
+    if (fabsf(x) >= 0.5f) return sinf(x);
+    const float x2 = x * x;
+    return x * (1.f + x2 * (-1.f / 6.f + x2 * (1.f / 120.f + x2 * (-1.f / 5040.f + x2 * (1.f / 362880.f)))));
+}
+// asin x for x in [0, 1]: odd series to x^9 below 0.25 (relative error < 1e-7), library routine beyond
+__device__ __forceinline__ float geo_asin(float x) {
+    if (x >= 0.25f) return asinf(x);
+    const float x2 = x * x;
+    return x * (1.f + x2 * (1.f / 6.f + x2 * (3.f / 40.f + x2 * (15.f / 336.f + x2 * (105.f / 3456.f)))));
+}
+__device__ __forceinline__ float geo_dist_km(float lat1, float lon1, float coslat1, float lat2, float lon2, float coslat2) {
     // Load_Data_GeoIE.py:28-42: 12742 asin(sqrt(c)), c = sin^2(dlat/2) + cos(lat1) cos(lat2) sin^2(dlon/2) -- the form the
     // loader's docstring states is equivalent to its (1 - cos)/2 expression, without the cancellation in float32
     const float p = 0.017453292519943295f;
-    const float sa = sinf((lat1 - lat2) * p * 0.5f), sb = sinf((lon1 - lon2) * p * 0.5f);
-    const float c = sa * sa + coslat1 * cosf(lat2 * p) * sb * sb;
-    return 12742.0f * asinf(sqrtf(fminf(c, 1.0f)));
+    const float sa = geo_sin((lat1 - lat2) * p * 0.5f), sb = geo_sin((lon1 - lon2) * p * 0.5f);
+    const float c = sa * sa + coslat1 * coslat2 * sb * sb;
+    return 12742.0f * geo_asin(sqrtf(fminf(c, 1.0f)));
 }
 
 // dots of both candidates of this warp against history row `lane`; HS = padded row stride of Gs
@@ -73,12 +87,15 @@ __device__ __forceinline__ void geo_dots2(const float* __restrict__ Gs, int HS, 
 
 // lane j: weight pieces for candidate at (clat, clon): pw = d^b, lg = ln d (0 when d = 0, Theano's switch in the gradient
 // of pow).  Masked lanes (j > i) return 0.
-__device__ __forceinline__ void geo_weight(bool on, float hlat, float hlon, float hcos, float2 cc, float b, float& pw, float& pwlog) {
+__device__ __forceinline__ void geo_weight(bool on, float hlat, float hlon, float hcos, float4 cc, float b, float& pw, float& pwlog) {
     pw = 0.f; pwlog = 0.f;
     if (!on) return;
-    const float dkm = geo_dist_km(hlat, hlon, hcos, cc.x, cc.y);
-    pw = powf(dkm, b);
-    pwlog = dkm == 0.f ? 0.f : pw * logf(dkm);
+    const float dkm = geo_dist_km(hlat, hlon, hcos, cc.x, cc.y, cc.z);
+    if (dkm == 0.f) { pw = b > 0.f ? 0.f : (b == 0.f ? 1.f : INFINITY); return; }      // 0 ** b as powf gives it; log part 0
+    // d ** b = 2 ** (b log2 d) on the special-function unit: absolute error 2^-22 on log2 d, i.e. ~1e-7 relative on d ** b
+    const float l2 = __log2f(dkm);
+    pw = exp2f(b * l2);
+    pwlog = pw * l2 * 0.6931471805599453f;
 }
 
 template <int NCOL>          // columns per thread: H <= 256 * NCOL
@@ -112,7 +129,7 @@ k_geoie_batch_k(float* __restrict__ g, float* __restrict__ h, const double* __re
         }
         float hlat = 0.f, hlon = 0.f, hcos = 1.f;
         const int32_t* Phu = gb.Ph + (size_t)u * gb.L;
-        if (lane < n) { const float2 cc = gb.coords_g[Pu[lane]]; hlat = cc.x; hlon = cc.y; hcos = cosf(cc.x * 0.017453292519943295f); }
+        if (lane < n) { const float4 cc = gb.coords_g[Pu[lane]]; hlat = cc.x; hlon = cc.y; hcos = cc.z; }
         __syncthreads();
         float Gcol[NCOL][GEO_MAXN], dG[NCOL][GEO_MAXN];
 #pragma unroll
@@ -206,6 +223,7 @@ k_geoie_batch_k(float* __restrict__ g, float* __restrict__ h, const double* __re
                             float dh = 0.f;
 #pragma unroll
                             for (int j4 = 0; j4 < GEO_MAXN / 4; ++j4) {
+                                if (4 * j4 > i) break;                   // rows j > i carry a zero coefficient
                                 const float4 cf = cf4[j4];
                                 dG[q][4 * j4 + 0] = fmaf(cf.x, hv, dG[q][4 * j4 + 0]); dh = fmaf(cf.x, Gcol[q][4 * j4 + 0], dh);
                                 dG[q][4 * j4 + 1] = fmaf(cf.y, hv, dG[q][4 * j4 + 1]); dh = fmaf(cf.y, Gcol[q][4 * j4 + 1], dh);
@@ -238,7 +256,8 @@ k_geoie_batch_k(float* __restrict__ g, float* __restrict__ h, const double* __re
                         float dh = 0.f;
 #pragma unroll
                         for (int j = 0; j < GEO_MAXN; ++j) {
-                            const float cf = -E * wP[j] * (j <= i ? 1.f : 0.f);
+                            if (j > i) break;
+                            const float cf = -E * wP[j];
                             dG[q][j] = fmaf(cf, hv, dG[q][j]); dh = fmaf(cf, Gcol[q][j], dh);
                         }
                         if (single) h[x * H + col] = hv - alpha * (dh + lambda * hv);

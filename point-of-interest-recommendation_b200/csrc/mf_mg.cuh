@@ -20,8 +20,8 @@
 #pragma once
 #include "mg_step.cuh"
 
-__global__ void k_mf_gather_coords(const float2* __restrict__ coords, const uint32_t* __restrict__ uniq, const uint32_t* __restrict__ n_dev,
-                                   int64_t cap, float2* __restrict__ out) {
+__global__ void k_mf_gather_coords(const float4* __restrict__ coords, const uint32_t* __restrict__ uniq, const uint32_t* __restrict__ n_dev,
+                                   int64_t cap, float4* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap && i < *n_dev) out[i] = coords[uniq[i]];
 }
@@ -140,7 +140,7 @@ extern "C" int poi_geoie_step_mg(poi_engine* e, const poi_geoie_params* prm, con
     POI_CK(e, cudaMemsetAsync(err, 0, 4, e->stream));
 
     GeoBatch gg; gg.Bu = Bu; gg.L = L; gg.K = K;                         // global ids
-    gg.coords_g = gg.coords_h = reinterpret_cast<const float2*>(coords_dev);
+    gg.coords_g = gg.coords_h = reinterpret_cast<const float4*>(coords_dev);
     if (on_host) {
         const void* hs[2] = {P, Q}; size_t bs[2] = {(size_t)Bu * L * 4, (size_t)Bu * L * K * 4}; void* dv[2];
         POI_TRY(upload_many(e, hs, bs, 2, dv));
@@ -159,7 +159,7 @@ extern "C" int poi_geoie_step_mg(poi_engine* e, const poi_geoie_params* prm, con
     // ---- every owner has applied the previous step -> gather the compact tables from the owners' shards ----
     POI_CAT(e, CAT_OTHER, 0, 0);
     POI_LAUNCH(e, k_mg_wait, 1, 32, 0, pr->flags[me] + W, W, (uint32_t)(step - 1), err, timeout_ns, 100);
-    float *cg = nullptr, *ch = nullptr, *cz = nullptr; float2 *xg = nullptr, *xh = nullptr;
+    float *cg = nullptr, *ch = nullptr, *cz = nullptr; float4 *xg = nullptr, *xh = nullptr;
     POI_TRY(arena_get(e, (size_t)n_g * H, &cg)); POI_TRY(arena_get(e, (size_t)n_occ * H, &ch)); POI_TRY(arena_get(e, (size_t)n_occ * H, &cz));
     POI_TRY(arena_get(e, (size_t)n_g, &xg)); POI_TRY(arena_get(e, (size_t)n_occ, &xh));
     POI_TRY(mf_gather_sharded(e, pr->shard[0], W, H, seg_g.uniq, seg_g.n_unique, n_g, cg));

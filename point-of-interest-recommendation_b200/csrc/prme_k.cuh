@@ -290,29 +290,36 @@ k_prme_apply(SegList seg, const float* __restrict__ du, float* __restrict__ dp, 
 // ------------------------------------------------------------------------------------------------------------------
 // Phase A with the rows staged by TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): the
 // 2K + 4 rows of a check-in (du[u], ds[prev], dp[x_j], ds[x_j], j = 0..K) are one 1 KB-per-row burst into a shared-memory
-// stage; two stages per CTA, so the rows of check-in i+1 stream in while check-in i is scored out of shared memory --
-// no register holds an in-flight row, and every row is read from L2 / HBM exactly once (the register version re-reads
-// the rows in its second pass).  Persistent CTAs, two per SM.  Used when 256 % (d/4) == 0 and two stages fit.
+// stage; as many stages as fit in ~200 KB (4 at K = 20, d = 256), so the rows of check-in i + nst - 1 stream in while
+// check-in i is scored out of shared memory -- no register holds an in-flight row, and every row is read from L2 / HBM
+// exactly once (the register version re-reads the rows in its second pass).  Persistent CTAs of 16 warps, one per SM
+// (round-2 ncu of the 2-stage / 2-CTA version: barrier-stall bound, 29 % issue slots, 1.4 TB/s: a request had ONE ~1 us
+// iteration to land).  Used when 512 % (d/4) == 0 and at least two stages fit.
 // Stage layout (rows of d floats): 0 du[u] | 1 ds[prev] | 2 .. K+2 dp[x_j] | K+3 .. 2K+3 ds[x_j].
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int PRME_TMA_THREADS = 512;
+constexpr int PRME_TMA_MAXST = 8;
+
+__global__ void __launch_bounds__(PRME_TMA_THREADS)
 k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, const float* __restrict__ ds, int d4, PrmeBatchIdx b,
-                 int thd, float cw, float* __restrict__ KP, float* __restrict__ KS, float* __restrict__ SL,
+                 int nst, int thd, float cw, float* __restrict__ KP, float* __restrict__ KS, float* __restrict__ SL,
                  float* __restrict__ GU, float* __restrict__ GL, double* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char prme_tma_smem[];
-    __shared__ uint64_t bar[2];
+    __shared__ uint64_t bar[PRME_TMA_MAXST];
     __shared__ float sD[PRME_MAXK + 1], sg[PRME_MAXK + 1];
-    __shared__ double sloss[8];
+    __shared__ double sloss[PRME_TMA_THREADS / 32];
+    constexpr int NW = PRME_TMA_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = b.K, R = K + 2, NR = 2 * K + 4, d = d4 * 4;
     const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = row_bytes * (uint32_t)NR;
-    float4* red = reinterpret_cast<float4*>(prme_tma_smem + 2 * (size_t)stage_bytes);     // [ngrp][2][d4]
-    const int ngrp = 256 / d4;
-    if (tid == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::fence_barrier_init(); }
+    float4* red = reinterpret_cast<float4*>(prme_tma_smem + (size_t)nst * stage_bytes);   // [ngrp][2][d4]
+    const int ngrp = PRME_TMA_THREADS / d4;
+    if (tid == 0) { for (int s = 0; s < nst; ++s) tc::mbar_init(&bar[s], 1); tc::fence_barrier_init(); }
     __syncthreads();
     // Warp 0 issues the bulk copies: lane 0 arms the stage's barrier with the byte count, then lane l sends rows l, l + 32,
-    // ... (one instruction per row).  The source pointers of a check-in are looked up one iteration AHEAD of their use
-    // (src_next), so that the index loads are off the critical path.
+    // ... (one instruction per row).  nst stages: the rows of check-in i + nst - 1 are requested while check-in i is scored,
+    // so a request has nst - 1 iterations to land (HBM latency ~ 2 us, an iteration ~ 1 us).  The source pointers of a
+    // check-in are looked up one iteration AHEAD of their use (src_next): the index loads are off the critical path.
     constexpr int MAXRPL = (2 * PRME_MAXK + 4 + 31) / 32;       // rows per lane, upper bound
     const int rpl = (NR + 31) / 32;
     const float* src_next[MAXRPL];
@@ -334,7 +341,7 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
     };
     auto issue = [&](int s) {
         if (warp != 0) return;
-        tc::fence_async_smem();                        // generic-proxy reads of this stage (two iterations ago) before async writes
+        tc::fence_async_smem();                        // generic-proxy reads of this stage (nst iterations ago) before async writes
         const uint32_t barp = tc::smem_u32(&bar[s]);
         if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barp), "r"(stage_bytes) : "memory");
         __syncwarp();
@@ -350,19 +357,24 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
     double loss_acc = 0.0;                              // thread k (1 <= k <= K) accumulates its own negative's terms
     int it = 0;
     const int G0 = (int)gridDim.x;
-    if ((int)blockIdx.x < b.N) { lookup(blockIdx.x); issue(0); lookup(blockIdx.x + G0); }
+    // prologue: check-ins 0 .. nst-2 of this CTA in flight, pointers of check-in nst-1 ready
+    for (int s = 0; s < nst - 1; ++s) {
+        const int i0 = blockIdx.x + s * G0;
+        if (i0 < b.N) { lookup(i0); issue(s); }
+    }
+    lookup(blockIdx.x + (nst - 1) * G0);
     for (int i = blockIdx.x; i < b.N; i += G0, ++it) {
-        const int s = it & 1;
-        if (i + G0 < b.N) { issue(s ^ 1); lookup(i + 2 * G0); }
+        const int s = it % nst;
+        if (i + (nst - 1) * G0 < b.N) { issue((it + nst - 1) % nst); lookup(i + nst * G0); }
         const bool far = b.gap[i] > thd;
         const float w = sqrtf(sqrtf(1.0f + b.dist[i]));
         const float cp = far ? 1.f : w * cw, cs = far ? 0.f : w * (1.f - cw);
-        tc::mbar_wait(&bar[s], (uint32_t)(it >> 1) & 1u);
+        tc::mbar_wait(&bar[s], (uint32_t)(it / nst) & 1u);
         const float4* st = reinterpret_cast<const float4*>(prme_tma_smem + (size_t)s * stage_bytes);
         const float4* U = st; const float4* SLr = st + d4;
         const float4* DP = st + 2 * (size_t)d4; const float4* DS = st + (size_t)(K + 3) * d4;
         // ---- pass 1: D(x_j), one warp per candidate ----
-        for (int j = warp; j <= K; j += 8) {
+        for (int j = warp; j <= K; j += NW) {
             float acc = 0.f;
             for (int c = lane; c < d4; c += 32) {
                 const float4 a = f4sub(U[c], DP[(size_t)j * d4 + c]);
@@ -405,17 +417,19 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
         }
         __syncthreads();          // stage s, red, sD, sg are free again
     }
-    // block loss: lanes in a fixed tree, then the 8 warps in order
+    // block loss: lanes in a fixed tree, then the warps in order
     loss_acc = warp_sum_d(loss_acc);
     if (lane == 0) sloss[warp] = loss_acc;
     __syncthreads();
-    if (tid == 0) { double t = 0.0; for (int ww = 0; ww < 8; ++ww) t += sloss[ww]; part[blockIdx.x] = t; }
+    if (tid == 0) { double t = 0.0; for (int ww = 0; ww < NW; ++ww) t += sloss[ww]; part[blockIdx.x] = t; }
 }
 
-static bool prme_score_tma_ok(int d4, int K, size_t* smem) {
-    const size_t stage = (size_t)(2 * K + 4) * d4 * 16;
-    *smem = 2 * stage + (size_t)2 * 256 * 16 + 128;
-    return d4 >= 1 && d4 <= 256 && 256 % d4 == 0 && 2 * d4 <= 256 && *smem <= 110 * 1024;
+// stages that fit beside the reduction scratch in ~200 KB; the path needs >= 2 and d/4 dividing the block size
+static bool prme_score_tma_ok(int d4, int K, size_t* smem, int* nst) {
+    const size_t stage = (size_t)(2 * K + 4) * d4 * 16, scratch = (size_t)2 * PRME_TMA_THREADS * 16 + 128;
+    int n = (int)std::min<size_t>(PRME_TMA_MAXST, (200 * 1024 - scratch) / stage);
+    *nst = n; *smem = (size_t)n * stage + scratch;
+    return d4 >= 1 && d4 <= 256 && PRME_TMA_THREADS % d4 == 0 && 2 * d4 <= PRME_TMA_THREADS && n >= 2;
 }
 
 // fixed-order sum of n doubles by one warp: lane l adds part[l], part[l + 32], ... in order, then a fixed shuffle tree

@@ -371,9 +371,8 @@ class ShardedGeoIE:
         self.n_rows, self.H = n_item + 1, n_hidden
         self._alpha, self._lambda = float(alpha_lambda[0]), float(alpha_lambda[1])
         self._ab = torch.tensor([float(init["a"]), float(init["b"])], dtype=torch.float64, device=dev)
-        c = np.zeros((self.n_rows, 2), dtype=np.float32)
-        cc = np.asarray(coords, dtype=np.float32); c[:min(len(cc), self.n_rows)] = cc[:self.n_rows]
-        self.coords = Shared(c, "float32", dev)
+        from .public.GeoIE import coords_table
+        self.coords = Shared(coords_table(coords, self.n_rows), "float32", dev)
         n = seq_len - 1
         cap = (max_users * n, max_users * n * (n_neg + 1))
         own, handles = {}, {}

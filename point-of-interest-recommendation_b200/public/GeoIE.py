@@ -94,6 +94,16 @@ class GeoIE:
                                        dist_pos, dist_neg, msk, self._alpha, self._lambda)
 
 
+def coords_table(coords, n_rows):
+    """[n_rows x 4] float32 = (lat, lon, cos(lat), 0) -- the layout the mini-batch kernel reads (cos evaluated here, in float64)."""
+    c = np.zeros((n_rows, 4), dtype=np.float32)
+    cc = np.asarray(coords, dtype=np.float64)
+    m = min(len(cc), n_rows)
+    c[:m, 0] = cc[:m, 0]; c[:m, 1] = cc[:m, 1]
+    c[:, 2] = np.cos(c[:, 0].astype(np.float64) * 0.017453292519943295)
+    return c
+
+
 class GeoIEBatch(GeoIE):
     """Mini-batch GeoIE with K negatives per target -- the throughput mode (BASELINE.json C4).  EXTENSION SEMANTICS (the
     reference trains one user per call with one negative): `train_batch(P, Q)` takes the POI sequences of a batch of users
@@ -103,10 +113,7 @@ class GeoIEBatch(GeoIE):
 
     def __init__(self, *args, coords=None, **kw):
         super(GeoIEBatch, self).__init__(*args, **kw)
-        c = np.zeros((self.g.t.shape[0], 2), dtype=np.float32)
-        cc = np.asarray(coords, dtype=np.float32)
-        c[:cc.shape[0]] = cc[:c.shape[0]]
-        self.coords = Shared(c, "float32", self.engine.torch_device)
+        self.coords = Shared(coords_table(coords, self.g.t.shape[0]), "float32", self.engine.torch_device)
 
     def train_batch(self, P, Q):
         return self.engine.geoie_train_batch_k(self.g.t, self.h.t, self.z.t, self.t.t, self._ab, P, Q, self.coords.t,

@@ -43,6 +43,6 @@ else:
     P, Q, coords = bench_geoie._data(cfg, Bu * args.steps)
     st = synth.init_mf_state("geoie", 8, I, d)
     tes = [[I]]
-    m = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [B0.ALPHA, B0.LAM], 8, I, d, d, None, init=st, coords=coords, device=0)
+    m = GeoIEBatch([tes, tes, [[1]], [[1]]], [tes, tes], [bench_geoie.ALPHA_C4, B0.LAM], 8, I, d, d, None, init=st, coords=coords, device=0)
     for s in range(args.steps):
         print("step", s, m.train_batch(torch.as_tensor(P[s * Bu:(s + 1) * Bu], device=dev), torch.as_tensor(Q[s * Bu:(s + 1) * Bu], device=dev)))
