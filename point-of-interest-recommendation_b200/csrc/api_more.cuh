@@ -540,7 +540,7 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
     POI_TRY(arena_get(e, (size_t)n * d, &GL));
     size_t tma_smem = 0; int tma_nst = 0;
     const bool use_tma = prme_score_tma_ok(d4, K, &tma_smem, &tma_nst) && !getenv("POI_PRME_NO_TMA");
-    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * (use_tma ? 1 : 8));
+    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * (use_tma ? 2 : 8));
     POI_TRY(arena_get(e, (size_t)blocks, &part));
     POI_TRY(arena_get(e, 1, &out_dev));
     const size_t smem = (size_t)8 * 2 * d4 * sizeof(float4);

@@ -76,13 +76,16 @@ __device__ __forceinline__ void geo_dots2(const float* __restrict__ Gs, int HS, 
                                           const float* __restrict__ h1, float& d0, float& d1) {
     const float4* g4 = reinterpret_cast<const float4*>(Gs + (size_t)lane * HS);
     const float4* a4 = reinterpret_cast<const float4*>(h0); const float4* b4 = reinterpret_cast<const float4*>(h1);
-    float x0 = 0.f, x1 = 0.f;
+    // four independent partial sums per candidate (one per float4 component): eight FMA chains in flight per lane -- with
+    // one or two CTAs per SM the FMA latency, not the issue rate, bounded the single-accumulator version (ncu: "wait" stalls)
+    float4 x0 = f4zero(), x1 = f4zero();
+#pragma unroll 4
     for (int k = 0; k < (H >> 2); ++k) {
         const float4 g = g4[k], a = a4[k], b = b4[k];
-        x0 = fmaf(g.x, a.x, x0); x0 = fmaf(g.y, a.y, x0); x0 = fmaf(g.z, a.z, x0); x0 = fmaf(g.w, a.w, x0);
-        x1 = fmaf(g.x, b.x, x1); x1 = fmaf(g.y, b.y, x1); x1 = fmaf(g.z, b.z, x1); x1 = fmaf(g.w, b.w, x1);
+        x0.x = fmaf(g.x, a.x, x0.x); x0.y = fmaf(g.y, a.y, x0.y); x0.z = fmaf(g.z, a.z, x0.z); x0.w = fmaf(g.w, a.w, x0.w);
+        x1.x = fmaf(g.x, b.x, x1.x); x1.y = fmaf(g.y, b.y, x1.y); x1.z = fmaf(g.z, b.z, x1.z); x1.w = fmaf(g.w, b.w, x1.w);
     }
-    d0 = x0; d1 = x1;
+    d0 = (x0.x + x0.y) + (x0.z + x0.w); d1 = (x1.x + x1.y) + (x1.z + x1.w);
 }
 
 // lane j: weight pieces for candidate at (clat, clon): pw = d^b, lg = ln d (0 when d = 0, Theano's switch in the gradient
@@ -220,16 +223,17 @@ k_geoie_batch_k(float* __restrict__ g, float* __restrict__ h, const double* __re
                         for (int cw = 0; cw < nc; ++cw) {
                             const float hv = Ht[(size_t)cw * H + col];
                             const float4* cf4 = reinterpret_cast<const float4*>(coef + cw * 32);
-                            float dh = 0.f;
+                            float4 dh4 = f4zero();                       // four independent chains for d h[c]
 #pragma unroll
                             for (int j4 = 0; j4 < GEO_MAXN / 4; ++j4) {
                                 if (4 * j4 > i) break;                   // rows j > i carry a zero coefficient
                                 const float4 cf = cf4[j4];
-                                dG[q][4 * j4 + 0] = fmaf(cf.x, hv, dG[q][4 * j4 + 0]); dh = fmaf(cf.x, Gcol[q][4 * j4 + 0], dh);
-                                dG[q][4 * j4 + 1] = fmaf(cf.y, hv, dG[q][4 * j4 + 1]); dh = fmaf(cf.y, Gcol[q][4 * j4 + 1], dh);
-                                dG[q][4 * j4 + 2] = fmaf(cf.z, hv, dG[q][4 * j4 + 2]); dh = fmaf(cf.z, Gcol[q][4 * j4 + 2], dh);
-                                dG[q][4 * j4 + 3] = fmaf(cf.w, hv, dG[q][4 * j4 + 3]); dh = fmaf(cf.w, Gcol[q][4 * j4 + 3], dh);
+                                dG[q][4 * j4 + 0] = fmaf(cf.x, hv, dG[q][4 * j4 + 0]); dh4.x = fmaf(cf.x, Gcol[q][4 * j4 + 0], dh4.x);
+                                dG[q][4 * j4 + 1] = fmaf(cf.y, hv, dG[q][4 * j4 + 1]); dh4.y = fmaf(cf.y, Gcol[q][4 * j4 + 1], dh4.y);
+                                dG[q][4 * j4 + 2] = fmaf(cf.z, hv, dG[q][4 * j4 + 2]); dh4.z = fmaf(cf.z, Gcol[q][4 * j4 + 2], dh4.z);
+                                dG[q][4 * j4 + 3] = fmaf(cf.w, hv, dG[q][4 * j4 + 3]); dh4.w = fmaf(cf.w, Gcol[q][4 * j4 + 3], dh4.w);
                             }
+                            const float dh = (dh4.x + dh4.y) + (dh4.z + dh4.w);
                             const size_t o = occ0 + 1 + t0 + cw;
                             const size_t x = (size_t)sx[cw];
                             if (sfl[cw]) h[x * H + col] = hv - alpha * (dh + lambda * hv);

@@ -250,24 +250,54 @@ k_prme_apply(SegList seg, const float* __restrict__ du, float* __restrict__ dp, 
             gp[k] = f4zero(); gs[k] = f4zero();
             if (c < d4) { vp[k] = ld4(dp + (r * d4 + c) * 4); vs[k] = ld4(ds + (r * d4 + c) * 4); }
         }
-        for (uint32_t q = s0; q < s1; ++q) {                           // ascending occurrence id: fixed summation order
-            const uint32_t o = seg.vals[q];
-            const uint32_t i = o / (uint32_t)R, j = o - i * (uint32_t)R;
-            if ((int)j == R - 1) {
+        // Occurrences in ascending id (fixed summation order), 32 at a time: LANE l fetches the metadata of occurrence l
+        // (record number -> scalars, user) so that those dependent loads run in parallel across the occurrences; the rows
+        // of UN occurrences are then requested together before they are consumed in order.
+        for (uint32_t base = s0; base < s1; base += 32) {
+            const int cnt = (int)min(32u, s1 - base);
+            uint32_t mi = 0; int mtype = 0; float mkp = 0.f, mks = 0.f; uint32_t mu = 0;
+            if (lane < cnt) {
+                const uint32_t o = seg.vals[base + lane];
+                mi = o / (uint32_t)R;
+                const uint32_t j = o - mi * (uint32_t)R;
+                if ((int)j == R - 1) mtype = 1;                            // the prev occurrence: gradient row GL[i] for ds, none for dp
+                else { mkp = KP[o]; mks = KS[o]; mu = (uint32_t)b.u[mi]; }
+            }
+            constexpr int UN = NCH <= 1 ? 4 : 2;                           // occurrences whose rows are in flight together
+            for (int q0 = 0; q0 < cnt; q0 += UN) {
+                float4 ra[UN][NCH], rb[UN][NCH];
+                float kp[UN], ks[UN]; int ty[UN];
 #pragma unroll
-                for (int k = 0; k < NCH; ++k) {
-                    const int c = lane + 32 * k;
-                    if (c < d4) gs[k] = f4add(gs[k], ldg4(GL + ((size_t)i * d4 + c) * 4));
+                for (int t = 0; t < UN; ++t) {
+                    const int q = min(q0 + t, cnt - 1);
+                    const uint32_t i = __shfl_sync(0xffffffffu, mi, q), uu = __shfl_sync(0xffffffffu, mu, q);
+                    ty[t] = q0 + t < cnt ? __shfl_sync(0xffffffffu, mtype, q) : 2;       // 2 = past the end
+                    kp[t] = __shfl_sync(0xffffffffu, mkp, q); ks[t] = __shfl_sync(0xffffffffu, mks, q);
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        const int c = lane + 32 * k;
+                        if (c < d4 && ty[t] != 2) {
+                            if (ty[t] == 1) rb[t][k] = ldg4(GL + ((size_t)i * d4 + c) * 4);
+                            else {
+                                ra[t][k] = ldg4(du + ((size_t)uu * d4 + c) * 4);
+                                if (ks[t] != 0.f) rb[t][k] = ldg4(SL + ((size_t)i * d4 + c) * 4);
+                            }
+                        }
+                    }
                 }
-            } else {
-                const float kp = KP[o], ks = KS[o];
-                const size_t uu = (size_t)b.u[i];
 #pragma unroll
-                for (int k = 0; k < NCH; ++k) {
-                    const int c = lane + 32 * k;
-                    if (c < d4) {
-                        gp[k] = f4fma(kp, f4sub(vp[k], ldg4(du + (uu * d4 + c) * 4)), gp[k]);
-                        if (ks != 0.f) gs[k] = f4fma(ks, f4sub(vs[k], ldg4(SL + ((size_t)i * d4 + c) * 4)), gs[k]);
+                for (int t = 0; t < UN; ++t) {
+                    if (ty[t] == 2) continue;
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        const int c = lane + 32 * k;
+                        if (c < d4) {
+                            if (ty[t] == 1) gs[k] = f4add(gs[k], rb[t][k]);
+                            else {
+                                gp[k] = f4fma(kp[t], f4sub(vp[k], ra[t][k]), gp[k]);
+                                if (ks[t] != 0.f) gs[k] = f4fma(ks[t], f4sub(vs[k], rb[t][k]), gs[k]);
+                            }
+                        }
                     }
                 }
             }
@@ -290,14 +320,15 @@ k_prme_apply(SegList seg, const float* __restrict__ du, float* __restrict__ dp, 
 // ------------------------------------------------------------------------------------------------------------------
 // Phase A with the rows staged by TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): the
 // 2K + 4 rows of a check-in (du[u], ds[prev], dp[x_j], ds[x_j], j = 0..K) are one 1 KB-per-row burst into a shared-memory
-// stage; as many stages as fit in ~200 KB (4 at K = 20, d = 256), so the rows of check-in i + nst - 1 stream in while
+// stage; as many stages as fit in ~110 KB (2 at K = 20, d = 256), so the rows of the next check-in(s) stream in while
 // check-in i is scored out of shared memory -- no register holds an in-flight row, and every row is read from L2 / HBM
-// exactly once (the register version re-reads the rows in its second pass).  Persistent CTAs of 16 warps, one per SM
-// (round-2 ncu of the 2-stage / 2-CTA version: barrier-stall bound, 29 % issue slots, 1.4 TB/s: a request had ONE ~1 us
-// iteration to land).  Used when 512 % (d/4) == 0 and at least two stages fit.
+// exactly once (the register version re-reads the rows in its second pass).  Persistent CTAs of 8 warps, two per SM.
+// Round-2 ncu (profiles/r2_ncu_full_prme_score_apply_v1.csv): barrier-stall bound, 29 % of the issue slots, 1.4 TB/s of
+// DRAM reads (L2 serves the rest: the batch touches each of the 100k rows 3.7 times).
+// Used when 256 % (d/4) == 0 and at least two stages fit.
 // Stage layout (rows of d floats): 0 du[u] | 1 ds[prev] | 2 .. K+2 dp[x_j] | K+3 .. 2K+3 ds[x_j].
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int PRME_TMA_THREADS = 512;
+constexpr int PRME_TMA_THREADS = 256;
 constexpr int PRME_TMA_MAXST = 8;
 
 __global__ void __launch_bounds__(PRME_TMA_THREADS)
@@ -427,7 +458,9 @@ k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, con
 // stages that fit beside the reduction scratch in ~200 KB; the path needs >= 2 and d/4 dividing the block size
 static bool prme_score_tma_ok(int d4, int K, size_t* smem, int* nst) {
     const size_t stage = (size_t)(2 * K + 4) * d4 * 16, scratch = (size_t)2 * PRME_TMA_THREADS * 16 + 128;
-    int n = (int)std::min<size_t>(PRME_TMA_MAXST, (200 * 1024 - scratch) / stage);
+    // two CTAs per SM (measured: 296 CTAs x 8 warps x 2 stages 0.33 ms per 16 384 check-ins; 148 CTAs x 16 warps x 4 stages
+    // 0.60 ms -- the CTA is bound by its own barrier-separated phases, so more CTAs beat deeper prefetch)
+    int n = (int)std::min<size_t>(PRME_TMA_MAXST, (110 * 1024 - scratch) / stage);
     *nst = n; *smem = (size_t)n * stage + scratch;
     return d4 >= 1 && d4 <= 256 && PRME_TMA_THREADS % d4 == 0 && 2 * d4 <= PRME_TMA_THREADS && n >= 2;
 }
