@@ -8,6 +8,9 @@ for N in 2 4 8; do
     bench.py --config c5 --scaling strong --batch $B --gpus $N --steps 4 --warmup 3 > gpurun_out/r2_c5_strong_b${B}_n$N.json 2> gpurun_out/r2_c5_strong_b${B}_n$N.err
   tail -c 300 gpurun_out/r2_c5_strong_b${B}_n$N.err
 done
+# the largest global batch one GPU can hold (12288 users: 441 ms at N = 1), at N = 8
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29650 \
+  bench.py --config c5 --scaling strong --batch 12288 --gpus 8 --steps 4 --warmup 3 > gpurun_out/r2_c5_strong_b12288_n8.json 2> gpurun_out/r2_c5_strong_b12288_n8.err
 for N in 2 4 8; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+N)) \
     bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_c2_weak_n$N.json 2> gpurun_out/r2_c2_weak_n$N.err
