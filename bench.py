@@ -438,7 +438,14 @@ def run_ours(args):
     ms_e2e, done_e2e, _, _, _ = timed(step_host_rows, 1, K, W + K)
     # sustained figure: back-to-back steps for >= args.sustain_s seconds of wall clock (no L2 flush in between; host
     # overhead included) -- the long-run number next to the K-step timed region
-    k_sus = max(K, int(args.sustain_s / max(ms / K * 1e-3, 1e-5)) + 1) if args.sustain_s > 0 else 0
+    # (the step count must be the SAME on every rank -- the ranks run in lock-step -- so it is derived from the slowest
+    # rank's time)
+    ms_ref = ms
+    if dist is not None:
+        t_ = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms_ref = float(t_.item())
+    k_sus = max(K, int(args.sustain_s / max(ms_ref / K * 1e-3, 1e-5)) + 1) if args.sustain_s > 0 else 0
     sus = None
     if k_sus:
         ms_s, done_s, _, _, wall_s = timed(step_resident, 0, k_sus, 2 * (W + K), do_flush=False)

@@ -3,6 +3,7 @@ configs[3]).  One step = one `GeoIEBatch.train_batch` call over `--batch` users 
 algorithmic bytes per check-in = 203 rows x 2 x 1 KB + indices = 416 148 B."""
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -10,11 +11,11 @@ import numpy as np
 import bench as B0
 
 ALGO = 416148.0
-# The reference's alpha = 0.01 is a per-user step with ONE negative.  A mini-batch sums, without normalisation (Bpr's rule),
-# the gradients of batch x 31 targets x 100 negatives = 4e5 terms into the two shared scalars a, b: with 0.01 -- or 0.01 / batch --
-# the first step throws a to +-1e2 and the loss to NaN.  2e-6 keeps the run finite (the table rows still move by ~1e-5 of
-# their magnitude per step); the arithmetic per check-in does not depend on alpha.
-ALPHA_C4 = 2e-6
+# The reference's alpha = 0.01 is a per-user step with ONE negative (31 loss terms per step).  A mini-batch sums, without
+# normalisation (Bpr's rule), batch x 31 targets x 100 negatives = 4e5 .. 1e6 terms into the two shared scalars a and b -- and b
+# sits in the exponent of a d^b with d up to 50 km: with 0.01, 0.01 / batch or even 2e-6 a few steps send b to ~10 and the
+# scores to inf - inf = NaN (measured).  1e-7 keeps 50 steps finite; the arithmetic per check-in does not depend on alpha.
+ALPHA_C4 = 1e-7
 
 
 def _data(cfg, n_users, seed=123):
@@ -196,6 +197,8 @@ def run_ours(args):
             ts.append(time.perf_counter() - t_)
         cpu = {"value": n_ci * 2 / sum(ts[1:]), "unit": B0.UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "2 steps x 8 users of the %d-user step (torch-CPU oracle, float64, all cores)" % Bu}
+    if not np.isfinite(losses[-1]):
+        print("bench c4: WARNING the loss is not finite (%r): a / b have diverged" % losses[-1], file=sys.stderr, flush=True)
     line = {"metric": B0.METRIC, "value": value, "unit": B0.UNIT, "n_gpus": world, "steps": Kst, "warmup": W, "ms_per_step": ms / Kst,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": B0.make_config("c4", cfg, args.batch, world, args.scaling),
