@@ -167,6 +167,12 @@ def run_ours(args):
     roof = {"kernel": "k_geoie_batch_k + segment sums (the gather / scatter of the step)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
             "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_check_in": ALGO,
             "share_of_step": t_main / tot_ms, "whole_step_frac": ALGO * (N / world) / (ms / Kst * 1e-3) / 1e9 / peaks["hbm"]}
+    tp = os.path.join(B0.ROOT, "profiles", "r2_ncu_traffic.json")
+    if world == 1 and Bg == 128 and os.path.exists(tp):                  # the capture is of the 128-user step
+        with open(tp) as f:
+            tr = json.load(f).get("kernels", {})
+        if "geoie_batch_k" in tr:
+            roof["traffic"] = tr["geoie_batch_k"]["dram_bytes"]
     parity = None
     if not args.no_parity and world == 1:
         from oracle import models as OM
