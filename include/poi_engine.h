@@ -66,6 +66,9 @@ int         poi_set_fused_recurrence(poi_engine* e, int on);
 /* CTAs per 128 users in the fused recurrence kernels (thread-block cluster splitting the gate columns, next
  * operand exchanged through distributed shared memory): 0 = auto (default), 1, 2 or 4. */
 int         poi_set_fused_cluster(poi_engine* e, int cl);
+/* index lists longer than 4096 keys: 1 (default) = all radix passes and the segment arrays in ONE persistent launch
+ * (grid barrier between the phases, csrc/sort.cuh), 0 = one launch per phase (kept for A/B measurements) */
+int         poi_set_fused_sort(poi_engine* e, int on);
 /* poi_gru_train calls with B <= 8 (the reference's one-by-one mode) are captured into a CUDA graph the second time a
  * shape is seen and replayed afterwards (1 = default); 0 = always launch kernel by kernel.  poi_graph_replays: how
  * many calls were served by a graph launch. */

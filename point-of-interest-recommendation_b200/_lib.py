@@ -89,6 +89,7 @@ _PROTOS = {
     "poi_get_gemm_mode": (c_int, [_E, POINTER(c_int)]),
     "poi_set_fused_recurrence": (c_int, [_E, c_int]),
     "poi_set_fused_cluster": (c_int, [_E, c_int]),
+    "poi_set_fused_sort": (c_int, [_E, c_int]),
     "poi_set_graph_mode": (c_int, [_E, c_int]),
     "poi_set_small_batch_path": (c_int, [_E, c_int]),
     "poi_graph_replays": (c_int, [_E, POINTER(c_int64)]),

@@ -31,7 +31,9 @@ struct poi_engine {
     bool wgrad_mn = true;            // tensor-core weight gradients read the activations as they lie (MN-major UMMA operands, no transposes)
     bool small_batch_path = true;    // B <= 8: SIMT recurrence kernels with Wh resident in shared memory (gru_small.cuh)
     int fused_cluster = 0;           // CTAs per 128 users in the fused recurrence: 0 = auto, else 1 / 2 / 4
-    bool fuse_recurrence = true;     // tensor-core modes: forward recurrence as one persistent fused kernel (gru_fused.cuh)
+    bool fuse_recurrence = true;
+    bool fused_sort = true;          // n > 4096 keys: radix passes + segment arrays in one persistent launch (sort.cuh)
+    uint32_t* grid_bar = nullptr;    // {arrivals, generation} of that kernel's grid barrier; zero between launches     // tensor-core modes: forward recurrence as one persistent fused kernel (gru_fused.cuh)
     // bump arena (device scratch owned by the engine); reset at the start of every call
     std::vector<PoiChunk> chunks;
     size_t cur_chunk = 0, cur_off = 0, high_water = 0, call_bytes = 0;

@@ -100,6 +100,13 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
     lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
+// Epilogue functors may split their global READS from the math: `Pre pre(m, n) const` issues the loads of one 4-column
+// group, `operator()(m, n, v, pre)` consumes them.  The per-tile GEMM kernel then requests the inputs of four rows at a time
+// -- the first four before it waits for the accumulator -- instead of paying one memory round trip per row after it
+// (the per-time-step recurrence GEMMs of H > 128 spent a third of their life there).
+template <class T, class = void> struct epi_has_pre { static constexpr bool value = false; };
+template <class T> struct epi_has_pre<T, decltype((void)sizeof(typename T::Pre))> { static constexpr bool value = true; };
+
 constexpr int BM = 128;
 constexpr int BK = 32;            // 32 fp32 = 128 B = one swizzle row
 constexpr int PRODUCERS = 256;    // warps 0..7: stage operands, later run the epilogue
@@ -237,11 +244,52 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
     // through a private 4 KB swizzled staging tile (the pipeline stages are free by now) and calls the
     // functor with 8 lanes per row: 4 rows x 128 contiguous bytes per instruction.
     if (warp < 8) {
-        if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
         const uint32_t stg = sbase + warp * 4096;
         const int rbase = m0 + (warp & 3) * 32;
         const int cbeg = (warp >> 2) * (BN / 2);
         const int rr0 = lane >> 3, qq = lane & 7;
+        if constexpr (epi_has_pre<Epi>::value) {
+            typename Epi::Pre pf[4];
+            const int nq0 = n0 + cbeg + 4 * qq;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int m = rbase + rr0 + 4 * i; if (m < M && nq0 < N) pf[i] = epi.pre(m, nq0); }
+            if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
+                float v[16];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (KB > 0) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c0 + 16 * h), v);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        sts4(stg + lane * 128 + (((4 * h + q) ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                }
+                __syncwarp();
+                const int n = n0 + c0 + 4 * qq;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 1 || c0 != cbeg) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const int m = rbase + rr0 + 4 * (4 * half + i); if (m < M && n < N) pf[i] = epi.pre(m, n); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = rr0 + 4 * (4 * half + i);
+                        float4 x;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                     : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
+                        const int m = rbase + rr;
+                        if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4, pf[i]); }
+                    }
+                }
+                __syncwarp();
+            }
+        } else {
+        if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
             float v[16];
@@ -267,6 +315,7 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
                 if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4); }
             }
             __syncwarp();
+        }
         }
     }
     tc_fence_before();

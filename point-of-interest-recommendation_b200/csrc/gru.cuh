@@ -117,26 +117,38 @@ struct EpiBiasStore {               // C = acc + bias          (input projection
 
 struct EpiZR {   // z_r = sigmoid(ui[:2].x + wh[:2].h + bi[:2])   (GRU_Spatial.py:173-175); also r*h
     const float* AXj; const float* hp; float* Z; float* R; float* RH; int H;
-    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
-        float4 ax = ldg4(AXj + (size_t)m * 3 * H + n);
+    struct Pre { float4 ax, h; };
+    __device__ __forceinline__ Pre pre(int m, int n) const {
+        Pre p; p.ax = ldg4(AXj + (size_t)m * 3 * H + n);
+        p.h = n < H ? f4zero() : ldg4(hp + (size_t)m * H + (n - H));
+        return p;
+    }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4], const Pre& p) const {
+        const float4 ax = p.ax;
         float4 s = make_float4(sigmoidf_(v[0] + ax.x), sigmoidf_(v[1] + ax.y), sigmoidf_(v[2] + ax.z), sigmoidf_(v[3] + ax.w));
         if (n < H) {
             st4(Z + (size_t)m * H + n, s);
         } else {
             size_t o = (size_t)m * H + (n - H);
-            float4 h = ldg4(hp + o);
             st4(R + o, s);
-            st4(RH + o, make_float4(s.x * h.x, s.y * h.y, s.z * h.z, s.w * h.w));
+            st4(RH + o, make_float4(s.x * p.h.x, s.y * p.h.y, s.z * p.h.z, s.w * p.h.w));
         }
     }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const { (*this)(m, n, v, pre(m, n)); }
 };
 
 struct EpiC {    // c = tanh(ui[2].x + wh[2].(r*h) + bi[2]); h_t = (1-z)*h + z*c   (GRU_Spatial.py:176-178)
     const float* AXj; const float* hp; const float* Z; float* C; float* Hn; int H;
-    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
-        float4 ax = ldg4(AXj + (size_t)m * 3 * H + 2 * H + n);
+    struct Pre { float4 ax, z, h; };
+    __device__ __forceinline__ Pre pre(int m, int n) const {
+        Pre p; size_t o = (size_t)m * H + n;
+        p.ax = ldg4(AXj + (size_t)m * 3 * H + 2 * H + n); p.z = ldg4(Z + o); p.h = ldg4(hp + o);
+        return p;
+    }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const { (*this)(m, n, v, pre(m, n)); }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4], const Pre& p) const {
+        const float4 ax = p.ax, z = p.z, h = p.h;
         size_t o = (size_t)m * H + n;
-        float4 z = ldg4(Z + o), h = ldg4(hp + o);
         float4 c = make_float4(tanhf(v[0] + ax.x), tanhf(v[1] + ax.y), tanhf(v[2] + ax.z), tanhf(v[3] + ax.w));
         st4(C + o, c);
         st4(Hn + o, make_float4((1.f - z.x) * h.x + z.x * c.x, (1.f - z.y) * h.y + z.y * c.y,
@@ -156,9 +168,16 @@ struct EpiDHl {  // d cost/d h_j from the loss: Vs^T.do_j + e_j (xp_{j+1} - xq_{
 
 struct EpiM {    // m = Wh[2]^T.da_c ; dr = m*h_prev ; da_r = dr*r(1-r) ; dh_keep += m*r
     const float* hp; const float* R; float* DAj; float* DHK; int H;
-    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
+    struct Pre { float4 h, r, k; };
+    __device__ __forceinline__ Pre pre(int m, int n) const {
+        Pre p; size_t o = (size_t)m * H + n;
+        p.h = ldg4(hp + o); p.r = ldg4(R + o); p.k = ld4(DHK + o);
+        return p;
+    }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const { (*this)(m, n, v, pre(m, n)); }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4], const Pre& p) const {
         size_t o = (size_t)m * H + n;
-        float4 h = ldg4(hp + o), r = ldg4(R + o), k = ld4(DHK + o);
+        const float4 h = p.h, r = p.r, k = p.k;
         st4(DAj + (size_t)m * 3 * H + H + n,
             make_float4(v[0] * h.x * r.x * (1.f - r.x), v[1] * h.y * r.y * (1.f - r.y),
                         v[2] * h.z * r.z * (1.f - r.z), v[3] * h.w * r.w * (1.f - r.w)));
@@ -174,9 +193,16 @@ __device__ __forceinline__ void bwd_gate_math(float dht, float z, float c, float
 
 struct EpiDH {   // dh_{j-1} = dh_keep + [da_z,da_r].Wh[:2] ; then the gate math of step j-1
     float* DHK; const float* DHlp; const float* Zp; const float* Cp; const float* HPp; float* DAp; int H;
-    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
+    struct Pre { float4 k, l, z, c, h; };
+    __device__ __forceinline__ Pre pre(int m, int n) const {
+        Pre p; size_t o = (size_t)m * H + n;
+        p.k = ld4(DHK + o); p.l = ldg4(DHlp + o); p.z = ldg4(Zp + o); p.c = ldg4(Cp + o); p.h = ldg4(HPp + o);
+        return p;
+    }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const { (*this)(m, n, v, pre(m, n)); }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4], const Pre& p) const {
         size_t o = (size_t)m * H + n;
-        float4 k = ld4(DHK + o), l = ldg4(DHlp + o), z = ldg4(Zp + o), c = ldg4(Cp + o), h = ldg4(HPp + o);
+        const float4 k = p.k, l = p.l, z = p.z, c = p.c, h = p.h;
         float4 daz, dac, kp;
         bwd_gate_math(v[0] + k.x + l.x, z.x, c.x, h.x, daz.x, dac.x, kp.x);
         bwd_gate_math(v[1] + k.y + l.y, z.y, c.y, h.y, daz.y, dac.y, kp.y);

@@ -43,6 +43,9 @@ int poi_engine_create(int device, poi_engine** out) {
         g_create_err = "cudaMallocHost failed"; delete e; return -6;
     }
     for (auto& ev : e->ev) cudaEventCreate(&ev);
+    if (cudaMalloc((void**)&e->grid_bar, 256) != cudaSuccess || cudaMemset(e->grid_bar, 0, 256) != cudaSuccess) {
+        g_create_err = "cudaMalloc (grid barrier) failed"; cudaFreeHost(e->h_out); delete e; return -6;
+    }
     *out = e;
     return 0;
 }
@@ -55,6 +58,7 @@ void poi_engine_destroy(poi_engine* e) {
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     for (auto& c : e->chunks) cudaFree(c.ptr);
     if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->grid_bar) cudaFree(e->grid_bar);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& r : e->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -77,6 +81,7 @@ int poi_set_fused_recurrence(poi_engine* e, int on) { e->fuse_recurrence = on !=
 int poi_set_small_batch_path(poi_engine* e, int on) { e->small_batch_path = on != 0; return 0; }
 int poi_set_graph_mode(poi_engine* e, int on) { e->graph_mode = on != 0; return 0; }
 int poi_graph_replays(poi_engine* e, int64_t* out) { *out = e->graph_replays; return 0; }
+int poi_set_fused_sort(poi_engine* e, int on) { e->fused_sort = on != 0; return 0; }
 int poi_set_fused_cluster(poi_engine* e, int cl) {
     if (cl != 0 && cl != 1 && cl != 2 && cl != 4) POI_FAIL(e, "poi_set_fused_cluster: %d (0 auto, 1, 2, 4)", cl);
     e->fused_cluster = cl; return 0;

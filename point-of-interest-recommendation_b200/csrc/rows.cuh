@@ -174,43 +174,76 @@ __device__ __forceinline__ OccPair occ_begin(const RowSrc& s, uint32_t occ) {
 
 constexpr int ROW_LONG_THRESH = 96;
 
-// NCH float4 chunks per lane: dim <= 128*NCH
+// NCH float4 chunks per lane: dim <= 128*NCH.  A warp takes up to 32 consecutive segments at a time: lane l reads the bounds, key and
+// first occurrence of segment l (coalesced, one round trip for all 32), the warp then walks the segments with the metadata
+// broadcast by shuffles, and the table row is requested BEFORE the gradient rows are summed -- per segment the warp waits for
+// one memory round trip (gradient rows and table row in flight together) instead of four dependent ones.
 template <int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NCH == 1 ? 6 : (NCH == 2 ? 5 : (NCH == 4 ? 3 : 2)))
 k_rows_update_warp(SegList seg, float* __restrict__ table, int dim4, float alpha, float lambda,
                    RowSrc src, int long_thresh, uint32_t* long_list, uint32_t* long_count) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t nu = *seg.n_unique;
-    for (int64_t sg = warp; sg < nu; sg += nwarps) {
-        const uint32_t s0 = seg.seg_start[sg], s1 = seg.seg_start[sg + 1];
-        const uint32_t cnt = s1 - s0;
-        if (src.skip_single && cnt == 1u) continue;
-        if ((int)cnt > long_thresh) {
-            if (lane == 0) { uint32_t pos = atomicAdd(long_count, 1u); long_list[pos] = (uint32_t)sg; }
-            continue;
-        }
-        float4 acc[NCH];
+    const int64_t nu = *seg.n_unique;
+    const bool emit = src.emit_rows != nullptr;
+    int gs = 32;                                   // segments per warp and round: as many as leave every warp >= 4 rounds (balance)
+    while (gs > 1 && nu < nwarps * gs * 4) gs >>= 1;
+    for (int64_t sg0 = warp * gs; sg0 < nu; sg0 += nwarps * gs) {
+        const int64_t my = sg0 + lane;
+        uint32_t s0l = 0, s1l = 0, keyl = 0, v0l = 0;
+        if (lane < gs && my < nu) { s0l = seg.seg_start[my]; s1l = seg.seg_start[my + 1]; keyl = seg.uniq[my]; v0l = seg.vals[s0l]; }
+        const int nseg = (int)min((int64_t)gs, nu - sg0);
+        for (int j = 0; j < nseg; ++j) {
+            const uint32_t s0 = __shfl_sync(0xffffffffu, s0l, j), s1 = __shfl_sync(0xffffffffu, s1l, j);
+            const uint32_t key = __shfl_sync(0xffffffffu, keyl, j), v0 = __shfl_sync(0xffffffffu, v0l, j);
+            const uint32_t cnt = s1 - s0;
+            const int64_t sg = sg0 + j;
+            if (src.skip_single && cnt == 1u) continue;
+            if ((int)cnt > long_thresh) {
+                if (lane == 0) { uint32_t pos = atomicAdd(long_count, 1u); long_list[pos] = (uint32_t)sg; }
+                continue;
+            }
+            float4 trow[NCH];
+            if (!emit) {
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) acc[k] = f4zero();
-        float cntf = (float)cnt;
-        if (src.weights) { cntf = 0.f; for (uint32_t i = s0; i < s1; ++i) cntf += src.weights[seg.vals[i]]; }
-        for (uint32_t i = s0; i < s1; ++i) {
-            OccPair o = occ_begin(src, seg.vals[i]);
+                for (int k = 0; k < NCH; ++k) { const int c = lane + 32 * k; if (c < dim4) trow[k] = ld4(table + ((size_t)key * dim4 + c) * 4); }
+            }
+            float4 acc[NCH];
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                int c = lane + 32 * k;
-                if (c < dim4) {
-                    if (o.p1) acc[k] = f4add(acc[k], ld4(o.p1 + 4 * c));
-                    if (o.p2) acc[k] = f4fma(o.s2, ld4(o.p2 + 4 * c), acc[k]);
+            for (int k = 0; k < NCH; ++k) acc[k] = f4zero();
+            float cntf = (float)cnt;
+            if (src.weights) { cntf = 0.f; for (uint32_t i = s0; i < s1; ++i) cntf += src.weights[seg.vals[i]]; }
+            for (uint32_t i = s0; i < s1; ++i) {
+                OccPair o = occ_begin(src, i == s0 ? v0 : seg.vals[i]);
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    int c = lane + 32 * k;
+                    if (c < dim4) {
+                        if (o.p1) acc[k] = f4add(acc[k], ld4(o.p1 + 4 * c));
+                        if (o.p2) acc[k] = f4fma(o.s2, ld4(o.p2 + 4 * c), acc[k]);
+                    }
                 }
             }
-        }
+            if (emit) {
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-            int c = lane + 32 * k;
-            if (c < dim4) row_finish(src, table, dim4, seg.uniq[sg], (uint32_t)sg, c, acc[k], cntf, alpha, lambda);
+                for (int k = 0; k < NCH; ++k) {
+                    int c = lane + 32 * k;
+                    if (c < dim4) row_finish(src, table, dim4, key, (uint32_t)sg, c, acc[k], cntf, alpha, lambda);
+                }
+            } else {
+                const float lc = lambda * cntf;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < dim4) {
+                        float4 r = trow[k];
+                        r.x -= alpha * (acc[k].x + lc * r.x); r.y -= alpha * (acc[k].y + lc * r.y);
+                        r.z -= alpha * (acc[k].z + lc * r.z); r.w -= alpha * (acc[k].w + lc * r.w);
+                        st4(table + ((size_t)key * dim4 + c) * 4, r);
+                    }
+                }
+            }
         }
     }
 }
@@ -307,7 +340,18 @@ static int launch_rows_update(poi_engine* e, const SegList& seg, float* table, i
     POI_TRY(arena_get(e, (size_t)seg.n, &long_list));
     POI_TRY(arena_get(e, 4, &long_count));
     POI_CK(e, cudaMemsetAsync(long_count, 0, 4, e->stream));
-    int64_t warps = std::min<int64_t>(seg.n, (int64_t)e->num_sms * 64);
+    // one wave of resident CTAs (a grid-stride loop over more CTAs than fit would run its tail at a fraction of the occupancy)
+    static int occ[4] = {0, 0, 0, 0};
+    const int oi = dim4 <= 32 ? 0 : (dim4 <= 64 ? 1 : (dim4 <= 128 ? 2 : 3));
+    if (!occ[oi]) {
+        int o = 0;
+        if (oi == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_rows_update_warp<1>, 256, 0);
+        else if (oi == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_rows_update_warp<2>, 256, 0);
+        else if (oi == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_rows_update_warp<4>, 256, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_rows_update_warp<8>, 256, 0);
+        occ[oi] = std::max(o, 1);
+    }
+    int64_t warps = std::min<int64_t>(seg.n, (int64_t)e->num_sms * occ[oi] * 8);
     unsigned grid = (unsigned)std::max<int64_t>(poi_cdiv(warps * 32, 256), 1);
     if (dim4 <= 32)       POI_LAUNCH(e, (k_rows_update_warp<1>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);
     else if (dim4 <= 64)  POI_LAUNCH(e, (k_rows_update_warp<2>), grid, 256, 0, seg, table, dim4, alpha, lambda, src, long_thresh, long_list, long_count);

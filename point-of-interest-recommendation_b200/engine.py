@@ -152,6 +152,10 @@ class Engine:
         """CTAs per 128 users in the fused recurrence kernels: 0 auto, 1, 2 or 4."""
         self._ck(lib.poi_set_fused_cluster(self._h, int(cl)))
 
+    def set_fused_sort(self, on: bool):
+        """Index lists > 4096 keys: radix passes + segment arrays in one persistent launch (default) or one launch per phase."""
+        self._ck(lib.poi_set_fused_sort(self._h, int(bool(on))))
+
     def set_graph_mode(self, on: bool):
         """CUDA-graph replay of train calls with B <= 8 (the reference's one-by-one mode); default on."""
         self._ck(lib.poi_set_graph_mode(self._h, 1 if on else 0))

@@ -97,3 +97,38 @@ def test_scatter_without_gradient_is_pure_decay(engine):
     engine.scatter_sgd(t, idx, None, 0.5, 0.1)
     exp = np.full((6, 8), 2.0, dtype=np.float32); exp[5] = 2.0 - 0.5 * (0.1 * 3 * 2.0); exp[1] = 2.0 - 0.5 * (0.1 * 1 * 2.0)
     assert np.allclose(t.cpu().numpy(), exp, rtol=1e-6)
+
+
+@pytest.mark.parametrize("n,bound", [(4097, 255), (8192, 257), (8193, 65536), (70001, 65537), (1212417, 1 << 20),
+                                     (2500000, 40001), (300000, (1 << 31) - 1)])
+def test_fused_sort_segments_equal_the_phase_by_phase_path(engine, n, bound):
+    """csrc/sort.cuh: one persistent launch (grid barrier between radix passes and the segment phase) against the
+    launch-per-phase path and numpy; 1 to 4 passes, one and several tiles per CTA, a hot key, ragged tails."""
+    rs = np.random.RandomState(n % 7919)
+    idx = rs.randint(0, bound, size=n, dtype=np.int64).astype(np.int32)
+    idx[rs.randint(0, n, size=n // 7)] = bound - 1
+    idx[rs.randint(0, n, size=n // 50)] = 0
+    dev = torch.from_numpy(idx).cuda()
+    ref_u, ref_c = np.unique(idx, return_counts=True)
+    out = {}
+    try:
+        for mode in (1, 0):
+            engine.set_fused_sort(bool(mode))
+            uq, cnt = engine.unique(dev, bound)
+            out[mode] = (uq.cpu().numpy(), cnt.cpu().numpy())
+            assert np.array_equal(out[mode][0], ref_u.astype(np.int32)), mode
+            assert np.array_equal(out[mode][1], ref_c.astype(np.int32)), mode
+        if bound <= (1 << 20):
+            # the occurrence order inside a segment (stability) decides the summation order: bit-identical tables
+            dim = 8
+            table = rs.uniform(-0.5, 0.5, (bound, dim)).astype(np.float32)
+            grad = torch.from_numpy(rs.uniform(-1, 1, (n, dim)).astype(np.float32)).cuda()
+            res = {}
+            for mode in (1, 0):
+                engine.set_fused_sort(bool(mode))
+                t = torch.from_numpy(table.copy()).cuda()
+                engine.scatter_sgd(t, dev, grad, 0.01, 0.001)
+                res[mode] = t.cpu().numpy()
+            assert np.array_equal(res[0], res[1])
+    finally:
+        engine.set_fused_sort(True)
