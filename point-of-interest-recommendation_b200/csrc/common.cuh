@@ -32,6 +32,7 @@ struct poi_engine {
     bool small_batch_path = true;    // B <= 8: SIMT recurrence kernels with Wh resident in shared memory (gru_small.cuh)
     int fused_cluster = 0;           // CTAs per 128 users in the fused recurrence: 0 = auto, else 1 / 2 / 4
     bool fuse_recurrence = true;
+    bool gemm_csplit = true;         // per-tile tensor-core GEMMs with few tiles and long K: the two K halves as a 2-CTA cluster (POI_GEMM_CSPLIT=0 disables)
     bool fused_sort = true;          // n > 4096 keys: radix passes + segment arrays in one persistent launch (sort.cuh)
     uint32_t* grid_bar = nullptr;    // {arrivals, generation} of that kernel's grid barrier; zero between launches     // tensor-core modes: forward recurrence as one persistent fused kernel (gru_fused.cuh)
     // bump arena (device scratch owned by the engine); reset at the start of every call

@@ -107,6 +107,21 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
 template <class T, class = void> struct epi_has_pre { static constexpr bool value = false; };
 template <class T> struct epi_has_pre<T, decltype((void)sizeof(typename T::Pre))> { static constexpr bool value = true; };
 
+// thread-block-cluster helpers of the split-K pair (k_gemm_tn_tc<..., CSPLIT = true>)
+__device__ __forceinline__ uint32_t tcx_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void tcx_st_cluster4(uint32_t caddr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tcx_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+
+// rows whose inputs are requested together: all 8 of a 32-column group when the functor's inputs are small, else 4
+template <class T, bool = epi_has_pre<T>::value> struct epi_pre_rows { static constexpr int value = 8; };
+template <class T> struct epi_pre_rows<T, true> { static constexpr int value = sizeof(typename T::Pre) <= 48 ? 8 : 4; };
+
 constexpr int BM = 128;
 constexpr int BK = 32;            // 32 fp32 = 128 B = one swizzle row
 constexpr int PRODUCERS = 256;    // warps 0..7: stage operands, later run the epilogue
@@ -130,7 +145,13 @@ struct Cfg {
 // Warp-specialised: producers run ahead through a STAGES-deep ring (full/empty mbarriers, no block-wide
 // barrier in the main loop) with the next k-block's global loads already in flight in registers;
 // blockIdx.z selects a K range [z*k_per_split, ...) (split-K for the weight-gradient GEMMs).
-template <int BN, bool SPLIT3, class Epi>
+//
+// CSPLIT (few tiles, long K: the per-time-step recurrence GEMMs at a few hundred users per GPU): the two K halves of a tile
+// run as a cluster of two CTAs (cluster dims (1, 1, 2), rank = blockIdx.z) on two SMs -- the length of the dependent MMA
+// chain, which is what such a launch costs, halves.  Rank 1 pushes its accumulator into rank 0's shared memory
+// (st.shared::cluster, conflict-free slots), a cluster barrier orders it, rank 0 adds it (first half + second half: fixed
+// order) and runs the epilogue.  Requires a functor with Pre.
+template <int BN, bool SPLIT3, class Epi, bool CSPLIT = false>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
              int M, int N, int K, int k_per_split, Epi epi) {
@@ -146,6 +167,11 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
     const int kbeg = blockIdx.z * k_per_split;
     const int kend = min(K, kbeg + k_per_split);
     const int KB = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
+    // CSPLIT: [BM x BN] fp32 landing zone of rank 1's accumulator, behind the pipeline stages (BN = 64: 32 KB; measured against
+    // reusing the idle stages behind a second cluster barrier: the extra barrier costs 0.5 us per launch)
+    const uint32_t part_base = sbase + C::STAGES * C::STAGE_BYTES;
+    static_assert(!CSPLIT || BN == 64, "cluster split-K is instantiated for 64-wide tiles only");
+    const bool second_half = CSPLIT && blockIdx.z == 1;
 
     if (tid == 0) {
 #pragma unroll
@@ -249,13 +275,40 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
         const int cbeg = (warp >> 2) * (BN / 2);
         const int rr0 = lane >> 3, qq = lane & 7;
         if constexpr (epi_has_pre<Epi>::value) {
-            typename Epi::Pre pf[4];
+            constexpr int RB = epi_pre_rows<Epi>::value;
+            typename Epi::Pre pf[RB];
             const int nq0 = n0 + cbeg + 4 * qq;
+            if (!second_half) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const int m = rbase + rr0 + 4 * i; if (m < M && nq0 < N) pf[i] = epi.pre(m, nq0); }
+                for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * i; if (m < M && nq0 < N) pf[i] = epi.pre(m, nq0); }
+            }
             if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
+            if constexpr (CSPLIT) {
+                if (second_half) {
+                    const uint32_t dst = tcx_mapa(part_base, 0);
+                    int ci = 0;
 #pragma unroll 1
-            for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
+                    for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32, ++ci) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float v[16];
+                            if (KB > 0) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c0 + 16 * h), v);
+                            else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                tcx_st_cluster4(dst + (uint32_t)(((((warp * (BN / 64) + ci) * 2 + h) * 4 + q) * 32 + lane) * 16),
+                                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                        }
+                    }
+                }
+                tcx_cluster_sync();
+            }
+            int ci = 0;
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + BN / 2 && !second_half; c0 += 32, ++ci) {
                 float v[16];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -264,6 +317,15 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = 0.f;
                     }
+                    if constexpr (CSPLIT) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 pp;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pp.x), "=f"(pp.y), "=f"(pp.z), "=f"(pp.w)
+                                         : "r"(part_base + (uint32_t)(((((warp * (BN / 64) + ci) * 2 + h) * 4 + q) * 32 + lane) * 16)));
+                            v[4 * q] += pp.x; v[4 * q + 1] += pp.y; v[4 * q + 2] += pp.z; v[4 * q + 3] += pp.w;
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         sts4(stg + lane * 128 + (((4 * h + q) ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
@@ -271,14 +333,14 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
                 __syncwarp();
                 const int n = n0 + c0 + 4 * qq;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < 8 / RB; ++half) {
                     if (half == 1 || c0 != cbeg) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { const int m = rbase + rr0 + 4 * (4 * half + i); if (m < M && n < N) pf[i] = epi.pre(m, n); }
+                        for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * (RB * half + i); if (m < M && n < N) pf[i] = epi.pre(m, n); }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = rr0 + 4 * (4 * half + i);
+                    for (int i = 0; i < RB; ++i) {
+                        const int rr = rr0 + 4 * (RB * half + i);
                         float4 x;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                                      : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
@@ -318,6 +380,7 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
         }
         }
     }
+    if constexpr (CSPLIT) { if (warp >= 8) tcx_cluster_sync(); }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, BN);
@@ -463,9 +526,51 @@ k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restri
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
             int m0, n0, kbeg, kend; decode(t, m0, n0, kbeg, kend);
             const int buf = it & 1;
+            const int rbase = m0 + q * 32;
+            if constexpr (epi_has_pre<Epi>::value) {
+                // the functor's inputs of the first rows are requested while the MMAs of this tile are still running
+                constexpr int RB = epi_pre_rows<Epi>::value;
+                typename Epi::Pre pf[RB];
+                {
+                    const int n = n0 + 4 * qq;
+#pragma unroll
+                    for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * i; if (m < M && n < N) pf[i] = epi.pre(m, n); }
+                }
+                mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    float v[16];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0 + 16 * h), v);
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd)
+                            sts4(stg + lane * 128 + (((4 * h + qd) ^ (lane & 7)) << 4), make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]));
+                    }
+                    __syncwarp();
+                    const int n = n0 + c0 + 4 * qq;
+#pragma unroll
+                    for (int half = 0; half < 8 / RB; ++half) {
+                        if (half == 1 || c0 != 0) {
+#pragma unroll
+                            for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * (RB * half + i); if (m < M && n < N) pf[i] = epi.pre(m, n); }
+                        }
+#pragma unroll
+                        for (int i = 0; i < RB; ++i) {
+                            const int rr = rr0 + 4 * (RB * half + i);
+                            float4 x;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                         : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
+                            const int m = rbase + rr;
+                            if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4, pf[i]); }
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
             mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1);
             tc_fence_after();
-            const int rbase = m0 + q * 32;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[16];
@@ -487,6 +592,7 @@ k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restri
                     if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4); }
                 }
                 __syncwarp();
+            }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);          // accumulator drained: the MMA thread may overwrite it
@@ -696,6 +802,34 @@ static int launch_tc_inst(poi_engine* e, const float* A, int lda, const float* W
     return 0;
 }
 
+// the two K halves of every tile as a cluster of two CTAs (see k_gemm_tn_tc, CSPLIT)
+template <int BN, bool SPLIT3, class Epi>
+static int launch_tc_csplit(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K, const Epi& epi) {
+    using C = tc::Cfg<BN, SPLIT3>;
+    const int smem = C::SMEM_BYTES + tc::BM * BN * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        POI_CK(e, cudaFuncSetAttribute(tc::k_gemm_tn_tc<BN, SPLIT3, Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int k_per_split = (int)poi_cdiv(poi_cdiv(K, 2), tc::BK) * tc::BK;
+    ProfRec* pr = e->kprof ? prof_begin(e) : nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)poi_cdiv(N, BN), (unsigned)poi_cdiv(M, tc::BM), 2);
+    cfg.blockDim = dim3(tc::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 2;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t st = cudaLaunchKernelEx(&cfg, tc::k_gemm_tn_tc<BN, SPLIT3, Epi, true>, A, lda, W, ldw, (int)M, N, K, k_per_split, epi);
+    if (pr) cudaEventRecord(pr->b, e->stream);
+    e->cur_flops = 0.0; e->cur_bytes = 0.0;
+    e->launches++;
+    if (st == cudaSuccess) st = cudaPeekAtLastError();
+    if (st != cudaSuccess) POI_FAIL(e, "launch k_gemm_tn_tc (cluster split-K) failed: %s", cudaGetErrorString(st));
+    return 0;
+}
+
 template <int BN, bool SPLIT3, class Epi>
 static int launch_tc_persist(poi_engine* e, const float* A, int lda, const float* W, int ldw, int64_t M, int N, int K,
                              const Epi& epi, int splits, int k_per_split) {
@@ -730,6 +864,12 @@ static int launch_gemm_tn_tc(poi_engine* e, const float* A, int lda, const float
     const int64_t tiles64 = poi_cdiv(M, tc::BM) * poi_cdiv(N, 64);
     const double cost128 = (double)poi_cdiv(tiles128, e->num_sms), cost64 = 0.8 * (double)poi_cdiv(tiles64, e->num_sms);
     const bool wide = cost128 <= cost64;
+    if constexpr (tc::epi_has_pre<Epi>::value) {
+        // one partial wave and a long reduction: what the launch costs is the dependent MMA chain of one tile -> halve it
+        // (64-wide tiles only: measured at 1024 x 1024 x 512, 128-wide tiles + split were 6 us SLOWER than 64-wide unsplit)
+        if (e->gemm_csplit && split3 && K >= 256 && 2 * tiles64 <= e->num_sms)
+            return launch_tc_csplit<64, true>(e, A, lda, W, ldw, M, N, K, epi);
+    }
     if (split3) {
         if (wide) return launch_tc_inst<128, true>(e, A, lda, W, ldw, M, N, K, epi);
         return launch_tc_inst<64, true>(e, A, lda, W, ldw, M, N, K, epi);

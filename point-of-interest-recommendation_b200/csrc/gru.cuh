@@ -158,10 +158,15 @@ struct EpiC {    // c = tanh(ui[2].x + wh[2].(r*h) + bi[2]); h_t = (1-z)*h + z*c
 
 struct EpiDHl {  // d cost/d h_j from the loss: Vs^T.do_j + e_j (xp_{j+1} - xq_{j+1})
     float* DHl; const float* ev; const float* XDiff; int H;
-    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const {
+    struct Pre { float4 x; float e; };
+    __device__ __forceinline__ Pre pre(int m, int n) const {
+        Pre p; p.e = __ldg(ev + m); p.x = ldg4(XDiff + (size_t)m * H + n);
+        return p;
+    }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4]) const { (*this)(m, n, v, pre(m, n)); }
+    __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4], const Pre& p) const {
         size_t o = (size_t)m * H + n;
-        float e_ = __ldg(ev + m);
-        float4 x = ldg4(XDiff + o);
+        const float e_ = p.e; const float4 x = p.x;
         st4(DHl + o, make_float4(fmaf(e_, x.x, v[0]), fmaf(e_, x.y, v[1]), fmaf(e_, x.z, v[2]), fmaf(e_, x.w, v[3])));
     }
 };

@@ -1,5 +1,6 @@
 // poi_engine.cu -- extern "C" surface of the engine (see include/poi_engine.h).
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include "common.cuh"
 #include "sort.cuh"
@@ -39,6 +40,7 @@ int poi_engine_create(int device, poi_engine** out) {
     poi_engine* e = new poi_engine();
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
+    { const char* v = getenv("POI_GEMM_CSPLIT"); if (v && v[0] == '0') e->gemm_csplit = false; }
     if (cudaMallocHost((void**)&e->h_out, 64 * sizeof(double)) != cudaSuccess) {
         g_create_err = "cudaMallocHost failed"; delete e; return -6;
     }
