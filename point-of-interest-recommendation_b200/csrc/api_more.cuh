@@ -394,6 +394,8 @@ extern "C" int poi_gather_rows_sharded(poi_engine* e, const float* const* shards
     const int dim4 = dim / 4;
     // bytes: every row read once (world-1 of world over NVLink) and written once, plus the ids
     POI_CAT(e, CAT_GATHER, 0, 2.0 * (double)n_idx * dim * 4 + 4.0 * (double)n_idx);
+    if (peer_gather_mode() == 1 && dim * 4 * PG_WARPS * PG_ST <= (200 << 10))
+        return launch_gather_bulk(e, pt, dim, reinterpret_cast<const uint32_t*>(ids_dev), nullptr, n_idx, n_idx, out_dev);
     const int lpr = dim4 <= 8 ? 8 : (dim4 <= 16 ? 16 : 32);
     const int64_t threads_needed = poi_cdiv(n_idx, 4) * lpr;
     unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(threads_needed, 256), (int64_t)e->num_sms * 16));

@@ -118,9 +118,9 @@ __device__ __forceinline__ void tcx_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
 
-// rows whose inputs are requested together: all 8 of a 32-column group when the functor's inputs are small, else 4
-template <class T, bool = epi_has_pre<T>::value> struct epi_pre_rows { static constexpr int value = 8; };
-template <class T> struct epi_pre_rows<T, true> { static constexpr int value = sizeof(typename T::Pre) <= 48 ? 8 : 4; };
+// rows per request batch; two batches are kept in registers (the inputs of batch j + 1 are in flight while batch j is consumed)
+template <class T, bool = epi_has_pre<T>::value> struct epi_pre_rows { static constexpr int value = 4; };
+template <class T> struct epi_pre_rows<T, true> { static constexpr int value = sizeof(typename T::Pre) <= 32 ? 4 : 2; };
 
 constexpr int BM = 128;
 constexpr int BK = 32;            // 32 fp32 = 128 B = one swizzle row
@@ -275,13 +275,14 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
         const int cbeg = (warp >> 2) * (BN / 2);
         const int rr0 = lane >> 3, qq = lane & 7;
         if constexpr (epi_has_pre<Epi>::value) {
-            constexpr int RB = epi_pre_rows<Epi>::value;
-            typename Epi::Pre pf[RB];
-            const int nq0 = n0 + cbeg + 4 * qq;
-            if (!second_half) {
+            constexpr int SR = epi_pre_rows<Epi>::value, NB = 8 / SR;
+            typename Epi::Pre pf[2][SR];
+            auto request = [&](typename Epi::Pre (&set)[SR], int c0, int j) {
+                const int n = n0 + c0 + 4 * qq;
 #pragma unroll
-                for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * i; if (m < M && nq0 < N) pf[i] = epi.pre(m, nq0); }
-            }
+                for (int i = 0; i < SR; ++i) { const int m = rbase + rr0 + 4 * (SR * j + i); if (m < M && n < N) set[i] = epi.pre(m, n); }
+            };
+            if (!second_half) request(pf[0], cbeg, 0);
             if (KB > 0) { mbar_wait(&mbar_done, 0); tc_fence_after(); }
             if constexpr (CSPLIT) {
                 if (second_half) {
@@ -333,19 +334,17 @@ k_gemm_tn_tc(const float* __restrict__ A, int lda, const float* __restrict__ W, 
                 __syncwarp();
                 const int n = n0 + c0 + 4 * qq;
 #pragma unroll
-                for (int half = 0; half < 8 / RB; ++half) {
-                    if (half == 1 || c0 != cbeg) {
+                for (int j = 0; j < NB; ++j) {
+                    if (j + 1 < NB) request(pf[(j + 1) & 1], c0, j + 1);
+                    else if (c0 + 32 < cbeg + BN / 2) request(pf[0], c0 + 32, 0);
 #pragma unroll
-                        for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * (RB * half + i); if (m < M && n < N) pf[i] = epi.pre(m, n); }
-                    }
-#pragma unroll
-                    for (int i = 0; i < RB; ++i) {
-                        const int rr = rr0 + 4 * (RB * half + i);
+                    for (int i = 0; i < SR; ++i) {
+                        const int rr = rr0 + 4 * (SR * j + i);
                         float4 x;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                                      : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
                         const int m = rbase + rr;
-                        if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4, pf[i]); }
+                        if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4, pf[j & 1][i]); }
                     }
                 }
                 __syncwarp();
@@ -428,61 +427,68 @@ k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restri
 
     if (warp < 8) {
         // ------------------------------ producers ------------------------------
+        // The (tile, k-block) sequence of this CTA is walked as ONE stream: the global loads run two k-blocks ahead of the
+        // staging ACROSS tile boundaries (measured on the per-tile version: the first two k-blocks of every tile waited a
+        // full memory round trip with the tensor pipe drained -- a fifth of the producers' time at K = 256).
         float4 ra[3][C::LA], rw[3][C::LW];
         const int srow = tid >> 3, sc = tid & 7;
         const uint32_t soff = srow * 128 + ((sc ^ (srow & 7)) << 4);
         const size_t strA = (size_t)32 * lda, strW = (size_t)32 * ldw;
         int64_t gkb = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            int m0, n0, kbeg, kend; decode(t, m0, n0, kbeg, kend);
-            const int KB = (kend - kbeg + BK - 1) / BK;
-            const float* pA = A + (size_t)(m0 + srow) * lda + sc * 4;
-            const float* pW = W + (size_t)(n0 + srow) * ldw + sc * 4;
-            uint32_t okA = 0, okW = 0;
+        // load cursor
+        int lt = blockIdx.x, lkb = 0, lKB = 0, lkbeg = 0, lkend = 0;
+        const float* pA = A; const float* pW = W;
+        uint32_t okA = 0, okW = 0;
+        auto open_tile = [&]() {
+            if (lt >= total) return;
+            int m0, n0; decode(lt, m0, n0, lkbeg, lkend);
+            lKB = (lkend - lkbeg + BK - 1) / BK; lkb = 0;
+            pA = A + (size_t)(m0 + srow) * lda + sc * 4;
+            pW = W + (size_t)(n0 + srow) * ldw + sc * 4;
+            okA = 0; okW = 0;
 #pragma unroll
             for (int i = 0; i < C::LA; ++i) okA |= (m0 + srow + 32 * i < M ? 1u : 0u) << i;
 #pragma unroll
             for (int i = 0; i < C::LW; ++i) okW |= (n0 + srow + 32 * i < N ? 1u : 0u) << i;
-            auto gload = [&](int kb, float4 (&ra_)[C::LA], float4 (&rw_)[C::LW]) {
-                const int k0 = kbeg + kb * BK;
-                const bool kin = k0 + sc * 4 < kend;
+        };
+        open_tile();
+        auto load_next = [&](float4 (&ra_)[C::LA], float4 (&rw_)[C::LW]) -> bool {
+            if (lt >= total) return false;
+            const int k0 = lkbeg + lkb * BK;
+            const bool kin = k0 + sc * 4 < lkend;
 #pragma unroll
-                for (int i = 0; i < C::LA; ++i)
-                    ra_[i] = (kin && ((okA >> i) & 1u)) ? *reinterpret_cast<const float4*>(pA + i * strA + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < C::LA; ++i)
+                ra_[i] = (kin && ((okA >> i) & 1u)) ? *reinterpret_cast<const float4*>(pA + i * strA + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < C::LW; ++i)
-                    rw_[i] = (kin && ((okW >> i) & 1u)) ? *reinterpret_cast<const float4*>(pW + i * strW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            auto stage_in = [&](const float4 (&ra_)[C::LA], const float4 (&rw_)[C::LW]) {
-                const int s = (int)(gkb % C::STAGES);
-                if (gkb >= C::STAGES) mbar_wait(&mbar_empty[s], (uint32_t)((gkb / C::STAGES) - 1) & 1);
-                const uint32_t sA = sbase + s * C::STAGE_BYTES + soff, sW = sA + C::A_BYTES;
-                const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
+            for (int i = 0; i < C::LW; ++i)
+                rw_[i] = (kin && ((okW >> i) & 1u)) ? *reinterpret_cast<const float4*>(pW + i * strW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (++lkb == lKB) { lt += gridDim.x; open_tile(); }
+            return true;
+        };
+        auto stage_in = [&](const float4 (&ra_)[C::LA], const float4 (&rw_)[C::LW]) {
+            const int s = (int)(gkb % C::STAGES);
+            if (gkb >= C::STAGES) mbar_wait(&mbar_empty[s], (uint32_t)((gkb / C::STAGES) - 1) & 1);
+            const uint32_t sA = sbase + s * C::STAGE_BYTES + soff, sW = sA + C::A_BYTES;
+            const uint32_t sAl = sW + C::W_BYTES, sWl = sAl + C::A_BYTES;
 #pragma unroll
-                for (int i = 0; i < C::LA; ++i) {
-                    if (SPLIT3) { float4 hi, lo; split4(ra_[i], hi, lo); sts4(sA + i * 4096, hi); sts4(sAl + i * 4096, lo); }
-                    else sts4(sA + i * 4096, ra_[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < C::LW; ++i) {
-                    if (SPLIT3) { float4 hi, lo; split4(rw_[i], hi, lo); sts4(sW + i * 4096, hi); sts4(sWl + i * 4096, lo); }
-                    else sts4(sW + i * 4096, rw_[i]);
-                }
-                fence_async_smem();
-                mbar_arrive(&mbar_full[s]);
-                ++gkb;
-            };
-#pragma unroll
-            for (int u = 0; u < 2; ++u) if (u < KB) gload(u, ra[u], rw[u]);
-            for (int kb = 0; kb < KB; kb += 3) {
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    if (kb + u < KB) {
-                        if (kb + u + 2 < KB) gload(kb + u + 2, ra[(u + 2) % 3], rw[(u + 2) % 3]);
-                        stage_in(ra[u], rw[u]);
-                    }
-                }
+            for (int i = 0; i < C::LA; ++i) {
+                if (SPLIT3) { float4 hi, lo; split4(ra_[i], hi, lo); sts4(sA + i * 4096, hi); sts4(sAl + i * 4096, lo); }
+                else sts4(sA + i * 4096, ra_[i]);
             }
+#pragma unroll
+            for (int i = 0; i < C::LW; ++i) {
+                if (SPLIT3) { float4 hi, lo; split4(rw_[i], hi, lo); sts4(sW + i * 4096, hi); sts4(sWl + i * 4096, lo); }
+                else sts4(sW + i * 4096, rw_[i]);
+            }
+            fence_async_smem();
+            mbar_arrive(&mbar_full[s]);
+            ++gkb;
+        };
+        bool v0 = load_next(ra[0], rw[0]), v1 = load_next(ra[1], rw[1]), v2 = false;
+        for (;;) {
+            v2 = load_next(ra[2], rw[2]); if (!v0) break; stage_in(ra[0], rw[0]);
+            v0 = load_next(ra[0], rw[0]); if (!v1) break; stage_in(ra[1], rw[1]);
+            v1 = load_next(ra[1], rw[1]); if (!v2) break; stage_in(ra[2], rw[2]);
         }
     } else if (warp == 8) {
         if (lane == 0) {
@@ -529,13 +535,14 @@ k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restri
             const int rbase = m0 + q * 32;
             if constexpr (epi_has_pre<Epi>::value) {
                 // the functor's inputs of the first rows are requested while the MMAs of this tile are still running
-                constexpr int RB = epi_pre_rows<Epi>::value;
-                typename Epi::Pre pf[RB];
-                {
-                    const int n = n0 + 4 * qq;
+                constexpr int SR = epi_pre_rows<Epi>::value, NB = 8 / SR;
+                typename Epi::Pre pf[2][SR];
+                auto request = [&](typename Epi::Pre (&set)[SR], int c0, int j) {
+                    const int n = n0 + c0 + 4 * qq;
 #pragma unroll
-                    for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * i; if (m < M && n < N) pf[i] = epi.pre(m, n); }
-                }
+                    for (int i = 0; i < SR; ++i) { const int m = rbase + rr0 + 4 * (SR * j + i); if (m < M && n < N) set[i] = epi.pre(m, n); }
+                };
+                request(pf[0], 0, 0);
                 mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
@@ -551,19 +558,17 @@ k_gemm_tn_tc_persist(const float* __restrict__ A, int lda, const float* __restri
                     __syncwarp();
                     const int n = n0 + c0 + 4 * qq;
 #pragma unroll
-                    for (int half = 0; half < 8 / RB; ++half) {
-                        if (half == 1 || c0 != 0) {
+                    for (int j = 0; j < NB; ++j) {
+                        if (j + 1 < NB) request(pf[(j + 1) & 1], c0, j + 1);
+                        else if (c0 + 32 < BN) request(pf[0], c0 + 32, 0);
 #pragma unroll
-                            for (int i = 0; i < RB; ++i) { const int m = rbase + rr0 + 4 * (RB * half + i); if (m < M && n < N) pf[i] = epi.pre(m, n); }
-                        }
-#pragma unroll
-                        for (int i = 0; i < RB; ++i) {
-                            const int rr = rr0 + 4 * (RB * half + i);
+                        for (int i = 0; i < SR; ++i) {
+                            const int rr = rr0 + 4 * (SR * j + i);
                             float4 x;
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                                          : "r"(stg + rr * 128 + ((qq ^ (rr & 7)) << 4)));
                             const int m = rbase + rr;
-                            if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4, pf[i]); }
+                            if (m < M && n < N) { float q4[4] = {x.x, x.y, x.z, x.w}; epi(m, n, q4, pf[j & 1][i]); }
                         }
                     }
                     __syncwarp();

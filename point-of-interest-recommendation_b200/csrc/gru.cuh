@@ -117,15 +117,19 @@ struct EpiBiasStore {               // C = acc + bias          (input projection
 
 struct EpiZR {   // z_r = sigmoid(ui[:2].x + wh[:2].h + bi[:2])   (GRU_Spatial.py:173-175); also r*h
     const float* AXj; const float* hp; float* Z; float* R; float* RH; int H;
+    int fast;        // tensor-core modes: __expf / __fdividef forms (the same ones the fused H <= 128 kernels use); fp32 FMA mode: expf
+    __device__ __forceinline__ float sg(float x) const { return fast ? __fdividef(1.f, 1.f + __expf(-x)) : sigmoidf_(x); }
     struct Pre { float4 ax, h; };
     __device__ __forceinline__ Pre pre(int m, int n) const {
+        // both loads unconditional (the z half reads an h it does not use): a predicated load next to a register clear made
+        // every request wait for the previous one (scoreboard aliasing, seen in the ncu source view)
         Pre p; p.ax = ldg4(AXj + (size_t)m * 3 * H + n);
-        p.h = n < H ? f4zero() : ldg4(hp + (size_t)m * H + (n - H));
+        p.h = ldg4(hp + (size_t)m * H + (n < H ? n : n - H));
         return p;
     }
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4], const Pre& p) const {
         const float4 ax = p.ax;
-        float4 s = make_float4(sigmoidf_(v[0] + ax.x), sigmoidf_(v[1] + ax.y), sigmoidf_(v[2] + ax.z), sigmoidf_(v[3] + ax.w));
+        float4 s = make_float4(sg(v[0] + ax.x), sg(v[1] + ax.y), sg(v[2] + ax.z), sg(v[3] + ax.w));
         if (n < H) {
             st4(Z + (size_t)m * H + n, s);
         } else {
@@ -139,6 +143,8 @@ struct EpiZR {   // z_r = sigmoid(ui[:2].x + wh[:2].h + bi[:2])   (GRU_Spatial.p
 
 struct EpiC {    // c = tanh(ui[2].x + wh[2].(r*h) + bi[2]); h_t = (1-z)*h + z*c   (GRU_Spatial.py:176-178)
     const float* AXj; const float* hp; const float* Z; float* C; float* Hn; int H;
+    int fast;
+    __device__ __forceinline__ float th(float x) const { return fast ? 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)) : tanhf(x); }
     struct Pre { float4 ax, z, h; };
     __device__ __forceinline__ Pre pre(int m, int n) const {
         Pre p; size_t o = (size_t)m * H + n;
@@ -149,7 +155,7 @@ struct EpiC {    // c = tanh(ui[2].x + wh[2].(r*h) + bi[2]); h_t = (1-z)*h + z*c
     __device__ __forceinline__ void operator()(int m, int n, const float (&v)[4], const Pre& p) const {
         const float4 ax = p.ax, z = p.z, h = p.h;
         size_t o = (size_t)m * H + n;
-        float4 c = make_float4(tanhf(v[0] + ax.x), tanhf(v[1] + ax.y), tanhf(v[2] + ax.z), tanhf(v[3] + ax.w));
+        float4 c = make_float4(th(v[0] + ax.x), th(v[1] + ax.y), th(v[2] + ax.z), th(v[3] + ax.w));
         st4(C + o, c);
         st4(Hn + o, make_float4((1.f - z.x) * h.x + z.x * c.x, (1.f - z.y) * h.y + z.y * c.y,
                                 (1.f - z.z) * h.z + z.z * c.z, (1.f - z.w) * h.w + z.w * c.w));
@@ -532,9 +538,9 @@ static int gru_forward(poi_engine* e, const poi_gru_params* p, const GruIdx& ix,
         const float* hp = Hs + (size_t)j * B * H;
         const float* AXj = AX + (size_t)j * B * 3 * H;
         size_t o = (size_t)j * B * H;
-        POI_TRY(gemm_tn(e, hp, H, p->wh, H, B, 2 * H, j == 0 ? 0 : H, EpiZR{AXj, hp, Z + o, R + o, RH + o, H}));
+        POI_TRY(gemm_tn(e, hp, H, p->wh, H, B, 2 * H, j == 0 ? 0 : H, EpiZR{AXj, hp, Z + o, R + o, RH + o, H, e->gemm_mode != 0 ? 1 : 0}));
         POI_TRY(gemm_tn(e, RH + o, H, p->wh + (size_t)2 * H * H, H, B, H, j == 0 ? 0 : H,
-                        EpiC{AXj, hp, Z + o, C + o, Hs + o + (size_t)B * H, H}));
+                        EpiC{AXj, hp, Z + o, C + o, Hs + o + (size_t)B * H, H, e->gemm_mode != 0 ? 1 : 0}));
     }
     e->gemm_cat = -1;
     return 0;

@@ -272,12 +272,16 @@ static int gru_step_mg_body(poi_engine* e, const poi_gru_params* p, const poi_se
         for (int r = 0; r < W; ++r) pt.shard[r] = pr->shard[r];
         const int dim4 = d / 4;
         POI_CAT(e, CAT_GATHER, 0, 0);
+        if (peer_gather_mode() == 1 && d * 4 * PG_WARPS * PG_ST <= (200 << 10)) {
+            POI_TRY(launch_gather_bulk(e, pt, d, seg_lt.uniq, seg_lt.n_unique, 0, 2 * LB, rows));
+        } else {
         const int lpr = dim4 <= 8 ? 8 : (dim4 <= 16 ? 16 : 32);
         const int64_t threads_needed = poi_cdiv(2 * LB, 4) * lpr;
         unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(threads_needed, 256), (int64_t)e->num_sms * 16));
         if (lpr == 8)       POI_LAUNCH(e, (k_gather_rows_sharded_dev<8, 4>), grid, 256, 0, pt, dim4, seg_lt.uniq, seg_lt.n_unique, rows);
         else if (lpr == 16) POI_LAUNCH(e, (k_gather_rows_sharded_dev<16, 4>), grid, 256, 0, pt, dim4, seg_lt.uniq, seg_lt.n_unique, rows);
         else                POI_LAUNCH(e, (k_gather_rows_sharded_dev<32, 4>), grid, 256, 0, pt, dim4, seg_lt.uniq, seg_lt.n_unique, rows);
+        }
     }
     // ---- forward + backward into the own outbox / dense buffer / loss sums (nothing is updated) ----
     MgCtx mg; mg.rows = rows; mg.global_batch = B * W; mg.dense_grads = pr->dense[me];

@@ -17,8 +17,13 @@
 // Ordering between ranks comes from the two small NCCL all-reduces the step needs anyway (dense gradients; the
 // step-start barrier), see dist.py.
 #pragma once
+#include <stdlib.h>
+#ifndef POI_PEER_GATHER_DEFAULT
+#define POI_PEER_GATHER_DEFAULT 0
+#endif
 #include "common.cuh"
 #include "sort.cuh"
+#include "gemm_tc.cuh"
 
 constexpr int POI_MAX_PEERS = 16;
 
@@ -54,6 +59,73 @@ k_gather_rows_sharded(PeerTable pt, int dim4, const int32_t* __restrict__ ids, i
                 if (src[u]) out4[(r0 + u) * dim4 + c] = v[u];
         }
     }
+}
+
+// The same gather with the copy engines instead of the load/store units: one thread per warp drives a ring of PG_ST row
+// buffers in shared memory -- cp.async.bulk peer/global -> shared (completion on an mbarrier), then cp.async.bulk shared ->
+// global -- so that a warp has PG_ST - 1 whole rows in flight over NVLink whatever its register budget.
+// ids: uint32 row ids; n_dev (device scalar) overrides n_host when given.
+constexpr int PG_WARPS = 8, PG_ST = 4;
+__global__ void __launch_bounds__(PG_WARPS * 32)
+k_gather_rows_sharded_bulk(PeerTable pt, uint32_t row_bytes, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ n_dev,
+                           int64_t n_host, float* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t pg_smem[];          // [PG_WARPS][PG_ST][row_bytes]
+    __shared__ uint64_t bar[PG_WARPS][PG_ST];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane != 0) return;
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    for (int s2 = 0; s2 < PG_ST; ++s2) tc::mbar_init(&bar[w][s2], 1);
+    tc::fence_barrier_init();
+    const int64_t gw = (int64_t)blockIdx.x * PG_WARPS + w, nw = (int64_t)gridDim.x * PG_WARPS;
+    const uint32_t sm0 = tc::smem_u32(pg_smem) + (uint32_t)(w * PG_ST) * row_bytes;
+    const uint32_t W = (uint32_t)pt.world;
+    auto issue_load = [&](int st, uint32_t id) {
+        const char* src = reinterpret_cast<const char*>(pt.shard[id % W]) + (size_t)(id / W) * row_bytes;
+        const uint32_t barp = tc::smem_u32(&bar[w][st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barp), "r"(row_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sm0 + (uint32_t)st * row_bytes), "l"(src), "r"(row_bytes), "r"(barp) : "memory");
+    };
+    // prologue: PG_ST - 1 rows in flight, the id of the next one in a register
+    for (int s2 = 0; s2 < PG_ST - 1; ++s2) { const int64_t r = gw + s2 * nw; if (r < n) issue_load(s2, ids[r]); }
+    int64_t rn = gw + (PG_ST - 1) * nw;                         // next row to request
+    uint32_t idn = rn < n ? ids[rn] : 0u;
+    int it = 0;
+    for (int64_t r = gw; r < n; r += nw, ++it) {
+        const int st = it % PG_ST;
+        tc::mbar_wait(&bar[w][st], (uint32_t)(it / PG_ST) & 1u);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(reinterpret_cast<char*>(out) + (size_t)r * row_bytes), "r"(sm0 + (uint32_t)st * row_bytes), "r"(row_bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // the buffer stored one iteration ago is free once every group but the newest has been read out of shared memory
+        if (rn < n) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue_load((it + PG_ST - 1) % PG_ST, idn);
+            rn += nw;
+            idn = rn < n ? ids[rn] : 0u;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+static inline int peer_gather_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* v = getenv("POI_PEER_GATHER"); mode = (v && v[0] == '1') ? 1 : ((v && v[0] == '0') ? 0 : POI_PEER_GATHER_DEFAULT); }
+    return mode;
+}
+static int launch_gather_bulk(poi_engine* e, const PeerTable& pt, int dim, const uint32_t* ids, const uint32_t* n_dev, int64_t n_host,
+                              int64_t n_max, float* out) {
+    const uint32_t row_bytes = (uint32_t)dim * 4u;
+    const size_t smem = (size_t)PG_WARPS * PG_ST * row_bytes;
+    static size_t attr = 0;
+    if (smem > attr) {
+        POI_CK(e, cudaFuncSetAttribute(k_gather_rows_sharded_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)200 << 10) / std::max<size_t>(smem, 1)));
+    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(n_max, PG_WARPS), (int64_t)e->num_sms * per_sm));
+    POI_LAUNCH(e, k_gather_rows_sharded_bulk, grid, PG_WARPS * 32, smem, pt, row_bytes, ids, n_dev, n_host, out);
+    return 0;
 }
 
 struct PullTable {                        // one entry per source rank, in rank order
