@@ -936,11 +936,17 @@ struct EpiPartial {       // split-K partial tile: part[blockIdx.z][m][n]
 // round-to-nearest by k_reduce_update.  Chains are therefore capped at ATB_MAX_CHAIN rows (more, shorter splits
 // than one wave needs) as long as the partial buffer stays small.
 constexpr int64_t ATB_MAX_CHAIN = 2048;
+constexpr int64_t ATB_MAX_PARTIAL_BYTES = (int64_t)6 << 30;     // C5 at 8192 users: 2 M rows -> ~1000 partial tiles per output tile
 static inline int atb_tc_splits(int num_sms, int tiles, int64_t kblocks, int N1, int N2) {
     int64_t splits = std::max<int64_t>(1, std::min<int64_t>(num_sms / std::max(tiles, 1), kblocks));
     const int64_t want = poi_cdiv(kblocks * tc::BK, ATB_MAX_CHAIN);
-    const int64_t cap = std::max<int64_t>(1, ((int64_t)48 << 20) / ((int64_t)N1 * N2 * 4));     // <= 48 MB of partials
+    const int64_t cap = std::max<int64_t>(1, ATB_MAX_PARTIAL_BYTES / ((int64_t)N1 * N2 * 4));
     splits = std::max(splits, std::min(want, cap));
+    // fill the last wave: the launch lasts ceil(tiles * splits / #SMs) CTA lifetimes either way -- more, shorter chains make
+    // every one of them shorter (c2, Ui gradient: 6 tiles x 62 splits = 2.5 waves of 64 k-blocks -> 74 splits = 3.0 waves of 54)
+    const int64_t waves = poi_cdiv((int64_t)tiles * splits, num_sms);
+    const int64_t full = waves * num_sms / std::max(tiles, 1);
+    if (full > splits && full <= cap) splits = full;
     return (int)std::min(splits, kblocks);
 }
 

@@ -7,7 +7,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(128, 128, 32), (128, 64, 64), (256, 384, 256), (1000, 201, 128), (4096, 256, 128), (4096, 128, 204),
-          (130, 72, 36), (33, 16, 32), (20000, 384, 256), (777, 130, 100)]
+          (130, 72, 36), (33, 16, 32), (20000, 384, 256), (777, 130, 100),
+          # >= 2 tiles per SM: the persistent kernels (mode 1: A operand in tensor memory), ragged M / N / K tails
+          (126976, 384, 256), (40000, 130, 100), (50001, 204, 36), (37889, 128, 512)]
 
 
 def _ref(A, W, b):
