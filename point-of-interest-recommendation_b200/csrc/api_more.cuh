@@ -540,9 +540,13 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
     POI_TRY(arena_get(e, (size_t)n * d, &SL));
     POI_TRY(arena_get(e, (size_t)n * d, &GU));
     POI_TRY(arena_get(e, (size_t)n * d, &GL));
-    size_t tma_smem = 0; int tma_nst = 0;
-    const bool use_tma = prme_score_tma_ok(d4, K, &tma_smem, &tma_nst) && !getenv("POI_PRME_NO_TMA");
-    const int blocks = (int)std::min<int64_t>(n, (int64_t)e->num_sms * (use_tma ? 2 : 8));
+    // one warp per check-in, single pass (k_prme_score_warp); d > 512: the CTA-per-check-in kernel (rows do not fit the registers).
+    // POI_PRME_SCORE=cta forces the latter (A/B).  Measured on c3: 0.172 ms against 0.335 ms for the CTA kernels (register
+    // version and a TMA-staged version, removed), which spend their time in the four block barriers of a check-in.
+    const char* score_env = getenv("POI_PRME_SCORE");
+    const bool use_warp = (!score_env || score_env[0] == 'w') && d4 <= 128;
+    const int blocks = use_warp ? (int)std::min<int64_t>(poi_cdiv(n, 8), (int64_t)e->num_sms * 2)
+                                : (int)std::min<int64_t>(n, (int64_t)e->num_sms * 8);
     POI_TRY(arena_get(e, (size_t)blocks, &part));
     POI_TRY(arena_get(e, 1, &out_dev));
     const size_t smem = (size_t)8 * 2 * d4 * sizeof(float4);
@@ -552,13 +556,12 @@ extern "C" int poi_prme_train_batch_k(poi_engine* e, float* du, int64_t n_user, 
     int64_t awarps = std::min<int64_t>(n_occ, (int64_t)e->num_sms * 64);
     unsigned agrid = (unsigned)std::max<int64_t>(poi_cdiv(awarps * 32, 256), 1);
     POI_CAT(e, CAT_MF, 0, 0.5 * algo);
-    if (use_tma) {
-        POI_CK(e, cudaFuncSetAttribute(k_prme_score_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
-        POI_LAUNCH(e, k_prme_score_tma, blocks, PRME_TMA_THREADS, tma_smem, du, dp, ds_, d4, b, tma_nst, (int)threshold, (float)cw, KP, KS, SL, GU, GL, part);
-    }
 #define PRME_BK(NCH)                                                                                                        \
     do {                                                                                                                    \
-        if (!use_tma) {                                                                                                     \
+        if (use_warp) {                                                                                                     \
+            POI_LAUNCH(e, (k_prme_score_warp<(NCH <= 4 ? NCH : 4)>), blocks, 256, 0, du, dp, ds_, d4, b, (int)threshold, (float)cw, KP, KS,  \
+                       SL, GU, GL, part);                                                                                   \
+        } else {                                                                                                            \
             POI_CK(e, cudaFuncSetAttribute(k_prme_score<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
             POI_LAUNCH(e, (k_prme_score<NCH>), blocks, 256, smem, du, dp, ds_, d4, b, (int)threshold, (float)cw, KP, KS,    \
                        SL, GU, GL, part);                                                                                   \

@@ -225,6 +225,113 @@ k_prme_score(const float* __restrict__ du, const float* __restrict__ dp, const f
     if (tid == 0) part[blockIdx.x] = loss_acc;
 }
 
+// Phase A, one WARP per check-in, one pass, no block barrier (the CTA-per-check-in kernels above / below spend most of their
+// time in the four __syncthreads of a check-in: ncu, barrier-stall bound at 29 % of the issue slots).  What makes one pass
+// possible: c_j = sigmoid(D_0 - D_j) needs only the positive's distance, and
+//     sum_j c_j 2cp (du - dp[x_j])  with  c_0 = -G, G = sum_{j>=1} c_j      =   2cp sum_{j>=1} c_j (dp[x_0] - dp[x_j])
+// (likewise for ds[prev]), so with the positive's two rows kept in registers every negative is loaded, scored and folded
+// into the two gradient rows while it is still in registers: each row is read exactly once, nothing is staged in shared
+// memory.  A lane owns NCH float4 columns; the K candidate ids are read lane-parallel and broadcast by shuffles; UN
+// candidates (4 NCH UN float4 per lane) are in flight together.  Same outputs as k_prme_score.
+template <int NCH>
+__global__ void __launch_bounds__(256, NCH <= 2 ? 2 : 1)
+k_prme_score_warp(const float* __restrict__ du, const float* __restrict__ dp, const float* __restrict__ ds, int d4, PrmeBatchIdx b,
+                  int thd, float cw, float* __restrict__ KP, float* __restrict__ KS, float* __restrict__ SL,
+                  float* __restrict__ GU, float* __restrict__ GL, double* __restrict__ part) {
+    __shared__ double sloss[8];
+    constexpr int UN = NCH <= 2 ? 2 : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = b.K, R = K + 2;
+    double loss_acc = 0.0;                                  // lane 0 only
+    for (int i = blockIdx.x * 8 + warp; i < b.N; i += gridDim.x * 8) {
+        const int32_t uu = b.u[i], xp = b.p[i], xl = b.prev[i];
+        const bool far = b.gap[i] > thd;
+        const float w = sqrtf(sqrtf(1.0f + b.dist[i]));
+        const float cp = far ? 1.f : w * cw, cs = far ? 0.f : w * (1.f - cw);
+        int32_t qid[(PRME_MAXK + 31) / 32];
+#pragma unroll
+        for (int t = 0; t < (PRME_MAXK + 31) / 32; ++t) qid[t] = lane + 32 * t < K ? b.q[(size_t)i * K + lane + 32 * t] : 0;
+        float4 u[NCH], sl[NCH], p0[NCH], s0[NCH], au[NCH], as[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int c = lane + 32 * k;
+            au[k] = f4zero(); as[k] = f4zero();
+            if (c < d4) {
+                u[k] = ldg4(du + ((size_t)uu * d4 + c) * 4); sl[k] = ldg4(ds + ((size_t)xl * d4 + c) * 4);
+                p0[k] = ldg4(dp + ((size_t)xp * d4 + c) * 4); s0[k] = ldg4(ds + ((size_t)xp * d4 + c) * 4);
+            }
+        }
+        float D0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            if (lane + 32 * k < d4) {
+                const float4 a = f4sub(u[k], p0[k]), q = f4sub(s0[k], sl[k]);
+                D0 += cp * (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) + cs * (q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+            }
+        }
+        D0 = warp_sum(D0);
+        float G = 0.f;
+#pragma unroll
+        for (int t = 0; t < (PRME_MAXK + 31) / 32; ++t) {
+            if (32 * t >= K) break;
+            const int nl = min(32, K - 32 * t);
+            for (int l0 = 0; l0 < nl; l0 += UN) {
+                float4 P[UN][NCH], S[UN][NCH];
+#pragma unroll
+                for (int v = 0; v < UN; ++v) {
+                    const int32_t x = __shfl_sync(0xffffffffu, qid[t], min(l0 + v, nl - 1));
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        const int c = lane + 32 * k;
+                        if (c < d4) { P[v][k] = ldg4(dp + ((size_t)x * d4 + c) * 4); S[v][k] = ldg4(ds + ((size_t)x * d4 + c) * 4); }
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < UN; ++v) {
+                    if (l0 + v >= nl) break;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        if (lane + 32 * k < d4) {
+                            const float4 a = f4sub(u[k], P[v][k]), q = f4sub(S[v][k], sl[k]);
+                            acc += cp * (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) + cs * (q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+                        }
+                    }
+                    acc = warp_sum(acc);
+                    const float xx = acc - D0, g = sigmoidf_(-xx);
+                    const int j = 32 * t + l0 + v + 1;
+                    if (lane == 0) {
+                        loss_acc += (double)logsigmoidf_(xx);
+                        KP[(size_t)i * R + j] = g * 2.f * cp; KS[(size_t)i * R + j] = g * 2.f * cs;
+                    }
+                    G += g;
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        if (lane + 32 * k < d4) { au[k] = f4fma(g, f4sub(p0[k], P[v][k]), au[k]); as[k] = f4fma(g, f4sub(s0[k], S[v][k]), as[k]); }
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            KP[(size_t)i * R] = -G * 2.f * cp; KS[(size_t)i * R] = -G * 2.f * cs;
+            KP[(size_t)i * R + K + 1] = 0.f; KS[(size_t)i * R + K + 1] = 0.f;
+        }
+        const float kp2 = 2.f * cp, ks2 = 2.f * cs;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d4) {
+                st4(GU + ((size_t)i * d4 + c) * 4, make_float4(-kp2 * au[k].x, -kp2 * au[k].y, -kp2 * au[k].z, -kp2 * au[k].w));
+                st4(GL + ((size_t)i * d4 + c) * 4, make_float4(ks2 * as[k].x, ks2 * as[k].y, ks2 * as[k].z, ks2 * as[k].w));
+                st4(SL + ((size_t)i * d4 + c) * 4, sl[k]);
+            }
+        }
+    }
+    if (lane == 0) sloss[warp] = loss_acc;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int ww = 0; ww < 8; ++ww) t += sloss[ww]; part[blockIdx.x] = t; }
+}
+
 // Phase B.  One warp per unique row r of the batch; dp[r] and ds[r] are updated together (same key list).  Occurrence
 // o = i R + j of r contributes  KP[o] (dp[r] - du[u_i])  to d upq / d dp[r]  and  KS[o] (ds[r] - SL[i])  (j <= K) or GL[i]
 // (j = K + 1, the prev occurrence) to d upq / d ds[r]; ascent with the L2 term once per occurrence:
@@ -315,154 +422,6 @@ k_prme_apply(SegList seg, const float* __restrict__ du, float* __restrict__ dp, 
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Phase A with the rows staged by TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): the
-// 2K + 4 rows of a check-in (du[u], ds[prev], dp[x_j], ds[x_j], j = 0..K) are one 1 KB-per-row burst into a shared-memory
-// stage; as many stages as fit in ~110 KB (2 at K = 20, d = 256), so the rows of the next check-in(s) stream in while
-// check-in i is scored out of shared memory -- no register holds an in-flight row, and every row is read from L2 / HBM
-// exactly once (the register version re-reads the rows in its second pass).  Persistent CTAs of 8 warps, two per SM.
-// Round-2 ncu (profiles/r2_ncu_full_prme_score_apply_v1.csv): barrier-stall bound, 29 % of the issue slots, 1.4 TB/s of
-// DRAM reads (L2 serves the rest: the batch touches each of the 100k rows 3.7 times).
-// Used when 256 % (d/4) == 0 and at least two stages fit.
-// Stage layout (rows of d floats): 0 du[u] | 1 ds[prev] | 2 .. K+2 dp[x_j] | K+3 .. 2K+3 ds[x_j].
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int PRME_TMA_THREADS = 256;
-constexpr int PRME_TMA_MAXST = 8;
-
-__global__ void __launch_bounds__(PRME_TMA_THREADS)
-k_prme_score_tma(const float* __restrict__ du, const float* __restrict__ dp, const float* __restrict__ ds, int d4, PrmeBatchIdx b,
-                 int nst, int thd, float cw, float* __restrict__ KP, float* __restrict__ KS, float* __restrict__ SL,
-                 float* __restrict__ GU, float* __restrict__ GL, double* __restrict__ part) {
-    extern __shared__ __align__(128) unsigned char prme_tma_smem[];
-    __shared__ uint64_t bar[PRME_TMA_MAXST];
-    __shared__ float sD[PRME_MAXK + 1], sg[PRME_MAXK + 1];
-    __shared__ double sloss[PRME_TMA_THREADS / 32];
-    constexpr int NW = PRME_TMA_THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = b.K, R = K + 2, NR = 2 * K + 4, d = d4 * 4;
-    const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = row_bytes * (uint32_t)NR;
-    float4* red = reinterpret_cast<float4*>(prme_tma_smem + (size_t)nst * stage_bytes);   // [ngrp][2][d4]
-    const int ngrp = PRME_TMA_THREADS / d4;
-    if (tid == 0) { for (int s = 0; s < nst; ++s) tc::mbar_init(&bar[s], 1); tc::fence_barrier_init(); }
-    __syncthreads();
-    // Warp 0 issues the bulk copies: lane 0 arms the stage's barrier with the byte count, then lane l sends rows l, l + 32,
-    // ... (one instruction per row).  nst stages: the rows of check-in i + nst - 1 are requested while check-in i is scored,
-    // so a request has nst - 1 iterations to land (HBM latency ~ 2 us, an iteration ~ 1 us).  The source pointers of a
-    // check-in are looked up one iteration AHEAD of their use (src_next): the index loads are off the critical path.
-    constexpr int MAXRPL = (2 * PRME_MAXK + 4 + 31) / 32;       // rows per lane, upper bound
-    const int rpl = (NR + 31) / 32;
-    const float* src_next[MAXRPL];
-    auto lookup = [&](int i) {
-        if (warp != 0) return;
-#pragma unroll
-        for (int q = 0; q < MAXRPL; ++q) {
-            const int r = lane + 32 * q;
-            if (q < rpl && r < NR && i < b.N) {
-                if (r == 0) src_next[q] = du + (size_t)b.u[i] * d;
-                else if (r == 1) src_next[q] = ds + (size_t)b.prev[i] * d;
-                else {
-                    const int jj = r - 2 <= K ? r - 2 : r - 3 - K;
-                    const size_t x = (size_t)(jj == 0 ? b.p[i] : b.q[(size_t)i * K + jj - 1]);
-                    src_next[q] = (r - 2 <= K ? dp : ds) + x * d;
-                }
-            }
-        }
-    };
-    auto issue = [&](int s) {
-        if (warp != 0) return;
-        tc::fence_async_smem();                        // generic-proxy reads of this stage (nst iterations ago) before async writes
-        const uint32_t barp = tc::smem_u32(&bar[s]);
-        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barp), "r"(stage_bytes) : "memory");
-        __syncwarp();
-        const uint32_t base = tc::smem_u32(prme_tma_smem) + (uint32_t)s * stage_bytes;
-#pragma unroll
-        for (int q = 0; q < MAXRPL; ++q) {
-            const int r = lane + 32 * q;
-            if (q < rpl && r < NR)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(base + (uint32_t)r * row_bytes), "l"(src_next[q]), "r"(row_bytes), "r"(barp) : "memory");
-        }
-    };
-    double loss_acc = 0.0;                              // thread k (1 <= k <= K) accumulates its own negative's terms
-    int it = 0;
-    const int G0 = (int)gridDim.x;
-    // prologue: check-ins 0 .. nst-2 of this CTA in flight, pointers of check-in nst-1 ready
-    for (int s = 0; s < nst - 1; ++s) {
-        const int i0 = blockIdx.x + s * G0;
-        if (i0 < b.N) { lookup(i0); issue(s); }
-    }
-    lookup(blockIdx.x + (nst - 1) * G0);
-    for (int i = blockIdx.x; i < b.N; i += G0, ++it) {
-        const int s = it % nst;
-        if (i + (nst - 1) * G0 < b.N) { issue((it + nst - 1) % nst); lookup(i + nst * G0); }
-        const bool far = b.gap[i] > thd;
-        const float w = sqrtf(sqrtf(1.0f + b.dist[i]));
-        const float cp = far ? 1.f : w * cw, cs = far ? 0.f : w * (1.f - cw);
-        tc::mbar_wait(&bar[s], (uint32_t)(it / nst) & 1u);
-        const float4* st = reinterpret_cast<const float4*>(prme_tma_smem + (size_t)s * stage_bytes);
-        const float4* U = st; const float4* SLr = st + d4;
-        const float4* DP = st + 2 * (size_t)d4; const float4* DS = st + (size_t)(K + 3) * d4;
-        // ---- pass 1: D(x_j), one warp per candidate ----
-        for (int j = warp; j <= K; j += NW) {
-            float acc = 0.f;
-            for (int c = lane; c < d4; c += 32) {
-                const float4 a = f4sub(U[c], DP[(size_t)j * d4 + c]);
-                const float4 q = f4sub(DS[(size_t)j * d4 + c], SLr[c]);
-                acc += cp * (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) + cs * (q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) sD[j] = acc;
-        }
-        __syncthreads();
-        if (tid >= 1 && tid <= K) { const float x = sD[tid] - sD[0]; sg[tid] = sigmoidf_(-x); loss_acc += (double)logsigmoidf_(x); }
-        __syncthreads();
-        // G = sum_k g_k: every warp adds the same values in the same order (lane partial sums, fixed shuffle tree)
-        float G = 0.f;
-        for (int k = 1 + lane; k <= K; k += 32) G += sg[k];
-        G = warp_sum(G);
-        if (tid <= K + 1) {
-            const float cj = tid == 0 ? -G : (tid <= K ? sg[tid] : 0.f);
-            KP[(size_t)i * R + tid] = cj * 2.f * cp; KS[(size_t)i * R + tid] = cj * 2.f * cs;
-        }
-        // ---- pass 2: thread = (float4 column c, candidate group g): d/d du and d/d ds[prev] partial sums ----
-        {
-            const int c = tid % d4, g = tid / d4;
-            float4 au = f4zero(), as = f4zero();
-            const float4 u = U[c], sl = SLr[c];
-            for (int j = g; j <= K; j += ngrp) {
-                const float cj = j == 0 ? -G : sg[j];
-                au = f4fma(cj * 2.f * cp, f4sub(u, DP[(size_t)j * d4 + c]), au);
-                as = f4fma(cj * 2.f * cs, f4sub(sl, DS[(size_t)j * d4 + c]), as);
-            }
-            red[(g * 2 + 0) * d4 + c] = au; red[(g * 2 + 1) * d4 + c] = as;
-        }
-        __syncthreads();
-        if (tid < 2 * d4) {
-            const int c = tid % d4, which = tid / d4;
-            float4 t = red[which * d4 + c];
-            for (int g = 1; g < ngrp; ++g) t = f4add(t, red[(g * 2 + which) * d4 + c]);      // group order: fixed
-            if (which == 0) st4(GU + ((size_t)i * d4 + c) * 4, make_float4(-t.x, -t.y, -t.z, -t.w));
-            else { st4(GL + ((size_t)i * d4 + c) * 4, t); st4(SL + ((size_t)i * d4 + c) * 4, SLr[c]); }
-        }
-        __syncthreads();          // stage s, red, sD, sg are free again
-    }
-    // block loss: lanes in a fixed tree, then the warps in order
-    loss_acc = warp_sum_d(loss_acc);
-    if (lane == 0) sloss[warp] = loss_acc;
-    __syncthreads();
-    if (tid == 0) { double t = 0.0; for (int ww = 0; ww < NW; ++ww) t += sloss[ww]; part[blockIdx.x] = t; }
-}
-
-// stages that fit beside the reduction scratch in ~200 KB; the path needs >= 2 and d/4 dividing the block size
-static bool prme_score_tma_ok(int d4, int K, size_t* smem, int* nst) {
-    const size_t stage = (size_t)(2 * K + 4) * d4 * 16, scratch = (size_t)2 * PRME_TMA_THREADS * 16 + 128;
-    // two CTAs per SM (measured: 296 CTAs x 8 warps x 2 stages 0.33 ms per 16 384 check-ins; 148 CTAs x 16 warps x 4 stages
-    // 0.60 ms -- the CTA is bound by its own barrier-separated phases, so more CTAs beat deeper prefetch)
-    int n = (int)std::min<size_t>(PRME_TMA_MAXST, (110 * 1024 - scratch) / stage);
-    *nst = n; *smem = (size_t)n * stage + scratch;
-    return d4 >= 1 && d4 <= 256 && PRME_TMA_THREADS % d4 == 0 && 2 * d4 <= PRME_TMA_THREADS && n >= 2;
 }
 
 // fixed-order sum of n doubles by one warp: lane l adds part[l], part[l + 32], ... in order, then a fixed shuffle tree
