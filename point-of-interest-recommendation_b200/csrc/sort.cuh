@@ -152,6 +152,57 @@ k_small_sort(const uint32_t* keys_in, int n, int np2, uint32_t* keys_out, uint32
     }
 }
 
+// The same sort followed by the segment arrays, in the same launch (lists <= SMALL_SORT_MAX keys: every index list of a
+// one-by-one call, the reference's own mode -- 4 launches per list became 1).  Thread t owns the np2 / blockDim consecutive
+// sorted entries [t * per, (t + 1) * per): head flags, a block scan of the per-thread head counts, then the writes.
+__global__ void __launch_bounds__(1024)
+k_small_sort_seg(const uint32_t* keys_in, int n, int np2, uint32_t* keys_out, uint32_t* vals_out,
+                 uint32_t* seg_start, uint32_t* uniq, uint32_t* n_unique, uint32_t* seg_of_occ) {
+    extern __shared__ unsigned long long s_comp[];
+    __shared__ uint32_t warp_tot[32];
+    for (int i = threadIdx.x; i < np2; i += blockDim.x)
+        s_comp[i] = i < n ? (((unsigned long long)keys_in[i] << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    bool asc = (i & k) == 0;
+                    unsigned long long a = s_comp[i], b = s_comp[ixj];
+                    if ((a > b) == asc) { s_comp[i] = b; s_comp[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (np2 + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int i0 = tid * per, i1 = min(n, i0 + per);
+    uint32_t heads = 0;
+    for (int i = i0; i < i1; ++i) {
+        const uint32_t k = (uint32_t)(s_comp[i] >> 32);
+        heads += (i == 0 || k != (uint32_t)(s_comp[i - 1] >> 32)) ? 1u : 0u;
+    }
+    uint32_t inc = heads;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    uint32_t ex = inc - heads;
+    for (int ww = 0; ww < wid; ++ww) ex += warp_tot[ww];
+    for (int i = i0; i < i1; ++i) {
+        const unsigned long long c = s_comp[i];
+        const uint32_t k = (uint32_t)(c >> 32), v = (uint32_t)(c & 0xffffffffu);
+        const bool head = i == 0 || k != (uint32_t)(s_comp[i - 1] >> 32);
+        const uint32_t sid = head ? ex : ex - 1u;
+        keys_out[i] = k; vals_out[i] = v;
+        if (head) { seg_start[sid] = (uint32_t)i; uniq[sid] = k; ++ex; }
+        if (seg_of_occ) seg_of_occ[v] = sid;
+        if (i == n - 1) { *n_unique = sid + 1u; seg_start[sid + 1u] = (uint32_t)n; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // large path: LSD radix sort, 8 bits per pass, stable
 // ---------------------------------------------------------------------------------------------
@@ -658,14 +709,15 @@ static int build_segments(poi_engine* e, const uint32_t* keys_dev, int64_t n, ui
     POI_CAT(e, CAT_INDEX, 0, 0);
     size_t nn = (size_t)std::max<int64_t>(n, 1);
     const bool fused = e->fused_sort && n > SMALL_SORT_MAX;
-    if (fused) {
+    const bool small_fused = e->fused_sort && n > 0 && n <= SMALL_SORT_MAX;
+    if (fused || small_fused) {
         POI_TRY(arena_get(e, nn, &out->keys));
         POI_TRY(arena_get(e, nn, &out->vals));
     } else {
         POI_TRY(sort_pairs(e, keys_dev, n, bound, &out->keys, &out->vals));
     }
     uint32_t* excl = nullptr;
-    if (!fused) POI_TRY(arena_get(e, nn, &excl));
+    if (!fused && !small_fused) POI_TRY(arena_get(e, nn, &excl));
     POI_TRY(arena_get(e, nn + 1, &out->seg_start));
     POI_TRY(arena_get(e, nn, &out->uniq));
     POI_TRY(arena_get(e, 4, &out->n_unique));
@@ -673,6 +725,14 @@ static int build_segments(poi_engine* e, const uint32_t* keys_dev, int64_t n, ui
     if (want_inverse) POI_TRY(arena_get(e, nn, &out->seg_of_occ));
     if (n <= 0) { POI_CK(e, cudaMemsetAsync(out->n_unique, 0, 4, e->stream)); return 0; }
     if (fused) return fused_sort_launch(e, keys_dev, n, bound, out->keys, out->vals, out);
+    if (small_fused) {
+        int np2 = 32;
+        while (np2 < n) np2 <<= 1;
+        const int threads = std::min(1024, std::max(32, np2 / 2));
+        POI_LAUNCH(e, k_small_sort_seg, 1, threads, (size_t)np2 * 8, keys_dev, (int)n, np2, out->keys, out->vals, out->seg_start,
+                   out->uniq, out->n_unique, out->seg_of_occ);
+        return 0;
+    }
     unsigned g = (unsigned)poi_cdiv(n, 256);
     const int64_t nb = poi_cdiv(n, SCAN_TILE);
     uint32_t* bs = nullptr;

@@ -1,20 +1,27 @@
 #!/bin/bash
-# The multi-GPU measurements of round 2 on ONE box (run under `gpurun --gpus 8`): c5 strong scaling (global batch fixed),
-# c2 weak scaling, the multi-rank correctness tests.  Results land in gpurun_out/.
+# The multi-GPU measurements of round 2 at N ranks of ONE box: `gpurun --gpus N -- bash tools/scale_run.sh N [prefix]`
+# (one box per N: a call is charged N x its box time).  c5 strong scaling (global batch 8192 users), c2 weak scaling
+# (4096 users per GPU), c4 row-sharded at N = 2; at N = 8 also the bulk-copy variant of the sharded gather and the
+# peer-fabric micro-benchmark.  Results land in gpurun_out/.
+N=${1:-8}; P=${2:-r2f}
 mkdir -p gpurun_out
-B=${C5_BATCH:-8192}
-for N in 2 4 8; do
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) \
-    bench.py --config c5 --scaling strong --batch $B --gpus $N --steps 4 --warmup 3 > gpurun_out/r2_c5_strong_b${B}_n$N.json 2> gpurun_out/r2_c5_strong_b${B}_n$N.err
-  tail -c 300 gpurun_out/r2_c5_strong_b${B}_n$N.err
-done
-# the largest global batch one GPU can hold (12288 users: 441 ms at N = 1), at N = 8
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29650 \
-  bench.py --config c5 --scaling strong --batch 12288 --gpus 8 --steps 4 --warmup 3 > gpurun_out/r2_c5_strong_b12288_n8.json 2> gpurun_out/r2_c5_strong_b12288_n8.err
-for N in 2 4 8; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+N)) \
-    bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_c2_weak_n$N.json 2> gpurun_out/r2_c2_weak_n$N.err
-  tail -c 200 gpurun_out/r2_c2_weak_n$N.err
-done
-(timeout 500 python -m pytest tests/test_gpu_multigpu.py -m gpu -q -rf 2>&1 | tail -30) > gpurun_out/r2_mg_tests_8gpu.log
-tail -3 gpurun_out/r2_mg_tests_8gpu.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 400 $TR --master-port 29601 bench.py --config c5 --scaling strong --batch 8192 --gpus $N --steps 4 --warmup 3 \
+  > gpurun_out/${P}_c5_b8192_n$N.json 2> gpurun_out/${P}_c5_b8192_n$N.err
+tail -c 200 gpurun_out/${P}_c5_b8192_n$N.err
+timeout 300 $TR --master-port 29602 bench.py --gpus $N --steps 20 --warmup 5 \
+  > gpurun_out/${P}_c2_weak_n$N.json 2> gpurun_out/${P}_c2_weak_n$N.err
+tail -c 200 gpurun_out/${P}_c2_weak_n$N.err
+if [ "$N" = "2" ]; then
+  timeout 300 $TR --master-port 29603 bench.py --config c4 --gpus 2 --steps 10 --warmup 3 \
+    > gpurun_out/${P}_c4_n2.json 2> gpurun_out/${P}_c4_n2.err
+fi
+if [ "$N" = "8" ]; then
+  POI_PEER_GATHER=1 timeout 400 $TR --master-port 29604 bench.py --config c5 --scaling strong --batch 8192 --gpus $N --steps 4 --warmup 3 \
+    > gpurun_out/${P}_c5_b8192_n${N}_bulk.json 2> gpurun_out/${P}_c5_b8192_n${N}_bulk.err
+  for m in 0 1; do
+    POI_PEER_GATHER=$m timeout 200 $TR --master-port $((29605+m)) tools/peer_gather_bench.py 2>/dev/null | grep "^{" > gpurun_out/${P}_peer_n${N}_mode$m.json
+    cat gpurun_out/${P}_peer_n${N}_mode$m.json
+  done
+fi
+ls -la gpurun_out/${P}_*n$N* | awk '{print $5, $9}'
