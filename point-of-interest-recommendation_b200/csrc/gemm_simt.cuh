@@ -332,6 +332,55 @@ static int launch_colsum(poi_engine* e, const float* A, int lda, int64_t M, int 
     return 0;
 }
 
+// All split reductions of a step in ONE launch (the six k_reduce_update launches of a Distance2Pre step cost 14 us each,
+// most of it launch latency and an un-batched chain of loads).  Entry t owns the blocks [block0[t], block0[t + 1]); every
+// output element sums its partials in split order (fixed), then either takes the SGD step or lands in the gradient buffer.
+constexpr int REDUCE_MAX = 8;
+struct ReduceSet {
+    const float* part[REDUCE_MAX]; float* dst[REDUCE_MAX];
+    int splits[REDUCE_MAX], N1[REDUCE_MAX], N2[REDUCE_MAX], ld[REDUCE_MAX], n1[REDUCE_MAX], n2[REDUCE_MAX];
+    unsigned block0[REDUCE_MAX + 1];
+    int n, update;
+};
+__global__ void __launch_bounds__(256)
+k_reduce_multi(ReduceSet rs, float alpha, float lambda) {
+    int t = 0;
+    while (t + 1 < rs.n && blockIdx.x >= rs.block0[t + 1]) ++t;
+    const int64_t idx = (int64_t)(blockIdx.x - rs.block0[t]) * blockDim.x + threadIdx.x;
+    const int n2 = rs.n2[t];
+    if (idx >= (int64_t)rs.n1[t] * n2) return;
+    const int i = (int)(idx / n2), j = (int)(idx % n2);
+    const float* p = rs.part[t] + (size_t)i * rs.N2[t] + j;
+    const size_t stride = (size_t)rs.N1[t] * rs.N2[t];
+    const int splits = rs.splits[t];
+    float g = 0.f;
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(s + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g += v[u];
+    }
+    for (; s < splits; ++s) g += __ldg(p + (size_t)s * stride);
+    float* d = rs.dst[t] + (size_t)i * rs.ld[t] + j;
+    if (rs.update) { const float th = *d; *d = th - alpha * (g + lambda * th); }
+    else *d = g;
+}
+static inline void reduce_set_add(ReduceSet& rs, const AtbPlan& p, float* theta, int ldt, int n1_true, int n2_true, float* grad_out) {
+    const int t = rs.n++;
+    rs.part[t] = p.part; rs.splits[t] = p.splits; rs.N1[t] = p.N1; rs.N2[t] = p.N2;
+    rs.dst[t] = grad_out ? grad_out : theta; rs.ld[t] = ldt; rs.n1[t] = n1_true; rs.n2[t] = n2_true;
+    rs.update = grad_out ? 0 : 1;
+    rs.block0[t + 1] = rs.block0[t] + (unsigned)poi_cdiv((int64_t)n1_true * n2_true, 256);
+}
+static int launch_reduce_set(poi_engine* e, const ReduceSet& rs, float alpha, float lambda) {
+    if (rs.n == 0) return 0;
+    POI_CAT(e, CAT_WGRAD, 0, 0);
+    POI_LAUNCH(e, k_reduce_multi, rs.block0[rs.n], 256, 0, rs, alpha, lambda);
+    return 0;
+}
+
 static int launch_reduce_to(poi_engine* e, const AtbPlan& p, float* theta, int ldt, int n1_true, int n2_true,
                             float alpha, float lambda, float* grad_out) {
     if (!grad_out) return launch_reduce_update(e, p, theta, ldt, n1_true, n2_true, alpha, lambda);

@@ -687,14 +687,16 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
         if (head) POI_TRY(launch_colsum(e, S, nDp, TB, nDp, &g_bs));
     }
     float* dg = mg ? mg->dense_grads : nullptr;
-    POI_TRY(launch_reduce_to(e, g_ui, p->ui, din, 3 * H, din, alpha, lambda, dg ? dg + ML.ui : nullptr));
-    POI_TRY(launch_reduce_to(e, g_whzr, p->wh, H, 2 * H, H, alpha, lambda, dg ? dg + ML.wh : nullptr));
-    POI_TRY(launch_reduce_to(e, g_whc, p->wh + (size_t)2 * H * H, H, H, H, alpha, lambda, dg ? dg + ML.wh + (size_t)2 * H * H : nullptr));
-    POI_TRY(launch_reduce_to(e, g_bi, p->bi, 3 * H, 1, 3 * H, alpha, lambda, dg ? dg + ML.bi : nullptr));
+    ReduceSet rs; memset(&rs, 0, sizeof(rs));
+    reduce_set_add(rs, g_ui, p->ui, din, 3 * H, din, dg ? dg + ML.ui : nullptr);
+    reduce_set_add(rs, g_whzr, p->wh, H, 2 * H, H, dg ? dg + ML.wh : nullptr);
+    reduce_set_add(rs, g_whc, p->wh + (size_t)2 * H * H, H, H, H, dg ? dg + ML.wh + (size_t)2 * H * H : nullptr);
+    reduce_set_add(rs, g_bi, p->bi, 3 * H, 1, 3 * H, dg ? dg + ML.bi : nullptr);
     if (head) {
-        POI_TRY(launch_reduce_to(e, g_vs, p->vs, H, nD, H, alpha, lambda, dg ? dg + ML.vs : nullptr));
-        POI_TRY(launch_reduce_to(e, g_bs, p->bs, nD, 1, nD, alpha, lambda, dg ? dg + ML.bs : nullptr));
+        reduce_set_add(rs, g_vs, p->vs, H, nD, H, dg ? dg + ML.vs : nullptr);
+        reduce_set_add(rs, g_bs, p->bs, nD, 1, nD, dg ? dg + ML.bs : nullptr);
     }
+    POI_TRY(launch_reduce_set(e, rs, alpha, lambda));
     POI_CAT(e, CAT_REDUCE, 0, 0);
     POI_LAUNCH(e, k_finalize_gru, 1, 256, 0, part, loss_blocks, p->scal, head ? 1 : 0,
                (double)n_nonempty * 0.6931471805599453, (double)scale, alpha, lambda, out_dev,
@@ -717,7 +719,7 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
             src.emit_rows = mg->dense_grads + ML.di; src.emit_cnt = mg->dense_grads + ML.dicnt; src.emit_by_key = 1;
         }
         POI_TRY(launch_rows_update(e, seg_di, p->di, d, alpha, lambda, src, ROW_LONG_THRESH,
-                                   (double)TB * d * 4 + 4.0 * (double)LB));
+                                   (double)TB * d * 4 + 4.0 * (double)LB, nD));
     }
     phase_mark(e, 7);
 

@@ -267,6 +267,28 @@ __global__ void k_long_offsets(SegList seg, const uint32_t* __restrict__ long_li
     chunk_off[nl] = run;
 }
 
+// Small tables (the 201 distance-interval rows of Distance2Pre: every row is a hot row): all segments go through the chunked
+// path, so the list of "long" segments is simply 0 .. n_unique-1 and the chunk offsets are one block scan (n_unique <= 1024)
+// -- no pass of the per-segment kernel (measured 50 us for 201 rows) and no serial offset loop (15 us).
+__global__ void __launch_bounds__(1024)
+k_all_long_offsets(SegList seg, uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t* __restrict__ chunk_off) {
+    __shared__ uint32_t wtot[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nu = *seg.n_unique;
+    uint32_t c = 0;
+    if ((uint32_t)tid < nu) c = (seg.seg_start[tid + 1] - seg.seg_start[tid] + ROW_CHUNK - 1) / ROW_CHUNK;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wtot[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < wid; ++w) base += wtot[w];
+    if ((uint32_t)tid < nu) { long_list[tid] = (uint32_t)tid; chunk_off[tid] = base + inc - c; }
+    if ((uint32_t)tid + 1 == nu) chunk_off[nu] = base + inc;
+    if (tid == 0) { *long_count = nu; if (nu == 0) chunk_off[0] = 0; }
+}
+
 __global__ void __launch_bounds__(256)
 k_long_partial(SegList seg, int dim4, RowSrc src, const uint32_t* __restrict__ long_list,
                const uint32_t* __restrict__ long_count, const uint32_t* __restrict__ chunk_off,
@@ -332,13 +354,28 @@ k_long_final(SegList seg, float* __restrict__ table, int dim4, float alpha, floa
 
 static int launch_rows_update(poi_engine* e, const SegList& seg, float* table, int dim,
                               float alpha, float lambda, const RowSrc& src, int long_thresh,
-                              double algo_bytes = 0.0) {
+                              double algo_bytes = 0.0, int64_t table_rows = 0) {
     if (seg.n <= 0) return 0;
     POI_CAT(e, CAT_ROWS, 0, algo_bytes);
     const int dim4 = dim / 4;
     uint32_t *long_list = nullptr, *long_count = nullptr;
     POI_TRY(arena_get(e, (size_t)seg.n, &long_list));
     POI_TRY(arena_get(e, 4, &long_count));
+    if (table_rows > 0 && table_rows <= 1024 && seg.n > 8 * table_rows && !src.skip_single) {
+        // small table, many occurrences per row: the chunked path for every segment (k_all_long_offsets)
+        const size_t max_chunks = (size_t)seg.n / ROW_CHUNK + (size_t)table_rows + 2;
+        uint32_t* chunk_off = nullptr; float4* partial = nullptr; float* partial_w = nullptr;
+        POI_TRY(arena_get(e, (size_t)table_rows + 2, &chunk_off));
+        POI_TRY(arena_get(e, max_chunks * dim4, &partial));
+        POI_TRY(arena_get(e, max_chunks, &partial_w));
+        POI_LAUNCH(e, k_all_long_offsets, 1, 1024, 0, seg, long_list, long_count, chunk_off);
+        const size_t smem = (size_t)8 * dim4 * sizeof(float4);
+        unsigned lgrid = (unsigned)std::min<int64_t>((int64_t)max_chunks, (int64_t)e->num_sms * 8);
+        POI_LAUNCH(e, k_long_partial, lgrid, 256, smem, seg, dim4, src, long_list, long_count, chunk_off, partial, partial_w);
+        unsigned fgrid = (unsigned)std::min<int64_t>(table_rows, (int64_t)e->num_sms * 8);
+        POI_LAUNCH(e, k_long_final, fgrid, 128, 0, seg, table, dim4, alpha, lambda, src, long_list, long_count, chunk_off, partial, partial_w);
+        return 0;
+    }
     POI_CK(e, cudaMemsetAsync(long_count, 0, 4, e->stream));
     // one wave of resident CTAs (a grid-stride loop over more CTAs than fit would run its tail at a fraction of the occupancy)
     static int occ[4] = {0, 0, 0, 0};
