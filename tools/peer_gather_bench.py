@@ -59,6 +59,14 @@ def timed(fn):
 
 
 ms_peer = timed(lambda: eng.gather_rows_sharded(ptrs, ids, out))
+# the same rows requested owner by owner (a warp's rows, and a CTA's, then come from ONE peer at a time)
+order = torch.sort(ids.to(torch.int64) % world, stable=True).indices
+ids_grouped = ids[order].contiguous()
+ms_peer_grouped = timed(lambda: eng.gather_rows_sharded(ptrs, ids_grouped, out))
+# ... and with the owners rotated per rank, so that at any moment the ranks read from DIFFERENT peers
+rot = (ids.to(torch.int64) % world - rank) % world
+ids_rot = ids[torch.sort(rot, stable=True).indices].contiguous()
+ms_peer_rot = timed(lambda: eng.gather_rows_sharded(ptrs, ids_rot, out))
 # the same rows, all from the own shard (ids folded into the local range): the HBM-side cost
 ids_local = (ids.to(torch.int64) // world * world + rank).to(torch.int32)
 ms_local = timed(lambda: eng.gather_rows_sharded(ptrs, ids_local, out))
@@ -72,6 +80,7 @@ if rank == 0:
     remote = gb * (world - 1) / world
     print(json.dumps({"world": world, "rows": a.n, "dim": a.dim, "gathered_GB": gb, "remote_GB": remote,
                       "peer_gather_ms": ms_peer, "peer_gather_remote_GBps": remote / (ms_peer * 1e-3),
+                      "peer_gather_owner_grouped_ms": ms_peer_grouped, "peer_gather_owner_rotated_ms": ms_peer_rot,
                       "local_gather_ms": ms_local, "nccl_all_to_all_ms": ms_a2a,
                       "nccl_all_to_all_remote_GBps": per * (world - 1) * a.dim * 4 / 1e9 / (ms_a2a * 1e-3)}))
 dist.barrier()
