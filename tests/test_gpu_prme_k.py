@@ -80,10 +80,11 @@ def test_sequential_k1_is_the_reference_step(engine):
 
 
 @pytest.mark.parametrize("K,d,n,host", [(1, 8, 50, False), (20, 256, 300, False), (20, 256, 300, True), (100, 64, 40, False),
-                                        (100, 256, 64, True), (5, 512, 33, False)])
+                                        (100, 256, 64, True), (5, 512, 33, False), (3, 1024, 20, False)])
 def test_batch_k_matches_oracle(engine, K, d, n, host):
     """One mini-batch step: many duplicate rows inside the batch (small catalogue) -> both the in-place path (rows that
-    occur once) and the segment-sum path (rows that occur several times) are exercised."""
+    occur once) and the segment-sum path (rows that occur several times) are exercised.  d <= 512: the warp-per-check-in
+    scoring kernel (k_prme_score_warp); d = 1024: the CTA-per-check-in kernel (the rows no longer fit a warp's registers)."""
     import torch
     from poi_b200.public.PRME import Prme
     rs = np.random.RandomState(200 + K + d + n)
