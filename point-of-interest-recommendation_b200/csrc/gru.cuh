@@ -264,7 +264,7 @@ __global__ void k_dhl_nohead(const float* __restrict__ ev, const float* __restri
 // ---------------------------------------------------------------------------------------------
 constexpr int LOSS_RK = 8;          // logits per lane kept in registers by k_loss_head (rows up to 256 wide)
 
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 5)
 k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc,
             const float* __restrict__ XDiff, int H4, const int32_t* __restrict__ DPt,
             const int32_t* __restrict__ DQt, const int32_t* __restrict__ lensB,
@@ -284,7 +284,19 @@ k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc
     double a_sur = 0.0, a_bpr = 0.0, a_gwd = 0.0;
     for (int64_t m = warp; m < rows; m += nwarps) {
         const int j = (int)(m / B), b = (int)(m % B);
-        const bool valid = (j + 1) < lensB[b];
+        // every load of the row is issued before anything depends on one of them (length, interval ids, the two dot operands,
+        // the logits): one memory round trip per row instead of the three the branch structure used to serialise
+        const int len_b = lensB[b];
+        const bool in_regs = head && nDp <= 32 * LOSS_RK;
+        int P = 0, Q = 0;
+        if (head) { P = DPt[(int64_t)(j + 1) * B + b]; Q = DQt[(int64_t)(j + 1) * B + b]; }
+        float* row = S + (size_t)m * nDp;
+        float v[LOSS_RK];
+        if (in_regs) {
+#pragma unroll
+            for (int i = 0; i < LOSS_RK; ++i) { const int k = lane + 32 * i; v[i] = k < nD ? row[k] : -INFINITY; }
+        }
+        const bool valid = (j + 1) < len_b;
         const float4* h4 = reinterpret_cast<const float4*>(Hc) + m * H4;
         const float4* x4 = reinterpret_cast<const float4*>(XDiff) + m * H4;
         float dot = 0.f;
@@ -295,21 +307,14 @@ k_loss_head(float* __restrict__ S, int nD, int nDp, const float* __restrict__ Hc
         dot = warp_sum(dot);
         float e_ = 0.f, bpr = 0.f, sur = 0.f, gwd = 0.f;
         if (head) {
-            float* row = S + (size_t)m * nDp;
             if (!valid) {
                 for (int k = lane; k < nDp; k += 32) row[k] = 0.f;
             } else {
-                const int P = DPt[(int64_t)(j + 1) * B + b], Q = DQt[(int64_t)(j + 1) * B + b];
-                if (nDp <= 32 * LOSS_RK) {
+                if (in_regs) {
                     // the whole row lives in registers (<= LOSS_RK values per lane): one read, one exp per logit, one write
-                    float v[LOSS_RK];
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < LOSS_RK; ++i) {
-                        const int k = lane + 32 * i;
-                        v[i] = k < nD ? row[k] : -INFINITY;
-                        mx = fmaxf(mx, v[i]);
-                    }
+                    for (int i = 0; i < LOSS_RK; ++i) mx = fmaxf(mx, v[i]);
                     mx = warp_max(mx);
                     float sum = 0.f, cumr = 0.f, eP = 0.f, eQ = 0.f;
 #pragma unroll
@@ -585,7 +590,9 @@ static int gru_train_core(poi_engine* e, const poi_gru_params* p, const GruIdx& 
         POI_TRY(arena_get(e, TB1 * nDp, &S));
         POI_TRY(gemm_tn(e, Hc, H, p->vs, H, TB, nD, H, EpiBiasStore{S, nDp, p->bs, nD}));
     }
-    int loss_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(TB, 8), (int64_t)e->num_sms * 8));
+    static int loss_occ = 0;            // one wave of resident CTAs (a grid-stride loop over more would run its tail half empty)
+    if (!loss_occ) { int o = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_loss_head, 256, 0); loss_occ = std::max(o, 1); }
+    int loss_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(poi_cdiv(TB, 8), (int64_t)e->num_sms * loss_occ));
     double *part, *out_dev;
     POI_TRY(arena_get(e, (size_t)loss_blocks * 4, &part));
     POI_TRY(arena_get(e, 8, &out_dev));
